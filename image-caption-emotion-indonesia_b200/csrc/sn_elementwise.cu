@@ -1,0 +1,307 @@
+// Memory-bound kernels of the hot path: K1 gather/dropout/pack, K5 log-softmax+NLL(+grad, argmax,
+// top-5), deterministic loss reduction, K7 fused clamp+Adam.  All HBM-bound: coalesced, 16-byte
+// vectorised where the layout allows, grids sized from the SM count.
+#include "sn_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// K1
+// ------------------------------------------------------------------------------------------
+__global__ void gather_pack_fwd_kernel(const int64_t* __restrict__ captions, int64_t cap_ld,
+                                       const float* __restrict__ table, int E,
+                                       const float* __restrict__ features, int64_t feat_ld, int has_feat,
+                                       const int32_t* __restrict__ row_b, const int32_t* __restrict__ row_t,
+                                       const int32_t* __restrict__ tok_override, int64_t N,
+                                       float* __restrict__ X, int64_t ldx, float p, float inv_keep,
+                                       uint64_t seed) {
+  // one warp per packed row
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  int lane = threadIdx.x & 31;
+  int b = row_b[row], t = row_t[row];
+  int ov = tok_override ? tok_override[row] : -1;
+  float* dst = X + row * ldx;
+  if (ov < 0 && has_feat && t == 0) {
+    const float* src = features + (int64_t)b * feat_ld;
+    for (int c = lane; c < E; c += 32) dst[c] = src[c];
+    return;
+  }
+  int64_t tok = ov >= 0 ? (int64_t)ov : captions[(int64_t)b * cap_ld + (t - has_feat)];
+  const float* src = table + tok * E;
+  float pp = ov >= 0 ? 0.f : p;   // fed-back embeddings are not dropped out (model.py:184)
+  for (int c = lane; c < E; c += 32)
+    dst[c] = src[c] * sn::dropout_scale(seed, (uint32_t)row, (uint32_t)c, pp, inv_keep);
+}
+
+__global__ void gather_pack_bwd_kernel(const int64_t* __restrict__ captions, int64_t cap_ld,
+                                       float* __restrict__ dtable, int E, float* __restrict__ dfeatures,
+                                       int64_t feat_ld, int has_feat, const int32_t* __restrict__ row_b,
+                                       const int32_t* __restrict__ row_t,
+                                       const int32_t* __restrict__ tok_override, int64_t N,
+                                       const float* __restrict__ dX, int64_t ldx, float p, float inv_keep,
+                                       uint64_t seed) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  int lane = threadIdx.x & 31;
+  int b = row_b[row], t = row_t[row];
+  int ov = tok_override ? tok_override[row] : -1;
+  const float* src = dX + row * ldx;
+  if (ov < 0 && has_feat && t == 0) {
+    if (dfeatures) {
+      float* dst = dfeatures + (int64_t)b * feat_ld;
+      for (int c = lane; c < E; c += 32) dst[c] = src[c];
+    }
+    return;
+  }
+  int64_t tok = ov >= 0 ? (int64_t)ov : captions[(int64_t)b * cap_ld + (t - has_feat)];
+  float* dst = dtable + tok * E;
+  float pp = ov >= 0 ? 0.f : p;
+  for (int c = lane; c < E; c += 32) {
+    float s = sn::dropout_scale(seed, (uint32_t)row, (uint32_t)c, pp, inv_keep);
+    if (s != 0.f) atomicAdd(dst + c, src[c] * s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: one CTA per row; the row (V floats) is staged in shared memory so HBM sees one read of the
+// logits and (optionally) one write of the gradient.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_nll_kernel(const float* __restrict__ logits, int64_t V, int64_t ld,
+                                                          const int64_t* __restrict__ targets,
+                                                          float* __restrict__ row_loss, float* dlogits, int64_t ldd,
+                                                          float grad_scale, int64_t* __restrict__ argmax,
+                                                          int32_t* __restrict__ top5hit, int use_smem) {
+  extern __shared__ float srow[];
+  __shared__ float red_v[8];
+  __shared__ int red_i[8];
+  __shared__ float bc_f[2];
+  __shared__ int bc_i;
+  const int64_t row = blockIdx.x;
+  const float* src = logits + row * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // pass 1: max + first arg-max
+  float mx = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int64_t c = tid; c < V; c += 256) {
+    float v = src[c];
+    if (use_smem) srow[c] = v;
+    if (v > mx) { mx = v; mi = (int)c; }   // strictly greater keeps the lowest index per thread
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+    int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
+  }
+  if (lane == 0) { red_v[warp] = mx; red_i[warp] = mi; }
+  __syncthreads();
+  if (tid == 0) {
+    float bm = red_v[0]; int bi = red_i[0];
+    for (int w = 1; w < 8; ++w)
+      if (red_v[w] > bm || (red_v[w] == bm && red_i[w] < bi)) { bm = red_v[w]; bi = red_i[w]; }
+    bc_f[0] = bm; bc_i = bi;
+  }
+  __syncthreads();
+  mx = bc_f[0];
+  if (tid == 0 && argmax) argmax[row] = bc_i;
+  if (!targets) return;
+
+  const float* rd = use_smem ? srow : src;
+  const int64_t tgt = targets[row];
+  const float tv = rd[tgt];
+  // pass 2: sum exp, count of logits strictly above the target's
+  float se = 0.f;
+  int above = 0;
+  for (int64_t c = tid; c < V; c += 256) {
+    float v = rd[c];
+    se += expf(v - mx);
+    above += (v > tv);
+  }
+  se = sn::warp_sum(se);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+  __syncthreads();
+  if (lane == 0) { red_v[warp] = se; red_i[warp] = above; }
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f; int a = 0;
+    for (int w = 0; w < 8; ++w) { s += red_v[w]; a += red_i[w]; }
+    float lse = mx + logf(s);
+    bc_f[1] = lse;
+    if (row_loss) row_loss[row] = lse - tv;
+    if (top5hit) top5hit[row] = a < 5 ? 1 : 0;
+  }
+  __syncthreads();
+  if (dlogits) {
+    const float lse = bc_f[1];
+    float* dst = dlogits + row * ldd;
+    for (int64_t c = tid; c < V; c += 256) {
+      float pr = expf(rd[c] - lse);
+      dst[c] = (pr - (c == tgt ? 1.f : 0.f)) * grad_scale;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ x, int64_t N, float scale,
+                                                           float* out, int accumulate) {
+  __shared__ double part[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += 1024) s += (double)x[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += part[w];
+    float r = (float)(t * (double)scale);
+    *out = accumulate ? *out + r : r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: clamp + Adam, torch.optim.Adam op order (see sn100.h)
+// ------------------------------------------------------------------------------------------
+struct AdamRanges {
+  static constexpr int MAX = 48;
+  int64_t off[MAX], len[MAX];
+  float step_size[MAX], bc2_sqrt[MAX];
+  int64_t chunk_start[MAX + 1];   // prefix of per-range chunk counts
+  int n;
+};
+constexpr int ADAM_CHUNK = 4096;   // elements per CTA-iteration
+
+__global__ void __launch_bounds__(256) adam_clamp_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                         float* __restrict__ m, float* __restrict__ v,
+                                                         AdamRanges R, float beta1, float beta2, float eps,
+                                                         float clip) {
+  const int64_t total_chunks = R.chunk_start[R.n];
+  for (int64_t ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
+    int r = 0;
+    while (ch >= R.chunk_start[r + 1]) ++r;
+    const int64_t base = R.off[r] + (ch - R.chunk_start[r]) * ADAM_CHUNK;
+    const int64_t end = R.off[r] + R.len[r];
+    const float ss = R.step_size[r], bc = R.bc2_sqrt[r];
+#pragma unroll 4
+    for (int64_t i = base + threadIdx.x; i < base + ADAM_CHUNK && i < end; i += 256) {
+      float gi = g[i];
+      if (clip > 0.f) { gi = fminf(fmaxf(gi, -clip), clip); g[i] = gi; }   // clamp_ is in place (utils.py:60)
+      float mi = m[i], vi = v[i];
+      mi = mi + (1.f - beta1) * (gi - mi);
+      vi = vi * beta2 + (1.f - beta2) * gi * gi;
+      float denom = sqrtf(vi) / bc + eps;
+      p[i] = p[i] - ss * (mi / denom);
+      m[i] = mi; v[i] = vi;
+    }
+  }
+}
+
+__global__ void mean_pixels_kernel(const float* __restrict__ feat, int64_t P, int64_t D, float* __restrict__ out) {
+  int64_t b = blockIdx.y;
+  int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const float* src = feat + b * P * D + d;
+  float s = 0.f;
+  for (int64_t pz = 0; pz < P; ++pz) s += src[pz * D];
+  out[b * D + d] = s / (float)P;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t sn_gather_pack_fwd(const int64_t* captions, int64_t cap_ld, const float* table, int64_t E,
+                           const float* features, int64_t feat_ld, int32_t has_feat,
+                           const int32_t* row_b, const int32_t* row_t, const int32_t* tok_override,
+                           int64_t N, float* X, int64_t ldx, float p_drop, uint64_t seed, void* stream) {
+  SN_REQUIRE(N >= 0 && E > 0 && ldx >= E, "sn_gather_pack_fwd: bad dims N=%lld E=%lld ldx=%lld", (long long)N, (long long)E, (long long)ldx);
+  SN_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "sn_gather_pack_fwd: dropout p=%f out of [0,1)", p_drop);
+  SN_REQUIRE(!has_feat || features, "sn_gather_pack_fwd: has_feat without features");
+  if (N == 0) return 0;
+  float inv_keep = 1.f / (1.f - p_drop);
+  unsigned grid = (unsigned)((N + 7) / 8);
+  gather_pack_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(captions, cap_ld, table, (int)E, features, feat_ld,
+                                                                 has_feat, row_b, row_t, tok_override, N, X, ldx,
+                                                                 p_drop, inv_keep, seed);
+  return sn::check_launch("sn_gather_pack_fwd");
+}
+
+int32_t sn_gather_pack_bwd(const int64_t* captions, int64_t cap_ld, float* dtable, int64_t E,
+                           float* dfeatures, int64_t feat_ld, int32_t has_feat, const int32_t* row_b,
+                           const int32_t* row_t, const int32_t* tok_override, int64_t N,
+                           const float* dX, int64_t ldx, float p_drop, uint64_t seed, void* stream) {
+  SN_REQUIRE(N >= 0 && E > 0 && ldx >= E, "sn_gather_pack_bwd: bad dims");
+  SN_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "sn_gather_pack_bwd: dropout p=%f out of [0,1)", p_drop);
+  if (N == 0) return 0;
+  float inv_keep = 1.f / (1.f - p_drop);
+  unsigned grid = (unsigned)((N + 7) / 8);
+  gather_pack_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(captions, cap_ld, dtable, (int)E, dfeatures, feat_ld,
+                                                                 has_feat, row_b, row_t, tok_override, N, dX, ldx,
+                                                                 p_drop, inv_keep, seed);
+  return sn::check_launch("sn_gather_pack_bwd");
+}
+
+int32_t sn_softmax_nll(const float* logits, int64_t N, int64_t V, int64_t ld, const int64_t* targets,
+                       float* row_loss, float* dlogits, int64_t ldd, float grad_scale, int64_t* argmax,
+                       int32_t* top5hit, void* stream) {
+  SN_REQUIRE(N >= 0 && V > 0 && ld >= V, "sn_softmax_nll: bad dims");
+  if (N == 0) return 0;
+  size_t smem = (size_t)V * sizeof(float);
+  int use_smem = smem <= 200 * 1024;
+  if (use_smem && smem > 48 * 1024) {
+    static thread_local size_t configured = 0;
+    if (configured < smem) {
+      SN_CUDA(cudaFuncSetAttribute(softmax_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = 200 * 1024;
+    }
+  }
+  softmax_nll_kernel<<<(unsigned)N, 256, use_smem ? smem : 0, (cudaStream_t)stream>>>(
+      logits, V, ld, targets, row_loss, dlogits, ldd, grad_scale, argmax, top5hit, use_smem);
+  return sn::check_launch("sn_softmax_nll");
+}
+
+int32_t sn_reduce_sum(const float* x, int64_t N, float scale, float* out, int32_t accumulate, void* stream) {
+  SN_REQUIRE(N >= 0 && out, "sn_reduce_sum: bad args");
+  reduce_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, N, scale, out, accumulate);
+  return sn::check_launch("sn_reduce_sum");
+}
+
+int32_t sn_adam_clamp(float* p, float* g, float* m, float* v, int32_t n_ranges, const int64_t* ranges,
+                      const float* step_size, const float* bc2_sqrt, float beta1, float beta2, float eps,
+                      float clip, void* stream) {
+  SN_REQUIRE(n_ranges >= 0, "sn_adam_clamp: n_ranges < 0");
+  int done = 0;
+  while (done < n_ranges) {
+    AdamRanges R;
+    R.n = 0;
+    R.chunk_start[0] = 0;
+    while (done < n_ranges && R.n < AdamRanges::MAX) {
+      int64_t off = ranges[2 * done], len = ranges[2 * done + 1];
+      SN_REQUIRE(off >= 0 && len >= 0, "sn_adam_clamp: bad range %d", done);
+      R.off[R.n] = off; R.len[R.n] = len;
+      R.step_size[R.n] = step_size[done]; R.bc2_sqrt[R.n] = bc2_sqrt[done];
+      R.chunk_start[R.n + 1] = R.chunk_start[R.n] + (len + ADAM_CHUNK - 1) / ADAM_CHUNK;
+      ++R.n; ++done;
+    }
+    int64_t chunks = R.chunk_start[R.n];
+    if (chunks == 0) continue;
+    int64_t cap = (int64_t)sn::dev_info().sm_count * 8;
+    unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
+    adam_clamp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, R, beta1, beta2, eps, clip);
+    int32_t rc = sn::check_launch("sn_adam_clamp");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int32_t sn_mean_pixels(const float* feat, int64_t B, int64_t P, int64_t D, float* out, void* stream) {
+  SN_REQUIRE(B >= 0 && P > 0 && D > 0, "sn_mean_pixels: bad dims");
+  if (B == 0) return 0;
+  dim3 grid((unsigned)((D + 255) / 256), (unsigned)B);
+  mean_pixels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feat, P, D, out);
+  return sn::check_launch("sn_mean_pixels");
+}
+
+}  // extern "C"

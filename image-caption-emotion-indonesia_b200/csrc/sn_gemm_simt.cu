@@ -1,0 +1,165 @@
+// fp32 FFMA GEMM (SN_PREC_F32): the exact-fp32 arithmetic path and the validation reference for the
+// tcgen05 GEMMs.  128x128x8 tiles, 256 threads, 8x8 register micro-tiles, generic operand strides so
+// that NT / NN / TN all run without materialised transposes.
+#include "sn_common.cuh"
+
+namespace {
+
+struct GemmArgs {
+  int64_t M, N, K;
+  const float* A; int64_t sam, sak;   // A(m,k) = A[m*sam + k*sak]
+  const float* B; int64_t sbk, sbn;   // B(k,n) = B[k*sbk + n*sbn]
+  float* C; int64_t ldc;
+  const float* bias; float beta;
+  int64_t strideA, strideB, strideC, strideBias;
+};
+
+constexpr int BM = 128, BN = 128, BK = 8;
+
+// load a [ROWS(major) x BK] operand tile into smem as S[k][major]
+__device__ __forceinline__ void load_tile(float (*S)[BM + 4], const float* __restrict__ P, int64_t s_major,
+                                          int64_t s_k, int64_t major0, int64_t k0, int64_t major_lim,
+                                          int64_t k_lim, int tid) {
+  if (s_k == 1) {
+    // k contiguous: thread -> (major = tid/2, 4 consecutive k)
+    int mj = tid >> 1, kk = (tid & 1) * 4;
+    int64_t gm = major0 + mj, gk = k0 + kk;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gm < major_lim) {
+      const float* src = P + gm * s_major + gk;
+      if (gk + 3 < k_lim && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        float4 t = *reinterpret_cast<const float4*>(src);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (gk + j < k_lim) v[j] = src[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S[kk + j][mj] = v[j];
+  } else {
+    // major contiguous (s_major == 1): thread -> (k = tid/32, 4 consecutive major)
+    int kk = tid >> 5, mj = (tid & 31) * 4;
+    int64_t gm = major0 + mj, gk = k0 + kk;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gk < k_lim) {
+      const float* src = P + gk * s_k + gm * s_major;
+      if (s_major == 1 && gm + 3 < major_lim && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        float4 t = *reinterpret_cast<const float4*>(src);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (gm + j < major_lim) v[j] = src[j * s_major];
+      }
+    }
+    *reinterpret_cast<float4*>(&S[kk][mj]) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const float* A = g.A + blockIdx.z * g.strideA;
+  const float* B = g.B + blockIdx.z * g.strideB;
+  float* C = g.C + blockIdx.z * g.strideC;
+  const float* bias = g.bias ? g.bias + blockIdx.z * g.strideBias : nullptr;
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int64_t k0 = 0; k0 < g.K; k0 += BK) {
+    load_tile(As, A, g.sam, g.sak, m0, k0, g.M, g.K, tid);
+    load_tile(Bs, B, g.sbn, g.sbk, n0, k0, g.N, g.K, tid);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      int64_t n = n0 + jh * 64 + tx * 4;
+      float* dst = C + m * g.ldc + n;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (n + j < g.N) {
+          float v = acc[i][jh * 4 + j];
+          if (bias) v += bias[n + j];
+          if (g.beta != 0.f) v += g.beta * dst[j];
+          dst[j] = v;
+        }
+      }
+    }
+  }
+}
+
+__global__ void colsum_kernel(const float* __restrict__ X, int64_t M, int64_t N, int64_t ldx,
+                              float* __restrict__ out, float beta) {
+  // block = 32 columns x 8 row-lanes; rows strided by 8*gridDim.y ... one block owns its columns fully
+  __shared__ float part[8][33];
+  int col = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (col < N)
+    for (int64_t m = threadIdx.y; m < M; m += 8) s += X[m * ldx + col];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += part[j][threadIdx.x];
+    out[col] = t + (beta != 0.f ? beta * out[col] : 0.f);
+  }
+}
+
+}  // namespace
+
+extern "C" int32_t sn_gemm(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                           const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias,
+                           float beta, int32_t batch, int64_t strideA, int64_t strideB,
+                           int64_t strideC, int64_t strideBias, void* stream) {
+  SN_REQUIRE(op >= 0 && op <= 2, "sn_gemm: bad op %d", op);
+  SN_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 1, "sn_gemm: bad dims M=%lld N=%lld K=%lld batch=%d",
+             (long long)M, (long long)N, (long long)K, batch);
+  if (M == 0 || N == 0) return 0;
+  SN_REQUIRE(A && B && C, "sn_gemm: null operand");
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.B = B; g.C = C; g.ldc = ldc; g.bias = bias; g.beta = beta;
+  g.strideA = strideA; g.strideB = strideB; g.strideC = strideC; g.strideBias = strideBias;
+  if (op == SN_OP_NT) { g.sam = lda; g.sak = 1; g.sbk = 1; g.sbn = ldb; }
+  else if (op == SN_OP_NN) { g.sam = lda; g.sak = 1; g.sbk = ldb; g.sbn = 1; }
+  else { g.sam = 1; g.sak = lda; g.sbk = ldb; g.sbn = 1; }
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch);
+  gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g);
+  return sn::check_launch("sn_gemm");
+}
+
+extern "C" int32_t sn_colsum(const float* X, int64_t M, int64_t N, int64_t ldx, float* out, float beta,
+                             void* stream) {
+  SN_REQUIRE(M >= 0 && N >= 0, "sn_colsum: bad dims");
+  if (N == 0) return 0;
+  dim3 grid((unsigned)((N + 31) / 32)), block(32, 8);
+  colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(X, M, N, ldx, out, beta);
+  return sn::check_launch("sn_colsum");
+}

@@ -1,0 +1,409 @@
+// K3: persistent recurrence kernels (fp32 exact path).
+//
+// One cooperative launch runs all T steps of   z_t = XP_t + h_{t-1} Whh^T ; gates ; c_t ; h_t .
+// The grid is (H/8 unit blocks) x (nbb batch blocks) <= #SMs, one CTA per SM:
+//   * CTA (ub, bb) owns hidden units [8ub, 8ub+8) (all four gate rows of them -> gate fusion is
+//     lane-local) for the samples of batch block bb, for ALL time steps;
+//   * its 32 rows of Whh stay resident in shared memory for the whole launch (read from HBM once);
+//   * h_t is exchanged between the CTAs of one batch block through Hall (L2) with one release/acquire
+//     counter per (batch block, step): no grid-wide barrier, CTAs of different batch blocks never wait
+//     on each other;
+//   * inside a warp: 8 unit lanes x 4 k lanes, SW samples per warp -> 4*SW accumulators per lane,
+//     k-partials combined with two warp shuffles, then the gate nonlinearities run in registers.
+// The backward kernel is the mirror image in reverse time with the column slice Whh[:, units] resident
+// (K = 4H), producing dZ (= dXP) and carrying dc in place.
+#include "sn_common.cuh"
+
+namespace {
+
+constexpr int UB = 8;          // hidden units per CTA
+constexpr int NW = 8;          // warps per CTA
+constexpr int NT = NW * 32;
+
+struct RecurArgs {
+  int cell, H, B, t0, t1, T;
+  const int* bs;
+  const int* off;
+  const float* XP;
+  const float* W;
+  const float* h_init;
+  const float* c_init;
+  const float* bhh;
+  float* Hall;
+  float* Call;
+  float* Hprev;
+  float* gates;
+  float* c_state;
+  const float* dHall;
+  float* dZ;
+  float* dh_carry;
+  float* dc_carry;
+  int* flags;
+  int n_ub, nbb, BB;
+};
+
+__device__ __forceinline__ void wait_flag(const int* flag, int target) {
+  if (threadIdx.x == 0) {
+    while (sn::ld_acquire(flag) < target) { __nanosleep(20); }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void signal_flag(int* flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    sn::red_release_add(flag, 1);
+  }
+}
+
+// acc[j][s] += sum_k Ws[(j*8+rl)][k] * INs[(sw0+s)][k] over this lane's k subset of [0,KC)
+template <int RPL, int SW>
+__device__ __forceinline__ void matvec_accum(const float* __restrict__ Ws, int ldw, int wk0,
+                                             const float* __restrict__ INs, int ldi, int KC, int rl, int kl,
+                                             int sw0, float (&acc)[RPL][SW]) {
+  for (int k = kl * 4; k < KC; k += 16) {
+    float4 w[RPL];
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) w[j] = *reinterpret_cast<const float4*>(Ws + (j * UB + rl) * ldw + wk0 + k);
+#pragma unroll
+    for (int s = 0; s < SW; ++s) {
+      float4 x = *reinterpret_cast<const float4*>(INs + (sw0 + s) * ldi + k);
+#pragma unroll
+      for (int j = 0; j < RPL; ++j) {
+        float a = acc[j][s];
+        a = fmaf(w[j].x, x.x, a);
+        a = fmaf(w[j].y, x.y, a);
+        a = fmaf(w[j].z, x.z, a);
+        a = fmaf(w[j].w, x.w, a);
+        acc[j][s] = a;
+      }
+    }
+  }
+}
+
+// stage rows [r0, r0+G) x cols [k0, k0+KC) of a [*, ld] global matrix into smem (zeros past nrows)
+__device__ __forceinline__ void stage_rows(float* __restrict__ INs, int ldi, const float* __restrict__ src,
+                                           int64_t ld, int nrows, int G, int k0, int KC, bool coherent_l2) {
+  const int vec_per_row = KC >> 2;
+  for (int i = threadIdx.x; i < G * vec_per_row; i += NT) {
+    int r = i / vec_per_row, c = (i - r * vec_per_row) << 2;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nrows && src) {
+      const float4* p = reinterpret_cast<const float4*>(src + (int64_t)r * ld + k0 + c);
+      v = coherent_l2 ? __ldcg(p) : __ldg(p);
+    }
+    *reinterpret_cast<float4*>(INs + r * ldi + c) = v;
+  }
+}
+
+template <int SW>
+__global__ void __launch_bounds__(NT, 1) recur_fwd_kernel(RecurArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = a.H, ldw = H + 4;
+  constexpr int G = NW * SW;
+  float* Ws = smem;                  // [32][ldw]
+  float* INs = smem + 32 * ldw;      // [G][ldw]
+  const int ub = blockIdx.x % a.n_ub, bb = blockIdx.x / a.n_ub;
+  const int u0 = ub * UB, sb0 = bb * a.BB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rl = lane & 7, kl = lane >> 3;
+  const int pos_o = a.cell == SN_CELL_LSTM ? 3 : 2, pos_c = a.cell == SN_CELL_LSTM ? 2 : 3;
+
+  // resident weight slice: row (j*8+u) <- Whh[j*H + u0 + u, :]
+  for (int i = tid; i < 32 * (H >> 2); i += NT) {
+    int r = i / (H >> 2), c = (i - r * (H >> 2)) << 2;
+    int j = r >> 3, u = r & 7;
+    *reinterpret_cast<float4*>(Ws + r * ldw + c) =
+        __ldg(reinterpret_cast<const float4*>(a.W + (int64_t)(j * H + u0 + u) * H + c));
+  }
+  __syncthreads();
+
+  for (int t = a.t0; t < a.t1; ++t) {
+    const int bt = a.bs[t];
+    const int nv = min(max(bt - sb0, 0), a.BB);
+    int* flag_t = a.flags + bb * a.T + t;
+    if (nv > 0) {
+      const float* hsrc;
+      int64_t row_prev0 = 0;
+      bool coherent = false;
+      if (t == a.t0) {
+        hsrc = a.h_init ? a.h_init + (int64_t)sb0 * H : nullptr;
+      } else {
+        row_prev0 = (int64_t)a.off[t - 1] + sb0;
+        hsrc = a.Hall + row_prev0 * H;
+        coherent = true;
+        wait_flag(a.flags + bb * a.T + (t - 1), a.n_ub);
+      }
+      const int64_t row0 = (int64_t)a.off[t] + sb0;
+      for (int g0 = 0; g0 < nv; g0 += G) {
+        const int ng = min(G, nv - g0);
+        stage_rows(INs, ldw, hsrc ? hsrc + (int64_t)g0 * H : nullptr, H, ng, G, 0, H, coherent);
+        __syncthreads();
+        if (a.Hprev) {
+          for (int i = tid; i < ng * UB; i += NT) {
+            int s = i >> 3, u = i & 7;
+            a.Hprev[(row0 + g0 + s) * H + u0 + u] = INs[s * ldw + u0 + u];
+          }
+        }
+        float acc[4][SW];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int s = 0; s < SW; ++s) acc[j][s] = 0.f;
+        const int sw0 = warp * SW;
+        if (sw0 < ng) matvec_accum<4, SW>(Ws, ldw, 0, INs, ldw, H, rl, kl, sw0, acc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int s = 0; s < SW; ++s) {
+            float v = acc[j][s];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            acc[j][s] = v;
+          }
+#pragma unroll
+        for (int s = 0; s < SW; ++s) {
+          if ((s & 3) == kl && sw0 + s < ng) {
+            const int sl = g0 + sw0 + s;             // sample index inside the batch block
+            const int64_t row = row0 + sl;
+            const int u = u0 + rl;
+            const float* xp = a.XP + row * 4 * H + u;
+            float zi = acc[0][s] + xp[0];
+            float zf = acc[1][s] + xp[H];
+            float z2 = acc[2][s] + xp[2 * H];
+            float z3 = acc[3][s] + xp[3 * H];
+            if (a.bhh) {
+              zi += a.bhh[u]; zf += a.bhh[H + u]; z2 += a.bhh[2 * H + u]; z3 += a.bhh[3 * H + u];
+            }
+            float zo = a.cell == SN_CELL_LSTM ? z3 : z2;
+            float zc = a.cell == SN_CELL_LSTM ? z2 : z3;
+            float gi = sn::sigmoidf_(zi), gf = sn::sigmoidf_(zf), go = sn::sigmoidf_(zo), gc = tanhf(zc);
+            float* cst = a.c_state + (int64_t)(sb0 + sl) * H + u;
+            float c = gf * (*cst) + gi * gc;
+            float h = a.cell == SN_CELL_LSTM ? go * tanhf(c) : go * c;
+            *cst = c;
+            a.Hall[row * H + u] = h;
+            if (a.Call) a.Call[row * H + u] = c;
+            if (a.gates) {
+              float* gp = a.gates + row * 4 * H + u;
+              gp[0] = gi; gp[H] = gf; gp[pos_o * H] = go; gp[pos_c * H] = gc;
+            }
+          }
+        }
+        __syncthreads();   // INs reused by the next group / step
+      }
+    }
+    signal_flag(flag_t);
+  }
+}
+
+template <int SW>
+__global__ void __launch_bounds__(NT, 1) recur_bwd_kernel(RecurArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = a.H, K = 4 * H, ldw = K + 4;
+  constexpr int G = NW * SW;
+  const int KC = H;                  // K chunk staged per pass
+  const int ldi = KC + 4;
+  float* Ws = smem;                  // [8][ldw]   Ws[u][k] = Whh[k, u0+u]
+  float* INs = smem + UB * ldw;      // [G][ldi]
+  const int ub = blockIdx.x % a.n_ub, bb = blockIdx.x / a.n_ub;
+  const int u0 = ub * UB, sb0 = bb * a.BB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rl = lane & 7, kl = lane >> 3;
+  const int pos_o = a.cell == SN_CELL_LSTM ? 3 : 2, pos_c = a.cell == SN_CELL_LSTM ? 2 : 3;
+
+  for (int i = tid; i < K * UB; i += NT) {
+    int k = i >> 3, u = i & 7;
+    Ws[u * ldw + k] = __ldg(a.W + (int64_t)k * H + u0 + u);
+  }
+  __syncthreads();
+
+  // t runs t1-1 .. t0, plus one extra pass (t == t0-1) that only produces dh_carry = dZ_{t0} Whh
+  for (int t = a.t1 - 1; t >= a.t0 - 1; --t) {
+    const bool tail = (t < a.t0);
+    const int bt = tail ? a.bs[a.t0] : a.bs[t];
+    const int nv = min(max(bt - sb0, 0), a.BB);
+    // samples that receive a recurrent gradient from step t+1
+    const int bnext = (t + 1 < a.t1) ? a.bs[t + 1] : 0;
+    const int nrec = min(max(bnext - sb0, 0), a.BB);
+    if (tail) {
+      // samples beyond b_{t0} get zero carry
+      for (int i = tid; i < a.BB * UB; i += NT) {
+        int s = i >> 3, u = i & 7;
+        if (s >= nrec && sb0 + s < a.B) a.dh_carry[(int64_t)(sb0 + s) * H + u0 + u] = 0.f;
+      }
+    }
+    if (nv > 0) {
+      if (nrec > 0) wait_flag(a.flags + bb * a.T + (t + 1), a.n_ub);
+      const int64_t row0 = tail ? 0 : (int64_t)a.off[t] + sb0;
+      const int64_t rown0 = (t + 1 < a.t1) ? (int64_t)a.off[t + 1] + sb0 : 0;
+      for (int g0 = 0; g0 < nv; g0 += G) {
+        const int ng = min(G, nv - g0);
+        const int ngrec = min(max(nrec - g0, 0), G);
+        float acc[1][SW];
+#pragma unroll
+        for (int s = 0; s < SW; ++s) acc[0][s] = 0.f;
+        const int sw0 = warp * SW;
+        if (ngrec > 0) {
+          for (int k0 = 0; k0 < K; k0 += KC) {
+            stage_rows(INs, ldi, a.dZ + (rown0 + g0) * K, K, ngrec, G, k0, KC, true);
+            __syncthreads();
+            if (sw0 < ngrec) matvec_accum<1, SW>(Ws, ldw, k0, INs, ldi, KC, rl, kl, sw0, acc);
+            __syncthreads();
+          }
+#pragma unroll
+          for (int s = 0; s < SW; ++s) {
+            float v = acc[0][s];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            acc[0][s] = v;
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < SW; ++s) {
+          if ((s & 3) == kl && sw0 + s < ng) {
+            const int sl = g0 + sw0 + s;
+            const int u = u0 + rl;
+            const int64_t sidx = (int64_t)(sb0 + sl) * H + u;
+            float dh_rec = (sl < nrec) ? acc[0][s] : 0.f;
+            if (tail) {
+              if (sl < nrec) a.dh_carry[sidx] = dh_rec;
+              continue;
+            }
+            if (t == a.t1 - 1) dh_rec = a.dh_carry[sidx];
+            const int64_t row = row0 + sl;
+            const float* gp = a.gates + row * K + u;
+            const float gi = gp[0], gf = gp[H], go = gp[pos_o * H], gc = gp[pos_c * H];
+            const float c = a.Call[row * H + u];
+            float cprev;
+            if (t > 0) cprev = a.Call[((int64_t)a.off[t - 1] + sb0 + sl) * H + u];
+            else cprev = a.c_init ? a.c_init[sidx] : 0.f;
+            const float dh = a.dHall[row * H + u] + dh_rec;
+            float dcar = a.dc_carry[sidx];
+            float d_o, dc;
+            if (a.cell == SN_CELL_LSTM) {
+              float tc = tanhf(c);
+              d_o = dh * tc;
+              dc = dcar + dh * go * (1.f - tc * tc);
+            } else {
+              d_o = dh * c;
+              dc = dcar + dh * go;
+            }
+            const float di = dc * gc, df = dc * cprev, dg = dc * gi;
+            a.dc_carry[sidx] = dc * gf;
+            float* dz = a.dZ + row * K + u;
+            dz[0] = di * gi * (1.f - gi);
+            dz[H] = df * gf * (1.f - gf);
+            dz[pos_o * H] = d_o * go * (1.f - go);
+            dz[pos_c * H] = dg * (1.f - gc * gc);
+          }
+        }
+      }
+    }
+    if (!tail) signal_flag(a.flags + bb * a.T + t);
+  }
+}
+
+struct Plan {
+  int n_ub, nbb, BB, SW;
+  size_t smem;
+};
+
+int32_t make_plan(bool bwd, int64_t H, int64_t B, Plan* p) {
+  const sn::DevInfo& d = sn::dev_info();
+  if (H % 16 != 0 || H < 16) return sn::fail(-1, "sn_recur: hidden size %lld must be a multiple of 16", (long long)H);
+  p->n_ub = (int)(H / UB);
+  if (p->n_ub > d.sm_count) return sn::fail(-1, "sn_recur: hidden size %lld needs %d CTAs > %d SMs", (long long)H, p->n_ub, d.sm_count);
+  int nbb = d.sm_count / p->n_ub;
+  int max_nbb = (int)((B + 7) / 8);
+  if (nbb > max_nbb) nbb = max_nbb;
+  if (nbb < 1) nbb = 1;
+  p->nbb = nbb;
+  p->BB = (int)((B + nbb - 1) / nbb);
+  const int cands[3] = {6, 4, 2};
+  int best = 0;
+  for (int i = 0; i < 3; ++i) {
+    int sw = cands[i];
+    size_t smem = bwd ? ((size_t)UB * (4 * H + 4) + (size_t)NW * sw * (H + 4)) * 4
+                      : ((size_t)32 * (H + 4) + (size_t)NW * sw * (H + 4)) * 4;
+    if (smem > (size_t)d.smem_optin) continue;
+    // smallest SW whose group covers the batch block, else the largest that fits
+    if (best == 0) { best = sw; p->smem = smem; }
+    if (NW * sw >= p->BB) { best = sw; p->smem = smem; }
+  }
+  if (best == 0) return sn::fail(-1, "sn_recur: hidden size %lld does not fit shared memory", (long long)H);
+  p->SW = best;
+  return 0;
+}
+
+template <typename K>
+int32_t launch_coop(K kernel, const Plan& p, RecurArgs& a, cudaStream_t stream, const char* what) {
+  SN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  void* params[] = {&a};
+  dim3 grid((unsigned)(p.n_ub * p.nbb)), block(NT);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kernel, grid, block, params, p.smem, stream);
+  if (e != cudaSuccess) return sn::fail((int32_t)e, "%s: cooperative launch failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t sn_recur_ws_bytes(int64_t B, int64_t T) {
+  (void)B;
+  return (int64_t)sizeof(int) * 160 * (T + 1);
+}
+
+int32_t sn_recur_fwd(int32_t cell, int64_t H, int64_t B, const int32_t* batch_sizes, const int32_t* offsets,
+                     int32_t t0, int32_t t1, const float* XP, const float* Whh, const float* h_init,
+                     const float* bhh, float* Hall, float* Call, float* Hprev, float* gates, float* c_state,
+                     void* ws, void* stream) {
+  SN_REQUIRE(cell == SN_CELL_FACTORED || cell == SN_CELL_LSTM, "sn_recur_fwd: bad cell %d", cell);
+  SN_REQUIRE(t0 >= 0 && t1 >= t0 && B > 0, "sn_recur_fwd: bad step range [%d,%d) or B", t0, t1);
+  SN_REQUIRE(XP && Whh && Hall && c_state && ws && batch_sizes && offsets, "sn_recur_fwd: null argument");
+  if (t1 == t0) return 0;
+  Plan p;
+  int32_t rc = make_plan(false, H, B, &p);
+  if (rc) return rc;
+  RecurArgs a = {};
+  a.cell = cell; a.H = (int)H; a.B = (int)B; a.t0 = t0; a.t1 = t1; a.T = t1;
+  a.bs = batch_sizes; a.off = offsets; a.XP = XP; a.W = Whh; a.h_init = h_init; a.bhh = bhh;
+  a.Hall = Hall; a.Call = Call; a.Hprev = Hprev; a.gates = gates; a.c_state = c_state;
+  a.flags = (int*)ws; a.n_ub = p.n_ub; a.nbb = p.nbb; a.BB = p.BB;
+  cudaStream_t st = (cudaStream_t)stream;
+  SN_CUDA(cudaMemsetAsync(ws, 0, sizeof(int) * (size_t)p.nbb * (size_t)t1, st));
+  switch (p.SW) {
+    case 6: return launch_coop(recur_fwd_kernel<6>, p, a, st, "sn_recur_fwd");
+    case 4: return launch_coop(recur_fwd_kernel<4>, p, a, st, "sn_recur_fwd");
+    default: return launch_coop(recur_fwd_kernel<2>, p, a, st, "sn_recur_fwd");
+  }
+}
+
+int32_t sn_recur_bwd(int32_t cell, int64_t H, int64_t B, const int32_t* batch_sizes, const int32_t* offsets,
+                     int32_t t0, int32_t t1, const float* Whh, const float* c_init, const float* Call,
+                     const float* gates, const float* dHall, float* dZ, float* dh_carry, float* dc_carry,
+                     void* ws, void* stream) {
+  SN_REQUIRE(cell == SN_CELL_FACTORED || cell == SN_CELL_LSTM, "sn_recur_bwd: bad cell %d", cell);
+  SN_REQUIRE(t0 >= 0 && t1 >= t0 && B > 0, "sn_recur_bwd: bad step range [%d,%d) or B", t0, t1);
+  SN_REQUIRE(Whh && Call && gates && dHall && dZ && dh_carry && dc_carry && ws, "sn_recur_bwd: null argument");
+  if (t1 == t0) return 0;
+  Plan p;
+  int32_t rc = make_plan(true, H, B, &p);
+  if (rc) return rc;
+  RecurArgs a = {};
+  a.cell = cell; a.H = (int)H; a.B = (int)B; a.t0 = t0; a.t1 = t1; a.T = t1 + 1;
+  a.bs = batch_sizes; a.off = offsets; a.W = Whh; a.c_init = c_init;
+  a.Call = const_cast<float*>(Call); a.gates = const_cast<float*>(gates); a.dHall = dHall; a.dZ = dZ;
+  a.dh_carry = dh_carry; a.dc_carry = dc_carry;
+  a.flags = (int*)ws; a.n_ub = p.n_ub; a.nbb = p.nbb; a.BB = p.BB;
+  cudaStream_t st = (cudaStream_t)stream;
+  SN_CUDA(cudaMemsetAsync(ws, 0, sizeof(int) * (size_t)p.nbb * (size_t)(t1 + 1), st));
+  switch (p.SW) {
+    case 6: return launch_coop(recur_bwd_kernel<6>, p, a, st, "sn_recur_bwd");
+    case 4: return launch_coop(recur_bwd_kernel<4>, p, a, st, "sn_recur_bwd");
+    default: return launch_coop(recur_bwd_kernel<2>, p, a, st, "sn_recur_bwd");
+  }
+}
+
+}  // extern "C"

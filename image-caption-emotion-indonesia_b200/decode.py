@@ -1,0 +1,122 @@
+"""Batched beam / greedy decoding on the kernels (K8): the reference's ``sample()`` semantics
+(stylenet/model.py:198-294, nic/model.py:117-207, app/backend/model.py:386-487) for n_img images at
+once, with all bookkeeping on the device and no host synchronisation inside the step loop."""
+import ctypes
+
+import torch
+
+from . import ops
+from ._lib import check
+
+_small = {}
+
+
+def _i32(device, vals):
+    key = (str(device), tuple(vals))
+    t = _small.get(key)
+    if t is None:
+        t = torch.tensor(list(vals), dtype=torch.int32, device=device)
+        _small[key] = t
+    return t
+
+
+class _StepCtx:
+    pass
+
+
+def single_step(dec, embedded, states, mode):
+    """forward_step(embedded, states[, mode]) -> (h, (h, c)) on the kernels (inference only)."""
+    h, c = states
+    R, H = h.shape
+    dev = h.device
+    ctx = _StepCtx()
+    ctx.XP = torch.empty(R, 4 * H, dtype=torch.float32, device=dev)
+    X = embedded.detach().float().contiguous()
+    with torch.no_grad():
+        dec._input_projection(ctx, X, mode, 0, R)
+        Whh, bhh = dec._recurrent_weights()
+        h_new = torch.empty(R, H, dtype=torch.float32, device=dev)
+        c_new = c.detach().float().clone()
+        ops.recur_fwd(dec.cell, H, R, _i32(dev, [R]), _i32(dev, [0]), 0, 1, ctx.XP, Whh, bhh,
+                      h.detach().float().contiguous(), h_new, None, None, None, c_new)
+    return h_new, (h_new, c_new)
+
+
+class BeamState:
+    def __init__(self, n_img, kmax, max_len, start_token, device):
+        L = max_len + 2
+        R = n_img * kmax
+        self.n_img, self.kmax, self.max_len, self.L, self.R = n_img, kmax, max_len, L, R
+        i32 = dict(dtype=torch.int32, device=device)
+        self.k_live = torch.full((n_img,), kmax, **i32)
+        self.run_score = torch.zeros(R, dtype=torch.float32, device=device)
+        self.prev_word = torch.full((R,), start_token, **i32)
+        self.src_row = torch.arange(R, **i32)
+        self.cur_buf = torch.zeros(n_img, **i32)
+        self.seqs = torch.zeros(2, R, L, **i32)
+        self.seqs[:, :, 0] = start_token
+        self.done_seq = torch.zeros(R, L, **i32)
+        self.done_len = torch.zeros(R, **i32)
+        self.done_score = torch.zeros(R, dtype=torch.float32, device=device)
+        self.n_done = torch.zeros(n_img, **i32)
+        self.out_seq = torch.zeros(n_img, L, **i32)
+        self.out_len = torch.zeros(n_img, **i32)
+        self.n_unfinished = torch.full((1,), n_img, **i32)
+
+    def step(self, logits, step, end_token):
+        p = ops._ptr
+        check(ops.lib().sn_beam_step(
+            p(logits), logits.stride(0), logits.shape[1], self.n_img, self.kmax, step, self.max_len, end_token,
+            p(self.k_live), p(self.run_score), p(self.prev_word), p(self.src_row), p(self.cur_buf), p(self.seqs),
+            p(self.done_seq), p(self.done_len), p(self.done_score), p(self.n_done), p(self.out_seq),
+            p(self.out_len), p(self.n_unfinished), ops._stream()), "sn_beam_step")
+
+    def results(self):
+        out = self.out_seq.cpu()
+        n = self.out_len.cpu()
+        return [out[i, :int(n[i])].long().unsqueeze(0) for i in range(self.n_img)]
+
+
+@torch.no_grad()
+def beam_sample(dec, features, start_token, end_token, k, mode, feed_image, sync_every=4):
+    """Returns a list of LongTensor [1, L_i] (one per image; the reference handles one image per call).
+    ``features``: [n_img, E] (or [n_img, 1, E]); rows are independent images."""
+    emb = dec._emb()
+    E = emb.weight.shape[1]
+    dev = emb.weight.device
+    ops.lib()
+    dec.arena()
+    feats = features.detach().to(dev).float().reshape(-1, E).contiguous()
+    n_img = feats.shape[0]
+    H = dec.hidden_size
+    st = BeamState(n_img, k, dec.max_seq_length, start_token, dev)
+    R = st.R
+    h = torch.zeros(R, H, dtype=torch.float32, device=dev)
+    c = torch.zeros(R, H, dtype=torch.float32, device=dev)
+    h_new = torch.empty_like(h)
+    out = dec._out()
+    V = out.weight.shape[0]
+    logits = torch.empty(R, V, dtype=torch.float32, device=dev)
+    X = torch.empty(R, E, dtype=torch.float32, device=dev)
+    ctx = _StepCtx()
+    ctx.XP = torch.empty(R, 4 * H, dtype=torch.float32, device=dev)
+    row_img = (torch.arange(R, device=dev, dtype=torch.int32) // k).contiguous()
+    row_zero = torch.zeros(R, dtype=torch.int32, device=dev)
+    dummy_cap = torch.zeros(1, 1, dtype=torch.int64, device=dev)
+    bs1, off1 = _i32(dev, [R]), _i32(dev, [0])
+    Whh, bhh = dec._recurrent_weights()
+    for step in range(1, dec.max_seq_length + 2):
+        if feed_image and step == 1:
+            ops.gather_pack_fwd(dummy_cap, emb.weight, feats, True, row_img, row_zero, None, R, X, 0.0, 0)
+        else:
+            ops.gather_pack_fwd(dummy_cap, emb.weight, None, False, row_img, row_zero, st.prev_word, R, X, 0.0, 0)
+        dec._input_projection(ctx, X, mode, 0, R)
+        ops.recur_fwd(dec.cell, H, R, bs1, off1, 0, 1, ctx.XP, Whh, bhh, h, h_new, None, None, None, c)
+        ops.gemm(ops.OP_NT, h_new, out.weight, logits, R, V, H, H, H, V, bias=out.bias)
+        st.step(logits, step, end_token)
+        idx = st.src_row.long()
+        h = h_new.index_select(0, idx)
+        c = c.index_select(0, idx)
+        if sync_every and step % sync_every == 0 and int(st.n_unfinished.item()) == 0:
+            break
+    return st.results()

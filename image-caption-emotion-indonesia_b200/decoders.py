@@ -1,0 +1,560 @@
+"""Drop-in decoder modules: the reference's ``nn.Module`` surface (constructor arguments, parameter names,
+``forward`` / ``forward_step`` / ``sample`` signatures) over the sm_100a kernels of libsn100.so.
+
+Reference surfaces mirrored here:
+  DecoderFactoredLSTM      stylenet/model.py:30-294
+  DecoderRNN               nic/model.py:29-207
+(the attention variants live in decoders_att.py)
+
+Host logic only: packing plans, the teacher-forcing coin sequence (one ``random.random()`` per step,
+stylenet/model.py:181), kernel sequencing and autograd glue.  All arithmetic runs in libsn100.so; there is
+no PyTorch/CPU fallback -- tensors must be CUDA tensors on an sm_100 device.
+"""
+import random
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .arena import ParamArena
+from .packing import get_plan
+
+GATES = ("i", "f", "o", "c")
+STYLES = ("factual", "happy", "sad", "angry")
+
+
+def style_attr(style, gate):
+    return ("S_f" + gate) if style == "factual" else ("S_%s_%s" % (style, gate))
+
+
+def _ref_init(module, emb, out):
+    """reset_parameters + init_weights, stylenet/model.py:99-113 (host-side init, not on the path)."""
+    for p in module.parameters():
+        if p.dim() >= 2:
+            nn.init.xavier_uniform_(p.data)
+        else:
+            nn.init.zeros_(p.data)
+    emb.weight.data.uniform_(-0.1, 0.1)
+    out.bias.data.fill_(0)
+    out.weight.data.uniform_(-0.1, 0.1)
+
+
+class _Ctx:
+    """Activations saved between forward and backward of one sequence."""
+    pass
+
+
+class _HiddenFn(torch.autograd.Function):
+    """captions/features -> Hall [N,H] through K1, K2, K3; backward publishes parameter gradients into
+    the arena and returns d features."""
+
+    @staticmethod
+    def forward(ctx, anchor, features, dec, plan, captions, coins, mode, save):
+        c = dec._run_forward(plan, captions, features, coins, mode, save=save)
+        ctx.dec, ctx.c = dec, c
+        ctx.need_dfeat = features is not None and features.requires_grad
+        return c.Hall
+
+    @staticmethod
+    def backward(ctx, dHall):
+        dec, c = ctx.dec, ctx.c
+        gbuf = dec._grad_target(c.grad_names)
+        dfeat = dec._run_backward(c, dHall.contiguous(), gbuf, ctx.need_dfeat)
+        dec._publish(c.grad_names, gbuf)
+        return None, dfeat, None, None, None, None, None, None
+
+
+class _LogitsFn(torch.autograd.Function):
+    """Hall -> logits [N,V] (the tensor the reference's forward() returns, stylenet/model.py:193-194)."""
+
+    @staticmethod
+    def forward(ctx, Hall, anchor, dec):
+        ctx.dec = dec
+        ctx.save_for_backward(Hall)
+        return dec._vocab_logits(Hall)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        dec = ctx.dec
+        (Hall,) = ctx.saved_tensors
+        gbuf = dec._grad_target(dec._out_names())
+        dHall = dec._vocab_backward(Hall, dlogits.contiguous(), gbuf)
+        dec._publish(dec._out_names(), gbuf)
+        return dHall, None, None
+
+
+class _DecoderBase(nn.Module):
+    """Shared host logic of the non-attention decoders."""
+
+    cell = ops.CELL_FACTORED
+
+    # ---- arena ----------------------------------------------------------------------------------
+    def _arena_groups(self):
+        raise NotImplementedError
+
+    def arena(self):
+        a = self.__dict__.get("_arena")
+        if a is None:
+            a = ParamArena(self, self._arena_groups())
+            self.__dict__["_arena"] = a
+        return a.ensure()
+
+    def _grad_target(self, names):
+        """Flat buffer the backward kernels write: the gradient arena itself, or a zeroed temporary when
+        one of the parameters about to be written already holds a gradient (accumulation across
+        backward calls without zero_grad)."""
+        a = self.arena()
+        if any(a.named[n].grad is not None for n in names):
+            return torch.zeros_like(a.gflat)
+        return a.gflat
+
+    def _publish(self, names, gbuf):
+        self.arena().publish_grads(names, gbuf)
+
+    def _check_inputs(self, captions, features):
+        if not captions.is_cuda:
+            raise ops._lib.SnError("decoder inputs must be CUDA tensors: this path has no CPU fallback")
+        ops.lib()
+
+    # ---- pieces each subclass provides -----------------------------------------------------------
+    def _emb(self):
+        raise NotImplementedError
+
+    def _out(self):
+        raise NotImplementedError
+
+    def _input_projection(self, c, X, mode, r0, n):
+        raise NotImplementedError
+
+    def _input_projection_bwd(self, c, dZ, gbuf):
+        raise NotImplementedError
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def _coins(self, T, teacher_forcing_ratio):
+        # one coin per time step for the whole batch, drawn from Python's global RNG exactly like the
+        # reference (stylenet/model.py:181); drawing them up front consumes the same stream.
+        return [random.random() < teacher_forcing_ratio for _ in range(T)]
+
+    def _run_forward(self, plan, captions, features, coins, mode, save):
+        a = self.arena()
+        dev = captions.device
+        d = plan.dev(dev)
+        H, N, B, T = self.hidden_size, plan.N, plan.B, plan.T
+        emb = self._emb()
+        E = emb.weight.shape[1]
+        has_feat = features is not None
+        c = _Ctx()
+        c.plan, c.mode, c.has_feat, c.captions = plan, mode, has_feat, captions
+        c.p_drop = float(self.dropout.p) if self.training else 0.0
+        self.__dict__["_calls"] = self.__dict__.get("_calls", 0) + 1
+        c.seed = (int(self.__dict__.get("_seed", 0x5EED)) * 1000003 + self._calls) & 0xFFFFFFFFFFFF
+        feats = None
+        if has_feat:
+            feats = features.detach()
+            if feats.dtype != torch.float32 or not feats.is_contiguous():
+                feats = feats.float().contiguous()
+            if feats.dim() == 3:
+                feats = feats.reshape(feats.shape[0], -1)
+        all_tf = all(coins)
+        c.tok_override = None
+        if not all_tf:
+            c.tok_override = torch.full((N,), -1, dtype=torch.int32, device=dev)
+        X = torch.empty(N, E, dtype=torch.float32, device=dev)
+        ops.gather_pack_fwd(captions, emb.weight, feats, has_feat, d["row_b"], d["row_t"], None, N, X,
+                            c.p_drop, c.seed)
+        c.X = X
+        c.XP = torch.empty(N, 4 * H, dtype=torch.float32, device=dev)
+        self._input_projection(c, X, mode, 0, N)
+        c.Hall = torch.empty(N, H, dtype=torch.float32, device=dev)
+        c.Call = torch.empty(N, H, dtype=torch.float32, device=dev) if save else None
+        c.Hprev = torch.empty(N, H, dtype=torch.float32, device=dev) if save else None
+        c.gates = torch.empty(N, 4 * H, dtype=torch.float32, device=dev) if save else None
+        c_state = torch.zeros(B, H, dtype=torch.float32, device=dev)
+        c.aux_argmax = None
+        Whh, bhh = self._recurrent_weights()
+
+        def run(t0, t1):
+            h_init = None
+            if t0 > 0:
+                h_init = c.Hall[plan.off[t0 - 1]:]
+            ops.recur_fwd(self.cell, H, B, d["bs"], d["off"], t0, t1, c.XP, Whh, bhh, h_init, c.Hall,
+                          c.Call, c.Hprev, c.gates, c_state)
+
+        if all_tf:
+            run(0, T)
+        else:
+            out = self._out()
+            V = out.weight.shape[0]
+            pred = captions[:, 0].to(torch.int32).contiguous()      # model.py:179
+            am = torch.empty(B, dtype=torch.int64, device=dev)
+            t = 0
+            while t < T:
+                if coins[t]:
+                    t1 = t
+                    while t1 < T and coins[t1]:
+                        t1 += 1
+                    run(t, t1)
+                    t = t1
+                else:
+                    bt, r0 = plan.bs[t], plan.off[t]
+                    if t > 0:
+                        # predicted = argmax C(h_{t-1})  (model.py:189-191), lowest index on ties
+                        bp, rp = plan.bs[t - 1], plan.off[t - 1]
+                        lg = torch.empty(bp, V, dtype=torch.float32, device=dev)
+                        ops.gemm(ops.OP_NT, c.Hall, out.weight, lg, bp, V, H, H, H, V, bias=out.bias,
+                                 a_off=rp * H)
+                        ops.softmax_nll(lg, bp, V, argmax=am)
+                        pred = am[:bp].to(torch.int32)
+                    c.tok_override[r0:r0 + bt] = pred[:bt]
+                    ops.gather_pack_fwd(captions, emb.weight, feats, has_feat, d["row_b"], d["row_t"],
+                                        c.tok_override, bt, X, c.p_drop, c.seed, row_off=r0)
+                    self._input_projection(c, X, mode, r0, bt)
+                    run(t, t + 1)
+                    t += 1
+        c.grad_names = self._seq_grad_names(mode)
+        c.feat_shape = None if features is None else features.shape
+        if not save:
+            c.X = c.XP = None
+        return c
+
+    def _run_backward(self, c, dHall, gbuf, need_dfeat):
+        a = self.arena()
+        plan = c.plan
+        dev = dHall.device
+        d = plan.dev(dev)
+        H, N, B, T = self.hidden_size, plan.N, plan.B, plan.T
+        emb = self._emb()
+        E = emb.weight.shape[1]
+        Whh, _ = self._recurrent_weights()
+        dZ = torch.empty(N, 4 * H, dtype=torch.float32, device=dev)
+        dh = torch.zeros(B, H, dtype=torch.float32, device=dev)
+        dc = torch.zeros(B, H, dtype=torch.float32, device=dev)
+        ops.recur_bwd(self.cell, H, B, d["bs"], d["off"], 0, T, Whh, None, c.Call, c.gates, dHall, dZ, dh, dc)
+        # dW_hh = dZ^T Hprev ; d b_hh = colsum(dZ)
+        gW, gbW = self._recurrent_grads(gbuf)
+        ops.gemm(ops.OP_TN, dZ, c.Hprev, gW, 4 * H, H, N, 4 * H, H, H)
+        ops.colsum(dZ, N, 4 * H, 4 * H, gbW)
+        dX = self._input_projection_bwd(c, dZ, gbuf)
+        gE = a.block([self._emb_name()], emb.weight.shape, grad=True) if gbuf is a.gflat else \
+            gbuf[a.offset[self._emb_name()]:a.offset[self._emb_name()] + emb.weight.numel()].view(emb.weight.shape)
+        gE.zero_()
+        dfeat = torch.empty(B, E, dtype=torch.float32, device=dev) if (need_dfeat and c.has_feat) else None
+        ops.gather_pack_bwd(c.captions, gE, dfeat, c.has_feat, d["row_b"], d["row_t"], c.tok_override, N, dX,
+                            c.p_drop, c.seed)
+        if dfeat is not None and c.feat_shape is not None:
+            dfeat = dfeat.view(c.feat_shape)
+        return dfeat
+
+    def _gview(self, gbuf, names, shape):
+        a = self.arena()
+        o, n = a._span(names)
+        return gbuf[o:o + n].view(shape)
+
+    # ---- vocabulary projection ---------------------------------------------------------------------
+    def _vocab_logits(self, Hall):
+        out = self._out()
+        return ops.linear_nt(Hall.contiguous(), out.weight, out.bias)
+
+    def _vocab_backward(self, Hall, dlogits, gbuf):
+        out = self._out()
+        V, H = out.weight.shape
+        N = Hall.shape[0]
+        wn, bn = self._out_names()
+        gC = self._gview(gbuf, [wn], (V, H))
+        gb = self._gview(gbuf, [bn], (V,))
+        dHall = torch.empty(N, H, dtype=torch.float32, device=Hall.device)
+        ops.gemm(ops.OP_NN, dlogits, out.weight, dHall, N, H, V, dlogits.stride(0), H, H)
+        ops.gemm(ops.OP_TN, dlogits, Hall, gC, V, H, N, dlogits.stride(0), H, H)
+        ops.colsum(dlogits, N, V, dlogits.stride(0), gb)
+        return dHall
+
+    # ---- public API --------------------------------------------------------------------------------
+    def _forward_hidden(self, captions, lengths, features, teacher_forcing_ratio, mode):
+        self._check_inputs(captions, features)
+        if features is not None and features.shape[-1] != self._emb().weight.shape[1]:
+            raise RuntimeError("features must be [B, embed_size]")
+        plan = get_plan(lengths)
+        if plan.B != captions.shape[0]:
+            raise RuntimeError("len(lengths) != batch size")
+        T_in = captions.shape[1] + (1 if features is not None else 0)
+        if plan.T > T_in:
+            raise RuntimeError("lengths exceed the (feature +) caption length")
+        coins = self._coins(plan.T, teacher_forcing_ratio)
+        captions = captions.contiguous()
+        anchor = self._out().weight
+        save = torch.is_grad_enabled()
+        return _HiddenFn.apply(anchor, features, self, plan, captions, coins, mode, save), plan
+
+    def forward_loss(self, captions, lengths, features=None, targets=None, teacher_forcing_ratio=1.0,
+                     mode="factual", backward=True, n_global=None):
+        """Fused training entry point (an addition beside the kept surface):
+        forward -> mean token NLL -> (optionally) backward, with log-softmax/NLL/gradient fused in one
+        pass over the logits and no autograd graph.  Populates ``.grad`` like ``loss.backward()`` after
+        ``zero_grad()`` would.  Returns ``(loss[1], stats)`` with stats = dict(argmax, top5hit).
+        ``n_global``: token count to normalise by (data parallel: the global count)."""
+        self._check_inputs(captions, features)
+        plan = get_plan(lengths)
+        coins = self._coins(plan.T, teacher_forcing_ratio)
+        captions = captions.contiguous()
+        dev = captions.device
+        with torch.no_grad():
+            c = self._run_forward(plan, captions, features, coins, mode, save=backward)
+            N = plan.N
+            out = self._out()
+            V = out.weight.shape[0]
+            if targets is None:
+                if features is None:
+                    raise ValueError("forward_loss: pass `targets` when features is None (language-only "
+                                     "pass: inputs captions[:, :-1], targets packed captions[:, 1:])")
+                targets = self._default_targets(captions, plan, True)
+            logits = self._vocab_logits(c.Hall)
+            row_loss = torch.empty(N, dtype=torch.float32, device=dev)
+            argmax = torch.empty(N, dtype=torch.int64, device=dev)
+            top5 = torch.empty(N, dtype=torch.int32, device=dev)
+            denom = float(n_global if n_global is not None else N)
+            ops.softmax_nll(logits, N, V, targets=targets, row_loss=row_loss,
+                            dlogits=logits if backward else None, grad_scale=1.0 / denom, argmax=argmax,
+                            top5hit=top5)
+            loss = torch.empty(1, dtype=torch.float32, device=dev)
+            ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
+            if backward:
+                gbuf = self._grad_target(c.grad_names + list(self._out_names()))
+                dHall = self._vocab_backward(c.Hall, logits, gbuf)
+                need_dfeat = features is not None and features.requires_grad
+                dfeat = self._run_backward(c, dHall, gbuf, need_dfeat)
+                self._publish(c.grad_names + list(self._out_names()), gbuf)
+                if dfeat is not None:
+                    features.grad = dfeat if features.grad is None else features.grad + dfeat
+        return loss, {"argmax": argmax, "top5hit": top5, "n_tokens": N}
+
+    def _default_targets(self, captions, plan, has_feat):
+        d = plan.dev(captions.device)
+        t = d["row_t"].long() if has_feat else d["row_t"].long() + 1
+        return captions[d["row_b"].long(), t].contiguous()
+
+
+class DecoderFactoredLSTM(_DecoderBase):
+    """StyleNet FactoredLSTM decoder -- signature of stylenet/model.py:32-41."""
+
+    cell = ops.CELL_FACTORED
+
+    def __init__(self, embed_size, hidden_size, factored_size, vocab_size, num_layers, feature_size=2048,
+                 bias=True, dropout=0.22, max_seq_length=40):
+        super().__init__()
+        if not bias:
+            raise NotImplementedError("bias=False is not supported by the fused path")
+        self.feature_size, self.hidden_size = feature_size, hidden_size
+        self.factored_size, self.embed_size = factored_size, embed_size
+        self.vocab_size, self.max_seq_length = vocab_size, max_seq_length
+        self.num_layers = num_layers   # accepted and ignored, like the reference (model.py:37)
+        self.dropout = nn.Dropout(dropout)
+        self.B = nn.Embedding(vocab_size, embed_size)
+        for g in GATES:
+            setattr(self, "U_" + g, nn.Linear(factored_size, hidden_size, bias=bias))
+            setattr(self, style_attr("factual", g), nn.Linear(factored_size, factored_size, bias=bias))
+            setattr(self, "V_" + g, nn.Linear(embed_size, factored_size, bias=bias))
+            setattr(self, "W_" + g, nn.Linear(hidden_size, hidden_size, bias=bias))
+        for s in STYLES[1:]:
+            for g in GATES:
+                setattr(self, style_attr(s, g), nn.Linear(factored_size, factored_size, bias=bias))
+        self.C = nn.Linear(hidden_size, vocab_size, bias=bias)
+        _ref_init(self, self.B, self.C)
+
+    # -- layout ------------------------------------------------------------------------------------
+    def _arena_groups(self):
+        groups = [["B.weight"]]
+        for pre in ("V_", "U_", "W_"):
+            groups.append([pre + g + ".weight" for g in GATES])
+            groups.append([pre + g + ".bias" for g in GATES])
+        for s in STYLES:
+            groups.append([style_attr(s, g) + ".weight" for g in GATES])
+            groups.append([style_attr(s, g) + ".bias" for g in GATES])
+        groups += [["C.weight"], ["C.bias"]]
+        return groups
+
+    def _emb(self):
+        return self.B
+
+    def _emb_name(self):
+        return "B.weight"
+
+    def _out(self):
+        return self.C
+
+    def _out_names(self):
+        return ("C.weight", "C.bias")
+
+    def _stack(self, pre, shape, grad=False, gbuf=None, bias=False):
+        names = [pre + g + (".bias" if bias else ".weight") for g in GATES]
+        if gbuf is not None:
+            return self._gview(gbuf, names, shape)
+        return self.arena().block(names, shape, grad=grad)
+
+    def _style_stack(self, mode, shape, gbuf=None, bias=False):
+        names = [style_attr(mode, g) + (".bias" if bias else ".weight") for g in GATES]
+        if gbuf is not None:
+            return self._gview(gbuf, names, shape)
+        return self.arena().block(names, shape)
+
+    def _recurrent_weights(self):
+        H = self.hidden_size
+        return self._stack("W_", (4 * H, H)), self._stack("W_", (4 * H,), bias=True)
+
+    def _recurrent_grads(self, gbuf):
+        H = self.hidden_size
+        return self._stack("W_", (4 * H, H), gbuf=gbuf), self._stack("W_", (4 * H,), gbuf=gbuf, bias=True)
+
+    def _seq_grad_names(self, mode):
+        names = ["B.weight"]
+        for pre in ("V_", "U_", "W_"):
+            names += [pre + g + sfx for g in GATES for sfx in (".weight", ".bias")]
+        names += [style_attr(mode, g) + sfx for g in GATES for sfx in (".weight", ".bias")]
+        return names
+
+    # -- K2: factored input projection U S V ----------------------------------------------------------
+    def _input_projection(self, c, X, mode, r0, n):
+        """XP[r0:r0+n] = U_g(S_{mode,g}(V_g x)) for the four gates (stylenet/model.py:119-150), as one
+        stacked GEMM and two 4-group batched GEMMs; biases of every stage included."""
+        if mode not in STYLES:
+            raise ValueError("mode name wrong: %r (expected one of %s)" % (mode, STYLES))
+        H, F = self.hidden_size, self.factored_size
+        Ein = X.shape[1]
+        dev = X.device
+        if r0 == 0 and n == X.shape[0]:
+            c.A1 = torch.empty(n, 4 * F, dtype=torch.float32, device=dev)
+            c.A2 = torch.empty(n, 4 * F, dtype=torch.float32, device=dev)
+        A1, A2 = c.A1, c.A2
+        Vc, bV = self._stack("V_", (4 * F, Ein)), self._stack("V_", (4 * F,), bias=True)
+        Sc, bS = self._style_stack(mode, (4 * F, F)), self._style_stack(mode, (4 * F,), bias=True)
+        Uc, bU = self._stack("U_", (4 * H, F)), self._stack("U_", (4 * H,), bias=True)
+        ops.gemm(ops.OP_NT, X, Vc, A1, n, 4 * F, Ein, Ein, Ein, 4 * F, bias=bV, a_off=r0 * Ein,
+                 c_off=r0 * 4 * F)
+        ops.gemm(ops.OP_NT, A1, Sc, A2, n, F, F, 4 * F, F, 4 * F, bias=bS, batch=4, sA=F, sB=F * F, sC=F,
+                 sBias=F, a_off=r0 * 4 * F, c_off=r0 * 4 * F)
+        ops.gemm(ops.OP_NT, A2, Uc, c.XP, n, H, F, 4 * F, F, 4 * H, bias=bU, batch=4, sA=F, sB=H * F, sC=H,
+                 sBias=H, a_off=r0 * 4 * F, c_off=r0 * 4 * H)
+
+    def _input_projection_bwd(self, c, dZ, gbuf):
+        H, F = self.hidden_size, self.factored_size
+        N, Ein = c.X.shape
+        dev = dZ.device
+        mode = c.mode
+        Vc = self._stack("V_", (4 * F, Ein))
+        Sc = self._style_stack(mode, (4 * F, F))
+        Uc = self._stack("U_", (4 * H, F))
+        gV, gbV = self._stack("V_", (4 * F, Ein), gbuf=gbuf), self._stack("V_", (4 * F,), gbuf=gbuf, bias=True)
+        gS, gbS = self._style_stack(mode, (4 * F, F), gbuf=gbuf), self._style_stack(mode, (4 * F,), gbuf=gbuf, bias=True)
+        gU, gbU = self._stack("U_", (4 * H, F), gbuf=gbuf), self._stack("U_", (4 * H,), gbuf=gbuf, bias=True)
+        # U stage: dU_g = dZ_g^T A2_g ; dbU = colsum(dZ) ; dA2_g = dZ_g U_g
+        ops.gemm(ops.OP_TN, dZ, c.A2, gU, H, F, N, 4 * H, 4 * F, F, batch=4, sA=H, sB=F, sC=H * F)
+        ops.colsum(dZ, N, 4 * H, 4 * H, gbU)
+        dA2 = torch.empty(N, 4 * F, dtype=torch.float32, device=dev)
+        ops.gemm(ops.OP_NN, dZ, Uc, dA2, N, F, H, 4 * H, F, 4 * F, batch=4, sA=H, sB=H * F, sC=F)
+        # S stage
+        ops.gemm(ops.OP_TN, dA2, c.A1, gS, F, F, N, 4 * F, 4 * F, F, batch=4, sA=F, sB=F, sC=F * F)
+        ops.colsum(dA2, N, 4 * F, 4 * F, gbS)
+        dA1 = torch.empty(N, 4 * F, dtype=torch.float32, device=dev)
+        ops.gemm(ops.OP_NN, dA2, Sc, dA1, N, F, F, 4 * F, F, 4 * F, batch=4, sA=F, sB=F * F, sC=F)
+        # V stage
+        ops.gemm(ops.OP_TN, dA1, c.X, gV, 4 * F, Ein, N, 4 * F, Ein, Ein)
+        ops.colsum(dA1, N, 4 * F, 4 * F, gbV)
+        dX = torch.empty(N, Ein, dtype=torch.float32, device=dev)
+        ops.gemm(ops.OP_NN, dA1, Vc, dX, N, Ein, 4 * F, 4 * F, Ein, Ein)
+        return dX
+
+    # -- reference surface ---------------------------------------------------------------------------
+    def forward(self, captions, lengths, features=None, teacher_forcing_ratio=0.8, mode="factual"):
+        """Same call and return as stylenet/model.py:157-196: packed logits [sum(lengths), V]."""
+        if mode not in STYLES:
+            raise ValueError("mode name wrong: %r (expected one of %s)" % (mode, STYLES))
+        hall, _ = self._forward_hidden(captions, lengths, features, teacher_forcing_ratio, mode)
+        return _LogitsFn.apply(hall, self.C.weight, self)
+
+    def forward_step(self, embedded, states, mode):
+        """One cell step (stylenet/model.py:115-155) on the kernels: K2 projection + one K3 step."""
+        from .decode import single_step
+        return single_step(self, embedded, states, mode)
+
+    def sample(self, features, start_token, end_token, k=5, factual_limit=-1, mode="factual",
+               feed_image=False):
+        """Beam search with the reference's semantics (stylenet/model.py:198-294; ``feed_image=True`` is
+        the app/backend/model.py:386-487 variant).  Returns LongTensor [1, L]."""
+        from .decode import beam_sample
+        return beam_sample(self, features, start_token, end_token, k, mode, feed_image)[0]
+
+
+class DecoderRNN(_DecoderBase):
+    """NIC LSTM decoder -- signature of nic/model.py:31-38."""
+
+    cell = ops.CELL_LSTM
+
+    def __init__(self, embed_size, hidden_size, vocab_size, num_layers, feature_size=2048, dropout=0.22,
+                 max_seq_length=40):
+        super().__init__()
+        self.feature_size, self.hidden_size, self.embed_size = feature_size, hidden_size, embed_size
+        self.vocab_size, self.max_seq_length = vocab_size, max_seq_length
+        self.num_layers = num_layers
+        self.dropout = nn.Dropout(dropout)
+        self.embed = nn.Embedding(vocab_size, embed_size)
+        self.lstm = nn.LSTMCell(embed_size, hidden_size, bias=True)
+        self.linear = nn.Linear(hidden_size, vocab_size)
+        _ref_init(self, self.embed, self.linear)
+
+    def _arena_groups(self):
+        return [["embed.weight"], ["lstm.weight_ih"], ["lstm.weight_hh"], ["lstm.bias_ih"], ["lstm.bias_hh"],
+                ["linear.weight"], ["linear.bias"]]
+
+    def _emb(self):
+        return self.embed
+
+    def _emb_name(self):
+        return "embed.weight"
+
+    def _out(self):
+        return self.linear
+
+    def _out_names(self):
+        return ("linear.weight", "linear.bias")
+
+    def _recurrent_weights(self):
+        self.arena()
+        return self.lstm.weight_hh, self.lstm.bias_hh
+
+    def _recurrent_grads(self, gbuf):
+        H = self.hidden_size
+        return self._gview(gbuf, ["lstm.weight_hh"], (4 * H, H)), self._gview(gbuf, ["lstm.bias_hh"], (4 * H,))
+
+    def _seq_grad_names(self, mode):
+        return ["embed.weight", "lstm.weight_ih", "lstm.weight_hh", "lstm.bias_ih", "lstm.bias_hh"]
+
+    def _input_projection(self, c, X, mode, r0, n):
+        """XP = x W_ih^T + b_ih (the first addmm of nn.LSTMCell, nic/model.py:77)."""
+        H = self.hidden_size
+        Ein = X.shape[1]
+        ops.gemm(ops.OP_NT, X, self.lstm.weight_ih, c.XP, n, 4 * H, Ein, Ein, Ein, 4 * H,
+                 bias=self.lstm.bias_ih, a_off=r0 * Ein, c_off=r0 * 4 * H)
+
+    def _input_projection_bwd(self, c, dZ, gbuf):
+        H = self.hidden_size
+        N, Ein = c.X.shape
+        gW = self._gview(gbuf, ["lstm.weight_ih"], (4 * H, Ein))
+        gb = self._gview(gbuf, ["lstm.bias_ih"], (4 * H,))
+        ops.gemm(ops.OP_TN, dZ, c.X, gW, 4 * H, Ein, N, 4 * H, Ein, Ein)
+        ops.colsum(dZ, N, 4 * H, 4 * H, gb)
+        dX = torch.empty(N, Ein, dtype=torch.float32, device=dZ.device)
+        ops.gemm(ops.OP_NN, dZ, self.lstm.weight_ih, dX, N, Ein, 4 * H, 4 * H, Ein, Ein)
+        return dX
+
+    def forward(self, captions, lengths, features, teacher_forcing_ratio=0.8):
+        """Same call and return as nic/model.py:81-115."""
+        hall, _ = self._forward_hidden(captions, lengths, features, teacher_forcing_ratio, None)
+        return _LogitsFn.apply(hall, self.linear.weight, self)
+
+    def forward_step(self, embedded, states):
+        from .decode import single_step
+        return single_step(self, embedded, states, None)
+
+    def sample(self, features, start_token, end_token, k=5, feed_image=False):
+        """Beam search, nic/model.py:117-207 (``feed_image=True``: app/backend variant)."""
+        from .decode import beam_sample
+        return beam_sample(self, features, start_token, end_token, k, None, feed_image)[0]

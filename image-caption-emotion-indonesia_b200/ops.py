@@ -1,0 +1,146 @@
+"""Thin tensor-level wrappers over the C ABI (include/sn100.h).  Tensors are only carriers of device
+pointers; every op launches hand-written sm_100a kernels on torch's current CUDA stream."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import OP_NN, OP_NT, OP_TN, CELL_FACTORED, CELL_LSTM, check  # noqa: F401
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _req(t, dtype=torch.float32):
+    if not t.is_cuda:
+        raise _lib.SnError("libsn100 ops need CUDA tensors (no CPU fallback); got %s" % t.device)
+    if t.dtype != dtype:
+        raise _lib.SnError("expected %s, got %s" % (dtype, t.dtype))
+    return t
+
+
+def lib():
+    l = _lib.load()
+    _lib.require_device(torch.cuda.current_device())
+    return l
+
+
+def gemm(op, A, B, C, M, N, K, lda, ldb, ldc, bias=None, beta=0.0, batch=1, sA=0, sB=0, sC=0, sBias=0,
+         a_off=0, b_off=0, c_off=0, bias_off=0):
+    """C = op(A) op(B) + bias + beta*C.  Offsets are in elements (pointer arithmetic on the base)."""
+    _req(A); _req(B); _req(C)
+    pa = ctypes.c_void_p(A.data_ptr() + 4 * a_off)
+    pb = ctypes.c_void_p(B.data_ptr() + 4 * b_off)
+    pc = ctypes.c_void_p(C.data_ptr() + 4 * c_off)
+    pbias = ctypes.c_void_p(bias.data_ptr() + 4 * bias_off) if bias is not None else None
+    check(lib().sn_gemm(op, M, N, K, pa, lda, pb, ldb, pc, ldc, pbias, float(beta), batch, sA, sB, sC, sBias,
+                        _stream()), "sn_gemm")
+    return C
+
+
+def linear_nt(x, w, bias=None, out=None):
+    """out[M,N] = x[M,K] @ w[N,K]^T + bias  (nn.Linear forward) for contiguous 2-D tensors."""
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    return gemm(OP_NT, x, w, out, M, N, K, x.stride(0), w.stride(0), out.stride(0), bias=bias)
+
+
+def colsum(X, M, N, ldx, out, beta=0.0, x_off=0, out_off=0):
+    _req(X); _req(out)
+    check(lib().sn_colsum(ctypes.c_void_p(X.data_ptr() + 4 * x_off), M, N, ldx,
+                          ctypes.c_void_p(out.data_ptr() + 4 * out_off), float(beta), _stream()), "sn_colsum")
+    return out
+
+
+def gather_pack_fwd(captions, table, features, has_feat, row_b, row_t, tok_override, N, X, p_drop, seed,
+                    row_off=0):
+    E = table.shape[1]
+    cap = _req(captions, torch.int64)
+    ro4 = 4 * row_off
+    check(lib().sn_gather_pack_fwd(
+        _ptr(cap), cap.stride(0), _ptr(_req(table)), E,
+        _ptr(features) if features is not None else None, features.stride(0) if features is not None else 0,
+        1 if has_feat else 0,
+        ctypes.c_void_p(row_b.data_ptr() + ro4), ctypes.c_void_p(row_t.data_ptr() + ro4),
+        ctypes.c_void_p(tok_override.data_ptr() + ro4) if tok_override is not None else None,
+        N, ctypes.c_void_p(X.data_ptr() + 4 * row_off * X.stride(0)), X.stride(0), float(p_drop),
+        ctypes.c_uint64(seed), _stream()), "sn_gather_pack_fwd")
+
+
+def gather_pack_bwd(captions, dtable, dfeatures, has_feat, row_b, row_t, tok_override, N, dX, p_drop, seed):
+    E = dtable.shape[1]
+    cap = _req(captions, torch.int64)
+    check(lib().sn_gather_pack_bwd(
+        _ptr(cap), cap.stride(0), _ptr(_req(dtable)), E,
+        _ptr(dfeatures) if dfeatures is not None else None,
+        dfeatures.stride(0) if dfeatures is not None else 0, 1 if has_feat else 0,
+        _ptr(row_b), _ptr(row_t), _ptr(tok_override) if tok_override is not None else None,
+        N, _ptr(_req(dX)), dX.stride(0), float(p_drop), ctypes.c_uint64(seed), _stream()), "sn_gather_pack_bwd")
+
+
+_ws_cache = {}
+
+
+def _recur_ws(device, T):
+    key = (device, T)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        nbytes = lib().sn_recur_ws_bytes(1, T)
+        ws = torch.empty(nbytes // 4 + 1, dtype=torch.int32, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def recur_fwd(cell, H, B, bs, off, t0, t1, XP, Whh, bhh, h_init, Hall, Call, Hprev, gates, c_state):
+    ws = _recur_ws(XP.device, t1 + 1)
+    check(lib().sn_recur_fwd(cell, H, B, _ptr(bs), _ptr(off), t0, t1, _ptr(_req(XP)), _ptr(_req(Whh)),
+                             _ptr(h_init), _ptr(bhh), _ptr(Hall), _ptr(Call), _ptr(Hprev), _ptr(gates),
+                             _ptr(c_state), _ptr(ws), _stream()), "sn_recur_fwd")
+
+
+def recur_bwd(cell, H, B, bs, off, t0, t1, Whh, c_init, Call, gates, dHall, dZ, dh_carry, dc_carry):
+    ws = _recur_ws(dZ.device, t1 + 1)
+    check(lib().sn_recur_bwd(cell, H, B, _ptr(bs), _ptr(off), t0, t1, _ptr(_req(Whh)), _ptr(c_init),
+                             _ptr(Call), _ptr(gates), _ptr(_req(dHall)), _ptr(dZ), _ptr(dh_carry),
+                             _ptr(dc_carry), _ptr(ws), _stream()), "sn_recur_bwd")
+
+
+def softmax_nll(logits, N, V, targets=None, row_loss=None, dlogits=None, grad_scale=1.0, argmax=None,
+                top5hit=None, row_off=0):
+    ld = logits.stride(0)
+    check(lib().sn_softmax_nll(
+        ctypes.c_void_p(logits.data_ptr() + 4 * row_off * ld), N, V, ld, _ptr(targets), _ptr(row_loss),
+        _ptr(dlogits), dlogits.stride(0) if dlogits is not None else 0, float(grad_scale), _ptr(argmax),
+        _ptr(top5hit), _stream()), "sn_softmax_nll")
+
+
+def reduce_sum(x, N, scale, out, accumulate=False):
+    check(lib().sn_reduce_sum(_ptr(_req(x)), N, float(scale), _ptr(out), 1 if accumulate else 0, _stream()),
+          "sn_reduce_sum")
+
+
+def adam_clamp(p, g, m, v, ranges, step_sizes, bc2_sqrts, beta1, beta2, eps, clip):
+    n = len(ranges)
+    if n == 0:
+        return
+    R = (ctypes.c_int64 * (2 * n))()
+    S = (ctypes.c_float * n)()
+    C = (ctypes.c_float * n)()
+    for i, (o, l) in enumerate(ranges):
+        R[2 * i], R[2 * i + 1] = o, l
+        S[i], C[i] = step_sizes[i], bc2_sqrts[i]
+    check(lib().sn_adam_clamp(_ptr(_req(p)), _ptr(_req(g)), _ptr(_req(m)), _ptr(_req(v)), n,
+                              ctypes.cast(R, ctypes.c_void_p), ctypes.cast(S, ctypes.c_void_p),
+                              ctypes.cast(C, ctypes.c_void_p), beta1, beta2, eps, clip, _stream()),
+          "sn_adam_clamp")
+
+
+def mean_pixels(feat, B, P, D, out):
+    check(lib().sn_mean_pixels(_ptr(_req(feat)), B, P, D, _ptr(out), _stream()), "sn_mean_pixels")

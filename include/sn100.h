@@ -1,0 +1,185 @@
+/*
+ * sn100.h -- C ABI of libsn100.so: hand-written sm_100a CUDA for the StyleNet / NIC caption-decoder
+ * hot path.  This is the drop-in boundary below the PyTorch module surface:
+ * plain pointers and sizes only, no torch / ATen / pybind types.
+ *
+ * The reference (deryrahman/image-caption-emotion-indonesia) has NO native code and no FFI: every
+ * function below replaces a *library call site* that the reference makes through torch eager.  The
+ * reference call site each entry point replaces is cited as `file:line` (paths relative to the
+ * reference repository root).  INTEGRATION.md shows the reference-side binding (ctypes).
+ *
+ * Conventions
+ *   - every function returns int32: 0 ok; <0 argument/shape/alignment error detected before launch
+ *     (text via sn_last_error()); >0 a cudaError_t from the launch.  No exceptions, no exit().
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch caching allocator); the library
+ *     never allocates, frees or retains them.  Work space is caller-provided.
+ *   - row-major everywhere; activations are time-major packed [N, *] (N = sum of lengths; row of
+ *     (sample b, step t) = off[t] + b, off[t] = sum_{s<t} batch_sizes[s]); weights keep the
+ *     nn.Linear layout [out, in].
+ *   - kernels are launched on the `stream` argument (cudaStream_t passed as void*), asynchronously.
+ *   - no CPU fallback: a device that is not sm_100 is a hard error.
+ */
+#ifndef SN100_H_
+#define SN100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SN_VERSION 100
+
+/* GEMM operand layouts */
+#define SN_OP_NT 0 /* C[M,N] = A[M,K] * B[N,K]^T   (y = x W^T, nn.Linear forward)            */
+#define SN_OP_NN 1 /* C[M,N] = A[M,K] * B[K,N]     (dx = dy W)                                */
+#define SN_OP_TN 2 /* C[M,N] = A[K,M]^T * B[K,N]   (dW = dy^T x)                              */
+
+/* GEMM arithmetic */
+#define SN_PREC_F32 0   /* fp32 FFMA, exact-fp32 accumulation (fp32 parity mode, <=1e-5)       */
+#define SN_PREC_TF32X3 1 /* tcgen05 kind::tf32, 3-pass split (fp32-grade accuracy on tensor cores) */
+#define SN_PREC_BF16 2  /* tcgen05 kind::f16 bf16 operands, fp32 accumulate in TMEM            */
+
+/* recurrent cell kinds */
+#define SN_CELL_FACTORED 0 /* gate blocks (i,f,o,c~); h = o*c        stylenet/model.py:147-153  */
+#define SN_CELL_LSTM 1     /* gate blocks (i,f,g,o);  h = o*tanh(c)  nic/model.py:52,77         */
+
+int32_t sn_version(void);
+const char* sn_last_error(void);
+/* device attributes the host side needs (SM count, opt-in shared memory, compute capability) */
+int32_t sn_device_info(int32_t* sm_count, int32_t* smem_optin, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- K1: embedding gather + dropout + feature row, packed time-major ------------------------
+ * replaces self.B(captions); self.dropout(.); torch.cat((features.unsqueeze(1), .)) and the
+ * per-step slicing embeddings[:b_sz, i, :]      stylenet/model.py:166-171,182; nic/model.py:85-89,101
+ * row r -> sample row_b[r], step row_t[r].  has_feat: step 0 is the image feature row.
+ * tok_override (optional, [N]): if >= 0 the row embeds that id instead (scheduled sampling feedback,
+ * model.py:184) and is NOT dropped out.  X is [N, ldx] fp32; columns >= E are left untouched.
+ * dropout: keep-prob 1-p, scale 1/(1-p), counter-based RNG (seed, row, col); p = 0 disables. */
+int32_t sn_gather_pack_fwd(const int64_t* captions, int64_t cap_ld, const float* table, int64_t E,
+                           const float* features, int64_t feat_ld, int32_t has_feat,
+                           const int32_t* row_b, const int32_t* row_t, const int32_t* tok_override,
+                           int64_t N, float* X, int64_t ldx, float p_drop, uint64_t seed,
+                           void* stream);
+/* backward of the above: dtable[id] += dX*mask (atomic, duplicates accumulate like nn.Embedding's
+ * dense gradient), dfeatures[b] = dX[row(b,0)] (may be NULL). */
+int32_t sn_gather_pack_bwd(const int64_t* captions, int64_t cap_ld, float* dtable, int64_t E,
+                           float* dfeatures, int64_t feat_ld, int32_t has_feat,
+                           const int32_t* row_b, const int32_t* row_t, const int32_t* tok_override,
+                           int64_t N, const float* dX, int64_t ldx, float p_drop, uint64_t seed,
+                           void* stream);
+
+/* ---- K2: GEMM (all nn.Linear call sites: V_g/S_*_g/U_g model.py:119-150, C model.py:189-194,
+ * encoder_att/decoder_att/f_beta/init_h/init_c model_att.py:59-61,192-193,283, LSTMCell's two
+ * addmm nic/model.py:77) and every matmul autograd derives from them.
+ * C = op(A) op(B) + bias[n] + beta*C, batched over `batch` groups with element strides.
+ * A,B,C dtype: fp32 for SN_PREC_F32; see sn_gemm_tc for the tensor-core operand formats. */
+int32_t sn_gemm(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, float beta,
+                int32_t batch, int64_t strideA, int64_t strideB, int64_t strideC, int64_t strideBias,
+                void* stream);
+/* column sums (bias gradients): out[n] = sum_m X[m,n] + beta*out[n] */
+int32_t sn_colsum(const float* X, int64_t M, int64_t N, int64_t ldx, float* out, float beta,
+                  void* stream);
+
+/* ---- K3: persistent recurrence (W_hh h + gates + cell), forward and reverse-time backward -----
+ * replaces the hot loop stylenet/model.py:180-187 with forward_step's W_g(h_t)+sigmoid/tanh+cell
+ * (model.py:147-153) resp. nn.LSTMCell (nic/model.py:77), for steps t0 <= t < t1.
+ *   XP    [N,4H]  time-parallel input projection incl. its biases (U(S(V x)) + bU  /  x W_ih^T + b_ih)
+ *   Whh   [4H,H]  W_i;W_f;W_o;W_c stacked (factored) / lstm.weight_hh
+ *   bhh   [4H]    recurrent bias (bW_i..bW_c stacked / lstm.bias_hh), may be NULL
+ *   h_init [B,H]  h before step t0 (NULL = zeros).  To continue a sequence at t0>0 pass the Hall rows
+ *                 of step t0-1 (Hall + offsets[t0-1]*H)
+ *   c_state [B,H] in/out: c before step t0 on entry (caller zero-fills / copies init_c), c after the
+ *                 last step of each sample on return
+ *   Hall  [N,H]   h_t per packed row (output; also the inter-SM exchange buffer)
+ *   Call  [N,H]   c_t per packed row (output, needed by backward; may be NULL for inference)
+ *   Hprev [N,H]   h_{t-1} per packed row (output, may be NULL) -- operand of dW_hh = dZ^T Hprev
+ *   gates [N,4H]  post-activation i,f,o,c~ (output, may be NULL for inference)
+ *   ws            >= sn_recur_ws_bytes() bytes of scratch; zeroed by the call itself */
+int64_t sn_recur_ws_bytes(int64_t B, int64_t T);
+int32_t sn_recur_fwd(int32_t cell, int64_t H, int64_t B, const int32_t* batch_sizes,
+                     const int32_t* offsets, int32_t t0, int32_t t1, const float* XP,
+                     const float* Whh, const float* h_init, const float* bhh, float* Hall,
+                     float* Call, float* Hprev, float* gates, float* c_state, void* ws,
+                     void* stream);
+/* reverse-time backward for steps t1 > t >= t0.
+ *   dHall [N,H]   dL/dh_t from everything downstream of the recurrence (vocab projection, attention)
+ *   dZ    [N,4H]  output: dL/d(pre-activation) = dXP (feeds dW_hh, dU, dS, dV, dB GEMMs)
+ *   dh_carry,dc_carry [B,H]  in/out: gradient flowing into h_{t1-1}.. from later steps (zeros at the
+ *                 end of the sequence); on return hold dL/dh_{t0-1}, dL/dc_{t0-1} */
+int32_t sn_recur_bwd(int32_t cell, int64_t H, int64_t B, const int32_t* batch_sizes,
+                     const int32_t* offsets, int32_t t0, int32_t t1, const float* Whh,
+                     const float* c_init, const float* Call, const float* gates, const float* dHall,
+                     float* dZ, float* dh_carry, float* dc_carry, void* ws, void* stream);
+
+/* ---- K5/K6: log-softmax + NLL (+ gradient) over logits, arg-max, top-5 ------------------------
+ * replaces nn.CrossEntropyLoss (train_multitask.py:134,383), output.max(1) (model.py:190) and
+ * utils.accuracy top-5 (utils.py:127-140).
+ * row_loss[N] = lse - logit[target]; dlogits = (softmax - onehot) * grad_scale (may alias logits, may
+ * be NULL); argmax[N] lowest index on ties (torch.max); top5hit[N] = 1 if fewer than 5 logits exceed
+ * the target's.  targets may be NULL (then only argmax is produced). */
+int32_t sn_softmax_nll(const float* logits, int64_t N, int64_t V, int64_t ld, const int64_t* targets,
+                       float* row_loss, float* dlogits, int64_t ldd, float grad_scale,
+                       int64_t* argmax, int32_t* top5hit, void* stream);
+/* loss = scale * sum(row_loss[0..N)) (+ loss if accumulate), deterministic order, double sum */
+int32_t sn_reduce_sum(const float* x, int64_t N, float scale, float* out, int32_t accumulate,
+                      void* stream);
+
+/* ---- K7: fused clamp + Adam over flat parameter ranges ---------------------------------------
+ * replaces utils.clip_gradient (utils.py:51-60) + torch.optim.Adam.step (train_multitask.py:388-389)
+ * ranges: n_ranges x {offset,length} (int64 pairs, HOST memory) into the flat p/g/m/v arrays;
+ * step_size[r] = lr/(1-beta1^t), bc2_sqrt[r] = sqrt(1-beta2^t) per range (HOST arrays).
+ * torch op order: m.lerp_(g,1-b1); v.mul_(b2).addcmul_(g,g,1-b2); p.addcdiv_(m, sqrt(v)/bc2_sqrt+eps, -step_size) */
+int32_t sn_adam_clamp(float* p, float* g, float* m, float* v, int32_t n_ranges,
+                      const int64_t* ranges, const float* step_size, const float* bc2_sqrt,
+                      float beta1, float beta2, float eps, float clip, void* stream);
+
+/* ---- K4: soft attention step (scores -> softmax over pixels -> context -> f_beta gate) ----------
+ * replaces Attention.forward after the hoisted encoder_att GEMM (model_att.py:61-70) and the gate
+ * multiply (model_att.py:283-284) for one time step over nb samples.
+ *   att1 [B,P,A] (= encoder_att(features), time-invariant), att2 [nb,A] (= decoder_att(h)),
+ *   feat [B,P,D], wfull [A], bfull scalar, gate_pre [nb,D] (= f_beta(h), pre-sigmoid)
+ *   alpha [nb,P] out, ctx [nb, ldc] out = sigmoid(gate_pre) * sum_p alpha_p feat_p */
+int32_t sn_att_step_fwd(const float* att1, const float* att2, const float* feat, const float* wfull,
+                        float bfull, const float* gate_pre, int64_t nb, int64_t P, int64_t A,
+                        int64_t D, float* alpha, int64_t ld_alpha, float* ctx, int64_t ldc,
+                        void* stream);
+/* backward of one attention step.  Inputs as forward plus dctx [nb, ldc] and dalpha_extra [nb,P]
+ * (gradient of the doubly-stochastic regulariser, may be NULL).  Outputs: datt2 [nb,A], dgate_pre
+ * [nb,D], datt1 [B,P,A] ACCUMULATED (+=), dwfull [A] ACCUMULATED via atomics, dfeat (may be NULL)
+ * ACCUMULATED. */
+int32_t sn_att_step_bwd(const float* att1, const float* att2, const float* feat, const float* wfull,
+                        float bfull, const float* gate_pre, const float* alpha, int64_t ld_alpha,
+                        const float* dctx, int64_t ldc, const float* dalpha_extra, int64_t ld_da,
+                        int64_t nb, int64_t P, int64_t A, int64_t D, float* datt2, float* dgate_pre,
+                        float* datt1, float* dwfull, float* dfeat, void* stream);
+/* mean over pixels: out[b,d] = mean_p feat[b,p,d]   (model_att.py:191) */
+int32_t sn_mean_pixels(const float* feat, int64_t B, int64_t P, int64_t D, float* out, void* stream);
+
+/* ---- K8: beam / greedy decode bookkeeping -----------------------------------------------------
+ * replaces log_softmax + running-score add + topk + index arithmetic + the host-side completion loop
+ * of sample() (stylenet/model.py:232-285; model_att.py:364-417; nic/model.py:145-198) for a BATCH of
+ * images, one step, with no host synchronisation.  Rows of image i are [i*kmax, (i+1)*kmax); the first
+ * k_live[i] rows are its live beams in top-k order.  L = max_len + 2 ints per sequence.
+ *   logits [n_img*kmax, ld]   this step's C(h) for every row (dead rows ignored)
+ *   k_live [n_img]            in/out live beam count (k shrinks as beams finish; 0 = image finished)
+ *   run_score/prev_word/src_row [n_img*kmax]   in/out running log-prob, the word to feed next, and the
+ *                             row whose (h,c) the beam continues from (caller gathers state with it)
+ *   cur_buf [n_img], seqs [2][n_img*kmax][L]    double-buffered partial sequences
+ *   done_seq/done_len/done_score/n_done         finished beams in completion order
+ *   out_seq [n_img][L], out_len [n_img]         final result when the image finishes: first arg-max of
+ *                             the un-normalised scores of finished beams, or [end] if none finished
+ *   n_unfinished [1]          decremented once per image when it finishes (poll to stop early)
+ * step counts from 1; an image finishes when k reaches 0 or after step > max_len (model.py:273,283). */
+int32_t sn_beam_step(const float* logits, int64_t ld, int64_t V, int32_t n_img, int32_t kmax,
+                     int32_t step, int32_t max_len, int32_t end_token, int32_t* k_live,
+                     float* run_score, int32_t* prev_word, int32_t* src_row, int32_t* cur_buf,
+                     int32_t* seqs, int32_t* done_seq, int32_t* done_len, float* done_score,
+                     int32_t* n_done, int32_t* out_seq, int32_t* out_len, int32_t* n_unfinished,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SN100_H_ */

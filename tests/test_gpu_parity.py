@@ -1,0 +1,223 @@
+"""Module-level parity (GPU): the drop-in decoders, through the C ABI, against
+ (a) the committed golden vectors produced by the unmodified reference (tests/golden/*.npz), and
+ (b) the CPU oracle port on fresh seeded inputs at the BASELINE sizes.
+Tolerances (BASELINE.json north_star): fp32 mode loss / logits / gradients <= 1e-5 relative (rel-L2 per
+tensor); greedy / beam token ids bit-exact."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import CASES, build_port, load_golden, rel_l2, sd_from
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def build_cuda(name, rec, prefix="sd.", dropout=0.0):
+    import icei_b200 as sn
+    V, E, H, F, A, D = (int(rec["meta." + k]) for k in ("V", "E", "H", "F", "A", "D"))
+    if name == "factored":
+        m = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=dropout, max_seq_length=12)
+    elif name == "nic":
+        m = sn.DecoderRNN(E, H, V, 1, dropout=dropout, max_seq_length=12)
+    elif name == "factored_att":
+        m = sn.DecoderFactoredLSTMAtt(A, E, H, F, V, 1, feature_size=D, dropout=dropout, max_seq_length=12)
+    else:
+        m = sn.DecoderRNNAtt(A, E, H, V, 1, feature_size=D, dropout=dropout, max_seq_length=12)
+    m.load_state_dict(sd_from(rec, prefix, torch.float32))
+    return m.cuda()
+
+
+def _inputs(rec):
+    cap = torch.from_numpy(rec["in.captions"]).cuda()
+    lens = [int(x) for x in rec["in.lengths"]]
+    feats = torch.from_numpy(rec["in.features"]).float().cuda()
+    return cap, lens, feats
+
+
+def _fwd(dec, rec, tf, mode, att, feats):
+    from oracle import port
+    cap, lens, _ = _inputs(rec)
+    kw = {} if mode is None else {"mode": mode}
+    random.seed(1234)
+    if att:
+        l1 = [l - 1 for l in lens]
+        out, alphas = dec(cap[:, :-1], l1, feats, teacher_forcing_ratio=tf, **kw)
+        tgt = port.pack_targets(cap[:, 1:].cpu(), l1).cuda()
+        loss = port.caption_loss(out, tgt, alphas)
+        return out, alphas, loss
+    out = dec(cap, lens, feats, teacher_forcing_ratio=tf, **kw)
+    tgt = port.pack_targets(cap.cpu(), lens).cuda()
+    return out, None, port.caption_loss(out, tgt)
+
+
+def _nonatt_cases():
+    return [n for n in CASES if not CASES[n][0]]
+
+
+def _cases_available():
+    import icei_b200 as sn
+    return [n for n in CASES if (not CASES[n][0]) or hasattr(sn, "DecoderFactoredLSTMAtt")]
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_golden_forward_backward(name):
+    if name not in _cases_available():
+        pytest.skip("attention decoders not built yet")
+    att, modes = CASES[name]
+    rec = load_golden(name)
+    dec = build_cuda(name, rec)
+    dec.train()
+    for mode in modes:
+        tag = "" if mode is None else "." + mode
+        dec.zero_grad()
+        _, _, feats0 = _inputs(rec)
+        feats = feats0.clone().requires_grad_(not att)
+        out, alphas, loss = _fwd(dec, rec, 1.0, mode, att, feats)
+        loss.backward()
+        assert rel_l2(out.detach().cpu(), rec["tf1.logits" + tag]) < TOL
+        assert abs(loss.item() - float(rec["tf1.loss" + tag])) < TOL * abs(float(rec["tf1.loss" + tag]))
+        if att:
+            assert rel_l2(alphas.detach().cpu(), rec["tf1.alphas" + tag]) < TOL
+        else:
+            assert rel_l2(feats.grad.cpu(), rec["tf1.dfeatures" + tag]) < TOL
+        pre = "tf1.grad%s." % tag
+        got = {n for n, p in dec.named_parameters() if p.grad is not None}
+        assert got == {k[len(pre):] for k in rec if k.startswith(pre)}, "set of parameters with a gradient"
+        for n, p in dec.named_parameters():
+            if p.grad is None:
+                continue
+            g = rec[pre + n]
+            if n.endswith("full_att.bias"):
+                assert float(p.grad.abs().max()) < 1e-6     # true gradient is exactly 0
+            else:
+                assert rel_l2(p.grad.cpu(), g) < TOL, n
+        # greedy validation path (tf = 0): logits and bit-exact arg-max ids
+        with torch.no_grad():
+            out0, _, _ = _fwd(dec, rec, 0.0, mode, att, feats0)
+        assert rel_l2(out0.cpu(), rec["tf0.logits" + tag]) < TOL
+        assert np.array_equal(out0.argmax(1).cpu().numpy(), rec["tf0.argmax" + tag])
+        # scheduled sampling with the same coin stream
+        dec.zero_grad()
+        out5, _, loss5 = _fwd(dec, rec, 0.5, mode, att, feats0)
+        loss5.backward()
+        assert rel_l2(out5.detach().cpu(), rec["tf05.logits" + tag]) < TOL
+        pre5 = "tf05.grad%s." % tag
+        for n, p in dec.named_parameters():
+            if p.grad is not None and not n.endswith("full_att.bias"):
+                assert rel_l2(p.grad.cpu(), rec[pre5 + n]) < TOL, n
+    if name == "factored":
+        cap, lens, _ = _inputs(rec)
+        l1 = [l - 1 for l in lens]
+        random.seed(1234)
+        outl = dec(cap[:, :-1], l1, None, teacher_forcing_ratio=1.0, mode="sad")
+        assert rel_l2(outl.detach().cpu(), rec["lang.logits.sad"]) < TOL
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_golden_fused_loss_and_adam(name):
+    """forward_loss (fused NLL, no autograd) + FusedClampAdam with the reference's two-optimizer,
+    alternating-mode schedule == reference clip_gradient + torch.optim.Adam after 3 steps."""
+    if name not in _cases_available():
+        pytest.skip("attention decoders not built yet")
+    import icei_b200 as sn
+    att, modes = CASES[name]
+    rec = load_golden(name)
+    dec = build_cuda(name, rec)
+    dec.train()
+    cap, lens, feats = _inputs(rec)
+    opt_a = sn.FusedClampAdam(dec, lr=2e-4, grad_clip=0.5)
+    opt_b = sn.FusedClampAdam(dec, lr=5e-4, grad_clip=0.5)
+    loss = None
+    for opt, mode in [(opt_a, modes[0]), (opt_b, modes[-1]), (opt_a, modes[0])]:
+        kw = {} if mode is None else {"mode": mode}
+        dec.zero_grad()
+        random.seed(1234)
+        if att:
+            l1 = [l - 1 for l in lens]
+            loss, _ = dec.forward_loss(cap[:, :-1], l1, feats, targets=None, full_captions=cap, **kw)
+        else:
+            loss, _ = dec.forward_loss(cap, lens, feats, **kw)
+        opt.step()
+    assert abs(loss.item() - float(rec["adam3.loss_last"])) < TOL * abs(float(rec["adam3.loss_last"]))
+    for k, v in dec.state_dict().items():
+        assert rel_l2(v.cpu(), rec["adam3.sd." + k]) < 2e-6, k
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_golden_decode_ids_bit_exact(name):
+    if name not in _cases_available():
+        pytest.skip("attention decoders not built yet")
+    att, modes = CASES[name]
+    rec = load_golden(name)
+    dec = build_cuda(name, rec, prefix="sharp.sd.")
+    dec.eval()
+    _, _, feats = _inputs(rec)
+    with torch.no_grad():
+        out0, _, _ = _fwd(dec, rec, 0.0, modes[-1], att, feats)
+    assert np.array_equal(out0.argmax(1).cpu().numpy(), rec["sharp.tf0.argmax"])
+    kw = {} if modes[-1] is None else {"mode": modes[-1]}
+    for key in [k for k in rec if k.startswith("sample.")]:
+        _, variant, img, kk = key.split(".")
+        img, kk = int(img[3:]), int(kk[1:])
+        extra = dict(kw)
+        if variant == "app":
+            extra["feed_image"] = True
+        ids = dec.sample(feats[img].unsqueeze(0), 1, 2, k=kk, **extra)
+        assert ids.dtype == torch.int64 and ids.dim() == 2 and ids.shape[0] == 1
+        assert np.array_equal(ids.cpu().numpy(), rec[key]), key
+
+
+@pytest.mark.parametrize("which", ["factored", "nic"])
+def test_oracle_parity_baseline_size(which):
+    """Configs 1 and 2 of BASELINE.json at full size against the CPU oracle port (fp32 oracle run in
+    float64 for a noise-free target): loss, logits, every gradient <= 1e-5."""
+    import icei_b200 as sn
+    from oracle import port
+    V, E, H, F, T = 10000, 300, 512, 512, 20
+    B = 96 if which == "factored" else 64
+    torch.manual_seed(0)
+    torch.set_default_dtype(torch.float64)
+    try:
+        if which == "factored":
+            ref = port.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0)
+        else:
+            ref = port.DecoderRNN(E, H, V, 1, dropout=0.0)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    if which == "factored":
+        dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0)
+        kw = {"mode": "happy"}
+    else:
+        dec = sn.DecoderRNN(E, H, V, 1, dropout=0.0)
+        kw = {}
+    dec.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    dec = dec.cuda().train()
+    ref.train()
+    cap, lens, feats = port.synthetic_batch(B, T, V, E=E, ragged=True, seed=1)
+    tgt = port.pack_targets(cap, lens)
+    out_ref = ref(cap, lens, feats.double(), teacher_forcing_ratio=1.0, **kw)
+    loss_ref = port.caption_loss(out_ref, tgt)
+    ref.zero_grad(); loss_ref.backward()
+    out = dec(cap.cuda(), lens, feats.cuda(), teacher_forcing_ratio=1.0, **kw)
+    loss = port.caption_loss(out, tgt.cuda())
+    dec.zero_grad(); loss.backward()
+    assert rel_l2(out.detach().cpu(), out_ref.detach()) < TOL
+    assert abs(loss.item() - loss_ref.item()) < TOL * abs(loss_ref.item())
+    gref = {n: p.grad for n, p in ref.named_parameters()}
+    for n, p in dec.named_parameters():
+        if gref[n] is None:
+            assert p.grad is None, n
+        else:
+            assert rel_l2(p.grad.cpu(), gref[n]) < TOL, n
+    # fused path gives the same loss and gradients as the autograd drop-in path
+    g_auto = {n: p.grad.clone() for n, p in dec.named_parameters() if p.grad is not None}
+    dec.zero_grad()
+    loss2, stats = dec.forward_loss(cap.cuda(), lens, feats.cuda(), **kw)
+    assert abs(loss2.item() - loss_ref.item()) < TOL * abs(loss_ref.item())
+    for n, p in dec.named_parameters():
+        if p.grad is not None:
+            assert rel_l2(p.grad.cpu(), g_auto[n].cpu()) < 1e-6, n
+    assert torch.equal(stats["argmax"].cpu(), out_ref.argmax(1))
