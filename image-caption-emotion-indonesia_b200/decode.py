@@ -120,3 +120,61 @@ def beam_sample(dec, features, start_token, end_token, k, mode, feed_image, sync
         if sync_every and step % sync_every == 0 and int(st.n_unfinished.item()) == 0:
             break
     return st.results()
+
+
+@torch.no_grad()
+def beam_sample_att(dec, features, start_token, end_token, k, mode, sync_every=4):
+    """Attention beam search (stylenet/model_att.py:307-426) for n_img images: features
+    [n_img, S, S, D] (or [n_img, P, D]).  The feature map and the hoisted att1 are stored once per image;
+    live beams index them through ``row_img`` instead of expanding them k times."""
+    emb = dec._emb()
+    E = emb.weight.shape[1]
+    dev = emb.weight.device
+    ops.lib()
+    dec.arena()
+    D, A, H = dec.feature_size, dec.attention_size, dec.hidden_size
+    feats = features.detach().to(dev).float()
+    n_img = feats.shape[0] if feats.dim() >= 3 else 1
+    feats = feats.reshape(n_img, -1, D).contiguous()
+    P = feats.shape[1]
+    att = dec._att_module(mode)
+    st = BeamState(n_img, k, dec.max_seq_length, start_token, dev)
+    R = st.R
+    f32 = dict(dtype=torch.float32, device=dev)
+    h0, c0 = dec.init_hidden_state(feats)
+    h = h0.repeat_interleave(k, 0).contiguous()
+    c = c0.repeat_interleave(k, 0).contiguous()
+    att1 = ops.linear_nt(feats.view(n_img * P, D), att.encoder_att.weight, att.encoder_att.bias)
+    # per-row views of the per-image tensors (beams of one image share its rows)
+    feats_r = feats.repeat_interleave(k, 0).contiguous()
+    att1_r = att1.view(n_img, P, A).repeat_interleave(k, 0).contiguous()
+    h_new = torch.empty_like(h)
+    out = dec._out()
+    V = out.weight.shape[0]
+    logits = torch.empty(R, V, **f32)
+    X = torch.empty(R, E + D, **f32)
+    att2 = torch.empty(R, A, **f32)
+    gate_pre = torch.empty(R, D, **f32)
+    alpha = torch.empty(R, P, **f32)
+    ctx = _StepCtx()
+    ctx.XP = torch.empty(R, 4 * H, **f32)
+    row_img = torch.zeros(R, dtype=torch.int32, device=dev)
+    dummy_cap = torch.zeros(1, 1, dtype=torch.int64, device=dev)
+    bs1, off1 = _i32(dev, [R]), _i32(dev, [0])
+    Whh, bhh = dec._recurrent_weights()
+    wfull = att.full_att.weight.view(-1)
+    for step in range(1, dec.max_seq_length + 2):
+        ops.gather_pack_fwd(dummy_cap, emb.weight, None, False, row_img, row_img, st.prev_word, R, X, 0.0, 0)
+        ops.gemm(ops.OP_NT, h, att.decoder_att.weight, att2, R, A, H, H, H, A, bias=att.decoder_att.bias)
+        ops.gemm(ops.OP_NT, h, dec.f_beta.weight, gate_pre, R, D, H, H, H, D, bias=dec.f_beta.bias)
+        ops.att_step_fwd(att1_r, att2, feats_r, wfull, 0.0, gate_pre, R, P, A, D, alpha, P, X[:, E:], E + D)
+        dec._input_projection(ctx, X, mode, 0, R)
+        ops.recur_fwd(dec.cell, H, R, bs1, off1, 0, 1, ctx.XP, Whh, bhh, h, h_new, None, None, None, c)
+        ops.gemm(ops.OP_NT, h_new, out.weight, logits, R, V, H, H, H, V, bias=out.bias)
+        st.step(logits, step, end_token)
+        idx = st.src_row.long()
+        h = h_new.index_select(0, idx)
+        c = c.index_select(0, idx)
+        if sync_every and step % sync_every == 0 and int(st.n_unfinished.item()) == 0:
+            break
+    return st.results()

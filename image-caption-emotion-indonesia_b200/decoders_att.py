@@ -1,0 +1,569 @@
+"""Soft-attention decoders: DecoderFactoredLSTMAtt (stylenet/model_att.py:73-426) and DecoderRNNAtt
+(nic/model_att.py:72-306) on the sm_100a kernels.
+
+What is time-parallel is hoisted out of the step loop (identical results):
+  * att1 = encoder_att(features) -- the reference recomputes it every step (model_att.py:59)
+  * the embedding columns of V (resp. W_ih): the chain is linear, so V x = V_emb emb + V_ctx ctx
+  * every weight gradient (one GEMM over all packed rows after the reverse-time loop)
+Per step only what depends on h_{t-1} runs: decoder_att / f_beta GEMMs, the fused attention kernel (K4),
+the context columns of the input projection, and one recurrence step (K3).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .decoders import GATES, STYLES, _Ctx, _DecoderBase, _ref_init, style_attr
+from .packing import get_plan
+
+
+def att_attr(style):
+    return "attention" if style == "factual" else "attention_" + style
+
+
+class Attention(nn.Module):
+    """Parameter container with the reference's names (model_att.py:32-49); the arithmetic of its
+    forward (model_att.py:51-70) runs in sn_att_step_fwd."""
+
+    def __init__(self, encoder_dim, decoder_dim, attention_dim):
+        super().__init__()
+        self.encoder_att = nn.Linear(encoder_dim, attention_dim)
+        self.decoder_att = nn.Linear(decoder_dim, attention_dim)
+        self.full_att = nn.Linear(attention_dim, 1)
+
+    def forward(self, encoder_out, decoder_hidden):
+        """(attention_weighted_encoding [b,D], alpha [b,P]) for one step, on the kernels."""
+        b, P, D = encoder_out.shape
+        A = self.encoder_att.weight.shape[0]
+        dev = encoder_out.device
+        with torch.no_grad():
+            feat = encoder_out.detach().float().contiguous()
+            att1 = ops.linear_nt(feat.view(b * P, D), self.encoder_att.weight, self.encoder_att.bias)
+            att2 = ops.linear_nt(decoder_hidden.detach().float().contiguous(), self.decoder_att.weight,
+                                 self.decoder_att.bias)
+            alpha = torch.empty(b, P, dtype=torch.float32, device=dev)
+            ctx = torch.empty(b, D, dtype=torch.float32, device=dev)
+            big = torch.full((b, D), 1e4, dtype=torch.float32, device=dev)   # sigmoid(1e4) == 1: ungated
+            ops.att_step_fwd(att1, att2, feat, self.full_att.weight.view(-1), float(self.full_att.bias.item()),
+                             big, b, P, A, D, alpha, P, ctx, D)
+        return ctx, alpha
+
+
+class _HiddenAttFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, features, dec, plan, captions, coins, mode, save):
+        c = dec._run_forward_att(plan, captions, features, coins, mode, save)
+        ctx.dec, ctx.c = dec, c
+        ctx.need_dfeat = features.requires_grad
+        return c.Hall, c.alphas
+
+    @staticmethod
+    def backward(ctx, dHall, dAlphas):
+        dec, c = ctx.dec, ctx.c
+        gbuf = dec._grad_target(c.grad_names)
+        dfeat = dec._run_backward_att(c, dHall.contiguous(), dAlphas, gbuf, ctx.need_dfeat)
+        dec._publish(c.grad_names, gbuf)
+        return None, dfeat, None, None, None, None, None, None
+
+
+class _AttBase(_DecoderBase):
+    """Host logic shared by the two attention decoders."""
+
+    def _att_module(self, mode):
+        raise NotImplementedError
+
+    def _att_prefix(self, mode):
+        raise NotImplementedError
+
+    def init_hidden_state(self, feature):
+        """(h0, c0) from the mean feature (model_att.py:185-194) on the kernels."""
+        with torch.no_grad():
+            f = feature.detach().float().contiguous()
+            B, P, D = f.shape
+            mean = torch.empty(B, D, dtype=torch.float32, device=f.device)
+            ops.mean_pixels(f, B, P, D, mean)
+            h = ops.linear_nt(mean, self.init_h.weight, self.init_h.bias)
+            c = ops.linear_nt(mean, self.init_c.weight, self.init_c.bias)
+        return h, c
+
+    # ---- forward -----------------------------------------------------------------------------------
+    def _run_forward_att(self, plan, captions, features, coins, mode, save):
+        a = self.arena()
+        dev = captions.device
+        d = plan.dev(dev)
+        H, N, B, T = self.hidden_size, plan.N, plan.B, plan.T
+        emb = self._emb()
+        E = emb.weight.shape[1]
+        D, A = self.feature_size, self.attention_size
+        feats = features.detach()
+        if feats.dtype != torch.float32:
+            feats = feats.float()
+        feats = feats.reshape(B, -1, D).contiguous()
+        P = feats.shape[1]
+        att = self._att_module(mode)
+        c = _Ctx()
+        c.plan, c.mode, c.captions, c.has_feat = plan, mode, captions, False
+        c.feats, c.P = feats, P
+        c.p_drop = float(self.dropout.p) if self.training else 0.0
+        self.__dict__["_calls"] = self.__dict__.get("_calls", 0) + 1
+        c.seed = (int(self.__dict__.get("_seed", 0x5EED)) * 1000003 + self._calls) & 0xFFFFFFFFFFFF
+        f32 = dict(dtype=torch.float32, device=dev)
+        # hoisted, time-invariant pieces
+        c.mean = torch.empty(B, D, **f32)
+        ops.mean_pixels(feats, B, P, D, c.mean)
+        h0 = ops.linear_nt(c.mean, self.init_h.weight, self.init_h.bias)
+        c.c0 = ops.linear_nt(c.mean, self.init_c.weight, self.init_c.bias)
+        c.att1 = ops.linear_nt(feats.view(B * P, D), att.encoder_att.weight, att.encoder_att.bias)
+        all_tf = all(coins)
+        c.tok_override = None if all_tf else torch.full((N,), -1, dtype=torch.int32, device=dev)
+        c.X = torch.empty(N, E, **f32)
+        ops.gather_pack_fwd(captions, emb.weight, None, False, d["row_b"], d["row_t"], None, N, c.X, c.p_drop, c.seed)
+        c.XP = torch.empty(N, 4 * H, **f32)
+        self._proj_embed_part(c, 0, N)
+        c.CTX = torch.empty(N, D, **f32)
+        c.att2 = torch.empty(N, A, **f32)
+        c.gate_pre = torch.empty(N, D, **f32)
+        Tmax = max(plan.lengths)
+        c.alphas = torch.zeros(B, Tmax, P, **f32)
+        c.Hall = torch.empty(N, H, **f32)
+        c.Call = torch.empty(N, H, **f32) if save else None
+        c.Hprev = torch.empty(N, H, **f32)
+        c.gates = torch.empty(N, 4 * H, **f32) if save else None
+        c_state = c.c0.clone()
+        Whh, bhh = self._recurrent_weights()
+        wfull = att.full_att.weight.view(-1)
+        c.bfull = float(att.full_att.bias.item()) if not save else None
+        bfull_t = att.full_att.bias
+        out = self._out()
+        V = out.weight.shape[0]
+        pred = captions[:, 0].to(torch.int32).contiguous()
+        am = torch.empty(B, dtype=torch.int64, device=dev)
+        # the scalar full_att bias shifts every score of a row equally and cancels in the softmax
+        # (model_att.py:63-65): it is passed as 0 to avoid a device->host read on the hot path.
+        for t in range(T):
+            n, r0 = plan.bs[t], plan.off[t]
+            hprev = h0 if t == 0 else c.Hall[plan.off[t - 1]:plan.off[t - 1] + n]
+            if not coins[t]:
+                if t > 0:
+                    bp, rp = plan.bs[t - 1], plan.off[t - 1]
+                    lg = torch.empty(bp, V, **f32)
+                    ops.gemm(ops.OP_NT, c.Hall, out.weight, lg, bp, V, H, H, H, V, bias=out.bias, a_off=rp * H)
+                    ops.softmax_nll(lg, bp, V, argmax=am)
+                    pred = am[:bp].to(torch.int32)
+                c.tok_override[r0:r0 + n] = pred[:n]
+                ops.gather_pack_fwd(captions, emb.weight, None, False, d["row_b"], d["row_t"], c.tok_override, n,
+                                    c.X, c.p_drop, c.seed, row_off=r0)
+                self._proj_embed_part(c, r0, n)
+            ops.gemm(ops.OP_NT, hprev, att.decoder_att.weight, c.att2, n, A, H, H, H, A, bias=att.decoder_att.bias,
+                     c_off=r0 * A)
+            ops.gemm(ops.OP_NT, hprev, self.f_beta.weight, c.gate_pre, n, D, H, H, H, D, bias=self.f_beta.bias,
+                     c_off=r0 * D)
+            ops.att_step_fwd(c.att1, c.att2[r0:], feats, wfull, 0.0, c.gate_pre[r0:], n, P, A, D,
+                             c.alphas[:, t], Tmax * P, c.CTX[r0:], D)
+            self._proj_step(c, r0, n)
+            ops.recur_fwd(self.cell, H, B, d["bs"], d["off"], t, t + 1, c.XP, Whh, bhh, hprev, c.Hall, c.Call,
+                          c.Hprev, c.gates, c_state)
+        c.grad_names = self._seq_grad_names(mode)
+        return c
+
+    # ---- backward ----------------------------------------------------------------------------------
+    def _run_backward_att(self, c, dHall, dAlphas, gbuf, need_dfeat):
+        a = self.arena()
+        plan = c.plan
+        dev = dHall.device
+        d = plan.dev(dev)
+        H, N, B, T = self.hidden_size, plan.N, plan.B, plan.T
+        D, A, P = self.feature_size, self.attention_size, c.P
+        emb = self._emb()
+        E = emb.weight.shape[1]
+        att = self._att_module(c.mode)
+        pre = self._att_prefix(c.mode)
+        f32 = dict(dtype=torch.float32, device=dev)
+        Whh, _ = self._recurrent_weights()
+        wfull = att.full_att.weight.view(-1)
+        dZ = torch.empty(N, 4 * H, **f32)
+        dh = torch.zeros(B, H, **f32)
+        dc = torch.zeros(B, H, **f32)
+        c.dCTX = torch.empty(N, D, **f32)
+        datt2 = torch.empty(N, A, **f32)
+        dgate = torch.empty(N, D, **f32)
+        datt1 = torch.zeros(B * P, A, **f32)
+        gwf = self._gview(gbuf, [pre + "full_att.weight"], (A,))
+        gwf.zero_()
+        self._gview(gbuf, [pre + "full_att.bias"], (1,)).zero_()   # exactly zero (softmax shift invariance)
+        dfeat = torch.zeros(B, P, D, **f32) if need_dfeat else None
+        Tmax = c.alphas.shape[1]
+        dAl = None
+        if dAlphas is not None:
+            dAl = dAlphas.contiguous()
+        self._proj_bwd_begin(c, N)
+        for t in range(T - 1, -1, -1):
+            n, r0 = plan.bs[t], plan.off[t]
+            ops.recur_bwd(self.cell, H, B, d["bs"], d["off"], t, t + 1, Whh, c.c0, c.Call, c.gates, dHall, dZ, dh, dc)
+            self._proj_step_bwd(c, dZ, r0, n)        # -> c.dCTX rows
+            ops.att_step_bwd(c.att1, c.att2[r0:], c.feats, wfull, 0.0, c.gate_pre[r0:], c.alphas[:, t], Tmax * P,
+                             c.dCTX[r0:], D, dAl[:, t] if dAl is not None else None, Tmax * P, n, P, A, D,
+                             datt2[r0:], dgate[r0:], datt1, gwf, dfeat)
+            # into h_{t-1}: through decoder_att and f_beta
+            ops.gemm(ops.OP_NN, datt2, att.decoder_att.weight, dh, n, H, A, A, H, H, beta=1.0, a_off=r0 * A)
+            ops.gemm(ops.OP_NN, dgate, self.f_beta.weight, dh, n, H, D, D, H, H, beta=1.0, a_off=r0 * D)
+        # time-batched weight gradients
+        gW, gbW = self._recurrent_grads(gbuf)
+        ops.gemm(ops.OP_TN, dZ, c.Hprev, gW, 4 * H, H, N, 4 * H, H, H)
+        ops.colsum(dZ, N, 4 * H, 4 * H, gbW)
+        ops.gemm(ops.OP_TN, datt2, c.Hprev, self._gview(gbuf, [pre + "decoder_att.weight"], (A, H)), A, H, N, A, H, H)
+        ops.colsum(datt2, N, A, A, self._gview(gbuf, [pre + "decoder_att.bias"], (A,)))
+        ops.gemm(ops.OP_TN, dgate, c.Hprev, self._gview(gbuf, ["f_beta.weight"], (D, H)), D, H, N, D, H, H)
+        ops.colsum(dgate, N, D, D, self._gview(gbuf, ["f_beta.bias"], (D,)))
+        ops.gemm(ops.OP_TN, datt1, c.feats.view(B * P, D), self._gview(gbuf, [pre + "encoder_att.weight"], (A, D)),
+                 A, D, B * P, A, D, D)
+        ops.colsum(datt1, B * P, A, A, self._gview(gbuf, [pre + "encoder_att.bias"], (A,)))
+        # init_h / init_c: dh, dc now hold dL/dh0, dL/dc0
+        ops.gemm(ops.OP_TN, dh, c.mean, self._gview(gbuf, ["init_h.weight"], (H, D)), H, D, B, H, D, D)
+        ops.colsum(dh, B, H, H, self._gview(gbuf, ["init_h.bias"], (H,)))
+        ops.gemm(ops.OP_TN, dc, c.mean, self._gview(gbuf, ["init_c.weight"], (H, D)), H, D, B, H, D, D)
+        ops.colsum(dc, B, H, H, self._gview(gbuf, ["init_c.bias"], (H,)))
+        dX = self._proj_weight_grads(c, dZ, gbuf)
+        gE = self._gview(gbuf, [self._emb_name()], emb.weight.shape)
+        gE.zero_()
+        ops.gather_pack_bwd(c.captions, gE, None, False, d["row_b"], d["row_t"], c.tok_override, N, dX, c.p_drop, c.seed)
+        if need_dfeat:
+            dmean = torch.empty(B, D, **f32)
+            ops.gemm(ops.OP_NN, dh, self.init_h.weight, dmean, B, D, H, H, D, D)
+            ops.gemm(ops.OP_NN, dc, self.init_c.weight, dmean, B, D, H, H, D, D, beta=1.0)
+            dfeat += (dmean / P).unsqueeze(1)
+            # through the hoisted encoder_att GEMM
+            ops.gemm(ops.OP_NN, datt1, att.encoder_att.weight, dfeat.view(B * P, D), B * P, D, A, A, D, D, beta=1.0)
+        return dfeat
+
+    # ---- public ------------------------------------------------------------------------------------
+    def _forward_att(self, captions, lengths, features, teacher_forcing_ratio, mode):
+        self._check_inputs(captions, features)
+        plan = get_plan(lengths)
+        if plan.B != captions.shape[0]:
+            raise RuntimeError("len(lengths) != batch size")
+        if plan.T > captions.shape[1]:
+            raise RuntimeError("lengths exceed the caption length")
+        coins = self._coins(plan.T, teacher_forcing_ratio)
+        captions = captions.contiguous()
+        save = torch.is_grad_enabled()
+        hall, alphas = _HiddenAttFn.apply(self._out().weight, features, self, plan, captions, coins, mode, save)
+        from .decoders import _LogitsFn
+        return _LogitsFn.apply(hall, self._out().weight, self), alphas
+
+    def forward_loss(self, captions, lengths, features, targets=None, teacher_forcing_ratio=1.0, mode="factual",
+                     backward=True, n_global=None, b_global=None, alpha_c=1.0, full_captions=None):
+        """Fused training entry point for the attention decoders: CE mean + alpha_c * mean((1-sum_t a)^2)
+        (stylenet/train_multitask_att.py:402-411), forward and backward without an autograd graph.
+        ``captions`` are the INPUT tokens (reference passes captions[:, :-1]); give the packed ``targets``
+        or ``full_captions`` (then targets = packed full_captions[:, 1:])."""
+        self._check_inputs(captions, features)
+        plan = get_plan(lengths)
+        coins = self._coins(plan.T, teacher_forcing_ratio)
+        captions = captions.contiguous()
+        dev = captions.device
+        with torch.no_grad():
+            c = self._run_forward_att(plan, captions, features, coins, mode, backward)
+            N, B, P = plan.N, plan.B, c.P
+            if targets is None:
+                if full_captions is None:
+                    raise ValueError("forward_loss: pass `targets` or `full_captions`")
+                d = plan.dev(dev)
+                targets = full_captions[d["row_b"].long(), d["row_t"].long() + 1].contiguous()
+            out = self._out()
+            V = out.weight.shape[0]
+            logits = self._vocab_logits(c.Hall)
+            row_loss = torch.empty(N, dtype=torch.float32, device=dev)
+            argmax = torch.empty(N, dtype=torch.int64, device=dev)
+            top5 = torch.empty(N, dtype=torch.int32, device=dev)
+            denom = float(n_global if n_global is not None else N)
+            ops.softmax_nll(logits, N, V, targets=targets, row_loss=row_loss, dlogits=logits if backward else None,
+                            grad_scale=1.0 / denom, argmax=argmax, top5hit=top5)
+            loss = torch.empty(1, dtype=torch.float32, device=dev)
+            ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
+            # doubly stochastic regulariser: tiny [B,P] reduction (plumbing-size torch ops)
+            bp = float((b_global if b_global is not None else B) * P)
+            resid = 1.0 - c.alphas.sum(dim=1)
+            loss += alpha_c * (resid * resid).sum() / bp
+            if backward:
+                dAl = (-2.0 * alpha_c / bp) * resid                       # d/d alpha[b,t,p], same for every t
+                dAl = dAl.unsqueeze(1).expand(B, c.alphas.shape[1], P).contiguous()
+                names = c.grad_names + list(self._out_names())
+                gbuf = self._grad_target(names)
+                dHall = self._vocab_backward(c.Hall, logits, gbuf)
+                dfeat = self._run_backward_att(c, dHall, dAl, gbuf, features.requires_grad)
+                self._publish(names, gbuf)
+                if dfeat is not None:
+                    dfeat = dfeat.view(features.shape)
+                    features.grad = dfeat if features.grad is None else features.grad + dfeat
+        return loss, {"argmax": argmax, "top5hit": top5, "n_tokens": N, "alphas": c.alphas}
+
+
+class DecoderFactoredLSTMAtt(_AttBase):
+    """Signature of stylenet/model_att.py:75-85."""
+
+    cell = ops.CELL_FACTORED
+
+    def __init__(self, attention_size, embed_size, hidden_size, factored_size, vocab_size, num_layers,
+                 feature_size=2048, bias=True, dropout=0.22, max_seq_length=40):
+        super().__init__()
+        if not bias:
+            raise NotImplementedError("bias=False is not supported by the fused path")
+        self.attention_size, self.feature_size = attention_size, feature_size
+        self.hidden_size, self.factored_size, self.embed_size = hidden_size, factored_size, embed_size
+        self.vocab_size, self.max_seq_length, self.num_layers = vocab_size, max_seq_length, num_layers
+        self.init_h = nn.Linear(feature_size, hidden_size)
+        self.init_c = nn.Linear(feature_size, hidden_size)
+        self.dropout = nn.Dropout(dropout)
+        self.attention = Attention(feature_size, hidden_size, attention_size)
+        self.B = nn.Embedding(vocab_size, embed_size)
+        self.f_beta = nn.Linear(hidden_size, feature_size)
+        for g in GATES:
+            setattr(self, "U_" + g, nn.Linear(factored_size, hidden_size, bias=bias))
+            setattr(self, style_attr("factual", g), nn.Linear(factored_size, factored_size, bias=bias))
+            setattr(self, "V_" + g, nn.Linear(embed_size + feature_size, factored_size, bias=bias))
+            setattr(self, "W_" + g, nn.Linear(hidden_size, hidden_size, bias=bias))
+        for s in STYLES[1:]:
+            setattr(self, att_attr(s), Attention(feature_size, hidden_size, attention_size))
+            for g in GATES:
+                setattr(self, style_attr(s, g), nn.Linear(factored_size, factored_size, bias=bias))
+        self.C = nn.Linear(hidden_size, vocab_size, bias=bias)
+        _ref_init(self, self.B, self.C)
+
+    # reuse the non-attention factored helpers
+    from .decoders import DecoderFactoredLSTM as _F
+    _stack = _F._stack
+    _style_stack = _F._style_stack
+    _recurrent_weights = _F._recurrent_weights
+    _recurrent_grads = _F._recurrent_grads
+    _input_projection = _F._input_projection
+    del _F
+
+    def _arena_groups(self):
+        groups = [["B.weight"]]
+        for pre in ("V_", "U_", "W_"):
+            groups.append([pre + g + ".weight" for g in GATES])
+            groups.append([pre + g + ".bias" for g in GATES])
+        for s in STYLES:
+            groups.append([style_attr(s, g) + ".weight" for g in GATES])
+            groups.append([style_attr(s, g) + ".bias" for g in GATES])
+        for s in STYLES:
+            p = att_attr(s) + "."
+            groups += [[p + "encoder_att.weight"], [p + "encoder_att.bias"], [p + "decoder_att.weight"],
+                       [p + "decoder_att.bias"], [p + "full_att.weight"], [p + "full_att.bias"]]
+        groups += [["init_h.weight"], ["init_h.bias"], ["init_c.weight"], ["init_c.bias"],
+                   ["f_beta.weight"], ["f_beta.bias"], ["C.weight"], ["C.bias"]]
+        return groups
+
+    def _emb(self):
+        return self.B
+
+    def _emb_name(self):
+        return "B.weight"
+
+    def _out(self):
+        return self.C
+
+    def _out_names(self):
+        return ("C.weight", "C.bias")
+
+    def _att_module(self, mode):
+        if mode not in STYLES:
+            raise ValueError("mode name wrong: %r (expected one of %s)" % (mode, STYLES))
+        return getattr(self, att_attr(mode))
+
+    def _att_prefix(self, mode):
+        return att_attr(mode) + "."
+
+    def _seq_grad_names(self, mode):
+        names = ["B.weight"]
+        for pre in ("V_", "U_", "W_"):
+            names += [pre + g + sfx for g in GATES for sfx in (".weight", ".bias")]
+        names += [style_attr(mode, g) + sfx for g in GATES for sfx in (".weight", ".bias")]
+        p = att_attr(mode) + "."
+        names += [p + n for n in ("encoder_att.weight", "encoder_att.bias", "decoder_att.weight", "decoder_att.bias",
+                                  "full_att.weight", "full_att.bias")]
+        names += ["init_h.weight", "init_h.bias", "init_c.weight", "init_c.bias", "f_beta.weight", "f_beta.bias"]
+        return names
+
+    # -- projection pieces: V x = V[:, :E] emb + V[:, E:] ctx ----------------------------------------------
+    def _proj_embed_part(self, c, r0, n):
+        H, F, E, D = self.hidden_size, self.factored_size, self.embed_size, self.feature_size
+        if r0 == 0 and n == c.X.shape[0]:
+            c.A1 = torch.empty(n, 4 * F, dtype=torch.float32, device=c.X.device)
+            c.A2 = torch.empty(n, 4 * F, dtype=torch.float32, device=c.X.device)
+        Vc, bV = self._stack("V_", (4 * F, E + D)), self._stack("V_", (4 * F,), bias=True)
+        ops.gemm(ops.OP_NT, c.X, Vc, c.A1, n, 4 * F, E, E, E + D, 4 * F, bias=bV, a_off=r0 * E, c_off=r0 * 4 * F)
+
+    def _proj_step(self, c, r0, n):
+        H, F, E, D = self.hidden_size, self.factored_size, self.embed_size, self.feature_size
+        Vc = self._stack("V_", (4 * F, E + D))
+        Sc, bS = self._style_stack(c.mode, (4 * F, F)), self._style_stack(c.mode, (4 * F,), bias=True)
+        Uc, bU = self._stack("U_", (4 * H, F)), self._stack("U_", (4 * H,), bias=True)
+        ops.gemm(ops.OP_NT, c.CTX, Vc, c.A1, n, 4 * F, D, D, E + D, 4 * F, beta=1.0, a_off=r0 * D, b_off=E,
+                 c_off=r0 * 4 * F)
+        ops.gemm(ops.OP_NT, c.A1, Sc, c.A2, n, F, F, 4 * F, F, 4 * F, bias=bS, batch=4, sA=F, sB=F * F, sC=F,
+                 sBias=F, a_off=r0 * 4 * F, c_off=r0 * 4 * F)
+        ops.gemm(ops.OP_NT, c.A2, Uc, c.XP, n, H, F, 4 * F, F, 4 * H, bias=bU, batch=4, sA=F, sB=H * F, sC=H,
+                 sBias=H, a_off=r0 * 4 * F, c_off=r0 * 4 * H)
+
+    def _proj_bwd_begin(self, c, N):
+        F = self.factored_size
+        c.dA2 = torch.empty(N, 4 * F, dtype=torch.float32, device=c.X.device)
+        c.dA1 = torch.empty(N, 4 * F, dtype=torch.float32, device=c.X.device)
+
+    def _proj_step_bwd(self, c, dZ, r0, n):
+        H, F, E, D = self.hidden_size, self.factored_size, self.embed_size, self.feature_size
+        Vc = self._stack("V_", (4 * F, E + D))
+        Sc = self._style_stack(c.mode, (4 * F, F))
+        Uc = self._stack("U_", (4 * H, F))
+        ops.gemm(ops.OP_NN, dZ, Uc, c.dA2, n, F, H, 4 * H, F, 4 * F, batch=4, sA=H, sB=H * F, sC=F,
+                 a_off=r0 * 4 * H, c_off=r0 * 4 * F)
+        ops.gemm(ops.OP_NN, c.dA2, Sc, c.dA1, n, F, F, 4 * F, F, 4 * F, batch=4, sA=F, sB=F * F, sC=F,
+                 a_off=r0 * 4 * F, c_off=r0 * 4 * F)
+        ops.gemm(ops.OP_NN, c.dA1, Vc, c.dCTX, n, D, 4 * F, 4 * F, E + D, D, a_off=r0 * 4 * F, b_off=E, c_off=r0 * D)
+
+    def _proj_weight_grads(self, c, dZ, gbuf):
+        H, F, E, D = self.hidden_size, self.factored_size, self.embed_size, self.feature_size
+        N = c.X.shape[0]
+        mode = c.mode
+        Vc = self._stack("V_", (4 * F, E + D))
+        gV, gbV = self._stack("V_", (4 * F, E + D), gbuf=gbuf), self._stack("V_", (4 * F,), gbuf=gbuf, bias=True)
+        gS, gbS = self._style_stack(mode, (4 * F, F), gbuf=gbuf), self._style_stack(mode, (4 * F,), gbuf=gbuf, bias=True)
+        gU, gbU = self._stack("U_", (4 * H, F), gbuf=gbuf), self._stack("U_", (4 * H,), gbuf=gbuf, bias=True)
+        ops.gemm(ops.OP_TN, dZ, c.A2, gU, H, F, N, 4 * H, 4 * F, F, batch=4, sA=H, sB=F, sC=H * F)
+        ops.colsum(dZ, N, 4 * H, 4 * H, gbU)
+        ops.gemm(ops.OP_TN, c.dA2, c.A1, gS, F, F, N, 4 * F, 4 * F, F, batch=4, sA=F, sB=F, sC=F * F)
+        ops.colsum(c.dA2, N, 4 * F, 4 * F, gbS)
+        ops.gemm(ops.OP_TN, c.dA1, c.X, gV, 4 * F, E, N, 4 * F, E, E + D)
+        ops.gemm(ops.OP_TN, c.dA1, c.CTX, gV, 4 * F, D, N, 4 * F, D, E + D, c_off=E)
+        ops.colsum(c.dA1, N, 4 * F, 4 * F, gbV)
+        dX = torch.empty(N, E, dtype=torch.float32, device=dZ.device)
+        ops.gemm(ops.OP_NN, c.dA1, Vc, dX, N, E, 4 * F, 4 * F, E + D, E)
+        return dX
+
+    # -- reference surface ----------------------------------------------------------------------------
+    def forward(self, captions, lengths, features, teacher_forcing_ratio=0.8, mode="factual"):
+        """(outputs [sum(lengths), V], alphas [B, max(lengths), P]) like model_att.py:238-305."""
+        self._att_module(mode)
+        return self._forward_att(captions, lengths, features, teacher_forcing_ratio, mode)
+
+    def forward_step(self, embedded, states, mode):
+        from .decode import single_step
+        return single_step(self, embedded, states, mode)
+
+    def sample(self, features, start_token, end_token, k=5, factual_limit=-1, mode="factual"):
+        """Beam search with attention, stylenet/model_att.py:307-426."""
+        from .decode import beam_sample_att
+        return beam_sample_att(self, features, start_token, end_token, k, mode)[0]
+
+
+class DecoderRNNAtt(_AttBase):
+    """Signature of nic/model_att.py:74-82."""
+
+    cell = ops.CELL_LSTM
+
+    def __init__(self, attention_size, embed_size, hidden_size, vocab_size, num_layers, feature_size=2048,
+                 dropout=0.22, max_seq_length=40):
+        super().__init__()
+        self.attention_size, self.feature_size = attention_size, feature_size
+        self.hidden_size, self.embed_size = hidden_size, embed_size
+        self.vocab_size, self.max_seq_length, self.num_layers = vocab_size, max_seq_length, num_layers
+        self.init_h = nn.Linear(feature_size, hidden_size)
+        self.init_c = nn.Linear(feature_size, hidden_size)
+        self.dropout = nn.Dropout(dropout)
+        self.attention = Attention(feature_size, hidden_size, attention_size)
+        self.embed = nn.Embedding(vocab_size, embed_size)
+        self.f_beta = nn.Linear(hidden_size, feature_size)
+        self.lstm = nn.LSTMCell(embed_size + feature_size, hidden_size, bias=True)
+        self.linear = nn.Linear(hidden_size, vocab_size)
+        _ref_init(self, self.embed, self.linear)
+
+    def _arena_groups(self):
+        p = "attention."
+        return [["embed.weight"], ["lstm.weight_ih"], ["lstm.weight_hh"], ["lstm.bias_ih"], ["lstm.bias_hh"],
+                [p + "encoder_att.weight"], [p + "encoder_att.bias"], [p + "decoder_att.weight"],
+                [p + "decoder_att.bias"], [p + "full_att.weight"], [p + "full_att.bias"],
+                ["init_h.weight"], ["init_h.bias"], ["init_c.weight"], ["init_c.bias"],
+                ["f_beta.weight"], ["f_beta.bias"], ["linear.weight"], ["linear.bias"]]
+
+    def _emb(self):
+        return self.embed
+
+    def _emb_name(self):
+        return "embed.weight"
+
+    def _out(self):
+        return self.linear
+
+    def _out_names(self):
+        return ("linear.weight", "linear.bias")
+
+    def _att_module(self, mode):
+        return self.attention
+
+    def _att_prefix(self, mode):
+        return "attention."
+
+    def _recurrent_weights(self):
+        self.arena()
+        return self.lstm.weight_hh, self.lstm.bias_hh
+
+    def _recurrent_grads(self, gbuf):
+        H = self.hidden_size
+        return self._gview(gbuf, ["lstm.weight_hh"], (4 * H, H)), self._gview(gbuf, ["lstm.bias_hh"], (4 * H,))
+
+    def _seq_grad_names(self, mode):
+        p = "attention."
+        return ["embed.weight", "lstm.weight_ih", "lstm.weight_hh", "lstm.bias_ih", "lstm.bias_hh"] + \
+            [p + n for n in ("encoder_att.weight", "encoder_att.bias", "decoder_att.weight", "decoder_att.bias",
+                             "full_att.weight", "full_att.bias")] + \
+            ["init_h.weight", "init_h.bias", "init_c.weight", "init_c.bias", "f_beta.weight", "f_beta.bias"]
+
+    def _input_projection(self, c, X, mode, r0, n):
+        """Full-width projection (used by forward_step / decode where the input is already [emb, ctx])."""
+        H = self.hidden_size
+        Ein = X.shape[1]
+        ops.gemm(ops.OP_NT, X, self.lstm.weight_ih, c.XP, n, 4 * H, Ein, Ein, Ein, 4 * H, bias=self.lstm.bias_ih,
+                 a_off=r0 * Ein, c_off=r0 * 4 * H)
+
+    def _proj_embed_part(self, c, r0, n):
+        H, E, D = self.hidden_size, self.embed_size, self.feature_size
+        ops.gemm(ops.OP_NT, c.X, self.lstm.weight_ih, c.XP, n, 4 * H, E, E, E + D, 4 * H, bias=self.lstm.bias_ih,
+                 a_off=r0 * E, c_off=r0 * 4 * H)
+
+    def _proj_step(self, c, r0, n):
+        H, E, D = self.hidden_size, self.embed_size, self.feature_size
+        ops.gemm(ops.OP_NT, c.CTX, self.lstm.weight_ih, c.XP, n, 4 * H, D, D, E + D, 4 * H, beta=1.0,
+                 a_off=r0 * D, b_off=E, c_off=r0 * 4 * H)
+
+    def _proj_bwd_begin(self, c, N):
+        pass
+
+    def _proj_step_bwd(self, c, dZ, r0, n):
+        H, E, D = self.hidden_size, self.embed_size, self.feature_size
+        ops.gemm(ops.OP_NN, dZ, self.lstm.weight_ih, c.dCTX, n, D, 4 * H, 4 * H, E + D, D, a_off=r0 * 4 * H,
+                 b_off=E, c_off=r0 * D)
+
+    def _proj_weight_grads(self, c, dZ, gbuf):
+        H, E, D = self.hidden_size, self.embed_size, self.feature_size
+        N = c.X.shape[0]
+        gW = self._gview(gbuf, ["lstm.weight_ih"], (4 * H, E + D))
+        ops.gemm(ops.OP_TN, dZ, c.X, gW, 4 * H, E, N, 4 * H, E, E + D)
+        ops.gemm(ops.OP_TN, dZ, c.CTX, gW, 4 * H, D, N, 4 * H, D, E + D, c_off=E)
+        ops.colsum(dZ, N, 4 * H, 4 * H, self._gview(gbuf, ["lstm.bias_ih"], (4 * H,)))
+        dX = torch.empty(N, E, dtype=torch.float32, device=dZ.device)
+        ops.gemm(ops.OP_NN, dZ, self.lstm.weight_ih, dX, N, E, 4 * H, 4 * H, E + D, E)
+        return dX
+
+    def forward(self, captions, lengths, features, teacher_forcing_ratio=0.8):
+        """(outputs, alphas) like nic/model_att.py:152-202."""
+        return self._forward_att(captions, lengths, features, teacher_forcing_ratio, None)
+
+    def forward_step(self, embedded, states):
+        from .decode import single_step
+        return single_step(self, embedded, states, None)
+
+    def sample(self, features, start_token, end_token, k=5):
+        """Beam search with attention, nic/model_att.py:204-306."""
+        from .decode import beam_sample_att
+        return beam_sample_att(self, features, start_token, end_token, k, None)[0]

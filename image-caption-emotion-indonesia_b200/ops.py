@@ -144,3 +144,17 @@ def adam_clamp(p, g, m, v, ranges, step_sizes, bc2_sqrts, beta1, beta2, eps, cli
 
 def mean_pixels(feat, B, P, D, out):
     check(lib().sn_mean_pixels(_ptr(_req(feat)), B, P, D, _ptr(out), _stream()), "sn_mean_pixels")
+
+
+def att_step_fwd(att1, att2, feat, wfull, bfull, gate_pre, nb, P, A, D, alpha, ld_alpha, ctx, ldc):
+    check(lib().sn_att_step_fwd(_ptr(_req(att1)), _ptr(_req(att2)), _ptr(_req(feat)), _ptr(_req(wfull)),
+                                float(bfull), _ptr(_req(gate_pre)), nb, P, A, D, _ptr(alpha), ld_alpha,
+                                _ptr(ctx), ldc, _stream()), "sn_att_step_fwd")
+
+
+def att_step_bwd(att1, att2, feat, wfull, bfull, gate_pre, alpha, ld_alpha, dctx, ldc, dalpha_extra, ld_da,
+                 nb, P, A, D, datt2, dgate_pre, datt1, dwfull, dfeat):
+    check(lib().sn_att_step_bwd(_ptr(_req(att1)), _ptr(_req(att2)), _ptr(_req(feat)), _ptr(_req(wfull)),
+                                float(bfull), _ptr(_req(gate_pre)), _ptr(alpha), ld_alpha, _ptr(_req(dctx)), ldc,
+                                _ptr(dalpha_extra), ld_da, nb, P, A, D, _ptr(datt2), _ptr(dgate_pre),
+                                _ptr(datt1), _ptr(dwfull), _ptr(dfeat), _stream()), "sn_att_step_bwd")
