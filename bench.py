@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- decoder train tokens/sec (fwd + bwd + clamp + Adam) on the BASELINE.json config:
+StyleNet FactoredLSTM, factored_size 512, emotion mode ("happy"), batch 96 per GPU, captions of length
+20 over a 10k vocabulary, synthetic features (configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+V, E, H, F, T = 10000, 300, 512, 512, 20
+B_PER_GPU = 96
+MODE = "happy"
+METRIC = "decoder_train_tokens_per_sec"
+UNIT = "tokens/s"
+
+
+def workload_config(n_gpus, dtype):
+    return {
+        "workload": "configs[1]: StyleNet DecoderFactoredLSTM(embed 300, hidden 512, factored 512, vocab 10000), "
+                    "mode=happy, teacher_forcing=1.0, dropout 0.5 on, fwd+bwd+clip(0.5)+Adam, T=20",
+        "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * n_gpus, "seq_len": T,
+        "tokens_per_step": B_PER_GPU * T * n_gpus, "parallelism": "dp%d" % n_gpus,
+        "l2": "flushed between timed steps (512 MiB write); step working set ~0.5 GB > 126 MB L2",
+        "arith": dtype,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference modules on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, max_seconds=None):
+    import random
+    import torch
+    from oracle import port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    dec = port.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5)
+    dec.train()
+    opt = torch.optim.Adam(dec.parameters(), lr=5e-4)
+    cap, lens, feats = port.synthetic_batch(B_PER_GPU, T, V, E=E, ragged=False, seed=0)
+    random.seed(0)
+    for _ in range(warmup):
+        port.train_step(dec, opt, cap, lens, feats, mode=MODE, teacher_forcing_ratio=1.0)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        port.train_step(dec, opt, cap, lens, feats, mode=MODE, teacher_forcing_ratio=1.0)
+        done += 1
+        if max_seconds is not None and time.perf_counter() - t0 > max_seconds:
+            break
+    dt = time.perf_counter() - t0
+    tok = done * sum(lens)
+    return {"value": tok / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d full steps of the same workload (B=%d, T=%d) in %.1f s, torch %s CPU, %d threads"
+                      % (done, B_PER_GPU, T, dt, torch.__version__, torch.get_num_threads()),
+            "ms_per_step": 1e3 * dt / done, "steps": done}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1, "f32 (torch CPU)"),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = oracle/port.py (restatement of stylenet/model.py + train_multitask.py:377-389) on the "
+                "host cores; the reference is pure Python/torch so there is nothing to compile into oracle/_ref",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def run_gpu(args):
+    import random
+    import torch
+    import torch.distributed as dist
+    import icei_b200 as sn
+    from icei_b200 import ops
+    from oracle import port   # synthetic-input generator only (shared with the CPU baseline)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)                        # identical weights on every rank
+    dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5).to(dev)
+    dec.train()
+    opt = sn.FusedClampAdam(dec, lr=5e-4, grad_clip=0.5)
+    trainer = sn.DataParallelTrainer(dec, opt)
+    cap_h, lens, feat_h = port.synthetic_batch(B_PER_GPU, T, V, E=E, ragged=False, seed=rank)
+    cap_pin, feat_pin = cap_h.pin_memory(), feat_h.pin_memory()
+    cap_d, feat_d = cap_pin.to(dev), feat_pin.to(dev)
+    loss_pin = torch.zeros(1).pin_memory()
+    n_tok_local = sum(lens)
+    random.seed(0)
+    flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device=dev)   # 512 MiB > L2
+
+    def step_resident():
+        return trainer.step(cap_d, lens, feat_d, mode=MODE, teacher_forcing_ratio=1.0)
+
+    def step_e2e():
+        c = cap_pin.to(dev, non_blocking=True)
+        f = feat_pin.to(dev, non_blocking=True)
+        loss, _ = trainer.step(c, lens, f, mode=MODE, teacher_forcing_ratio=1.0)
+        loss_pin.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_pin[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+
+    # ---- timed region: K steps, device time per step (CUDA events on the launching stream) -----------
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.LAUNCHES[0] = 0
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_resident()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = ops.LAUNCHES[0]
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop()
+    t_local = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    ms_total = float(t_local.item())
+    ms_per_step = ms_total / args.steps
+    value = n_tok_local * world * args.steps / (ms_total / 1e3)
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, wall clock ------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    dt = time.perf_counter() - t0
+    t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = n_tok_local * world * args.steps / float(t_e.item())
+    h2d = cap_pin.numel() * 8 + feat_pin.numel() * 4
+
+    line = None
+    if rank == 0:
+        hbm_peak, tf_peak, peak_src = measured_peaks()
+        roof, kernels = kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, "f32 FFMA"),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "timing": "wall clock incl. python, pinned H2D of captions+features, D2H loss, sync per step"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
+        }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(40, 1, max_seconds=args.cpu_seconds)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src):
+    """Per-kernel device time (CUDA events, L2 flushed) of the dominant HBM-bound kernels of one step, and
+    the roofline object for the dominant one.  ALGORITHMIC bytes per launch as defined in DESIGN.md."""
+    import torch
+    import icei_b200 as sn
+    from icei_b200 import ops
+    dev = cap_d.device
+    plan = sn.get_plan(lens)
+    d = plan.dev(dev)
+    N, B, TT = plan.N, plan.B, plan.T
+    f32 = dict(dtype=torch.float32, device=dev)
+    XP = torch.randn(N, 4 * H, **f32)
+    Whh, bhh = dec._recurrent_weights()
+    Hall, Call, Hprev = torch.empty(N, H, **f32), torch.empty(N, H, **f32), torch.empty(N, H, **f32)
+    gates = torch.empty(N, 4 * H, **f32)
+    dH = torch.randn(N, H, **f32)
+    dZ = torch.empty(N, 4 * H, **f32)
+    flush = torch.empty(64 * 1024 * 1024, **f32)
+
+    def timeit(fn, reps=5):
+        fn()
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps
+
+    def fwd():
+        cst = torch.zeros(B, H, **f32)
+        ops.recur_fwd(dec.cell, H, B, d["bs"], d["off"], 0, TT, XP, Whh, bhh, None, Hall, Call, Hprev, gates, cst)
+
+    def bwd():
+        dh, dc = torch.zeros(B, H, **f32), torch.zeros(B, H, **f32)
+        ops.recur_bwd(dec.cell, H, B, d["bs"], d["off"], 0, TT, Whh, None, Call, gates, dH, dZ, dh, dc)
+
+    logits = torch.randn(N, V, **f32)
+    tgt = torch.randint(0, V, (N,), device=dev)
+    rl = torch.empty(N, **f32)
+
+    def smx():
+        ops.softmax_nll(logits, N, V, targets=tgt, row_loss=rl, dlogits=logits, grad_scale=1.0 / N)
+
+    t_f, t_b, t_s = timeit(fwd), timeit(bwd), timeit(smx)
+    by_f = N * H * 48 + 4 * H * H * 4          # XP + h,c in/out + saved gates, + W_hh once
+    by_b = N * H * (16 + 16 + 4 + 8 + 8) + 4 * H * H * 4   # gates + dZ + dHall + c_t,c_{t-1} + dc carry
+    by_s = N * V * 8                           # logits read + gradient written in place
+    kernels = {
+        "recur_fwd_kernel": {"ms": t_f, "alg_bytes": by_f, "gbs": by_f / t_f / 1e6},
+        "recur_bwd_kernel": {"ms": t_b, "alg_bytes": by_b, "gbs": by_b / t_b / 1e6},
+        "softmax_nll_kernel": {"ms": t_s, "alg_bytes": by_s, "gbs": by_s / t_s / 1e6},
+    }
+    dom = max(("recur_fwd_kernel", "recur_bwd_kernel"), key=lambda k: kernels[k]["ms"])
+    ach = kernels[dom]["gbs"]
+    roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+            "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "note": "latency-bound at B=96 (T serial steps with an inter-SM exchange each); see DESIGN.md"}
+    return roof, kernels
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

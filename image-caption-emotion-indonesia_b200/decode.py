@@ -6,7 +6,7 @@ import ctypes
 import torch
 
 from . import ops
-from ._lib import check
+from .ops import check
 
 _small = {}
 

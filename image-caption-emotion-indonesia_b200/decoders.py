@@ -286,7 +286,7 @@ class _DecoderBase(nn.Module):
         return _HiddenFn.apply(anchor, features, self, plan, captions, coins, mode, save), plan
 
     def forward_loss(self, captions, lengths, features=None, targets=None, teacher_forcing_ratio=1.0,
-                     mode="factual", backward=True, n_global=None):
+                     mode="factual", backward=True, n_global=None, grad_hook=None):
         """Fused training entry point (an addition beside the kept surface):
         forward -> mean token NLL -> (optionally) backward, with log-softmax/NLL/gradient fused in one
         pass over the logits and no autograd graph.  Populates ``.grad`` like ``loss.backward()`` after
@@ -320,9 +320,13 @@ class _DecoderBase(nn.Module):
             if backward:
                 gbuf = self._grad_target(c.grad_names + list(self._out_names()))
                 dHall = self._vocab_backward(c.Hall, logits, gbuf)
+                if grad_hook is not None and gbuf is self.arena().gflat:
+                    grad_hook(list(self._out_names()))       # bucket 0 is final: overlap its all-reduce
                 need_dfeat = features is not None and features.requires_grad
                 dfeat = self._run_backward(c, dHall, gbuf, need_dfeat)
                 self._publish(c.grad_names + list(self._out_names()), gbuf)
+                if grad_hook is not None:
+                    grad_hook(c.grad_names if gbuf is self.arena().gflat else c.grad_names + list(self._out_names()))
                 if dfeat is not None:
                     features.grad = dfeat if features.grad is None else features.grad + dfeat
         return loss, {"argmax": argmax, "top5hit": top5, "n_tokens": N}

@@ -251,7 +251,8 @@ class _AttBase(_DecoderBase):
         return _LogitsFn.apply(hall, self._out().weight, self), alphas
 
     def forward_loss(self, captions, lengths, features, targets=None, teacher_forcing_ratio=1.0, mode="factual",
-                     backward=True, n_global=None, b_global=None, alpha_c=1.0, full_captions=None):
+                     backward=True, n_global=None, b_global=None, alpha_c=1.0, full_captions=None,
+                     grad_hook=None):
         """Fused training entry point for the attention decoders: CE mean + alpha_c * mean((1-sum_t a)^2)
         (stylenet/train_multitask_att.py:402-411), forward and backward without an autograd graph.
         ``captions`` are the INPUT tokens (reference passes captions[:, :-1]); give the packed ``targets``
@@ -290,8 +291,12 @@ class _AttBase(_DecoderBase):
                 names = c.grad_names + list(self._out_names())
                 gbuf = self._grad_target(names)
                 dHall = self._vocab_backward(c.Hall, logits, gbuf)
+                if grad_hook is not None and gbuf is self.arena().gflat:
+                    grad_hook(list(self._out_names()))
                 dfeat = self._run_backward_att(c, dHall, dAl, gbuf, features.requires_grad)
                 self._publish(names, gbuf)
+                if grad_hook is not None:
+                    grad_hook(c.grad_names if gbuf is self.arena().gflat else names)
                 if dfeat is not None:
                     dfeat = dfeat.view(features.shape)
                     features.grad = dfeat if features.grad is None else features.grad + dfeat

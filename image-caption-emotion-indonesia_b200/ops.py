@@ -5,7 +5,18 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import OP_NN, OP_NT, OP_TN, CELL_FACTORED, CELL_LSTM, check  # noqa: F401
+from ._lib import OP_NN, OP_NT, OP_TN, CELL_FACTORED, CELL_LSTM  # noqa: F401
+from ._lib import check as _check
+
+
+def check(rc, what=""):
+    _check(rc, what)
+    if what != "sn_device_info":
+        LAUNCHES[0] += 1
+
+
+# number of libsn100 kernels launched (bench.py's gpu_launches); one per call unless noted
+LAUNCHES = [0]
 
 
 def _stream():
