@@ -23,6 +23,8 @@ SIGNATURES = {
     "sn_gather_pack_fwd": (_I32, [_P, _I64, _P, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _P, _I64, _F, c_uint64, _P]),
     "sn_gather_pack_bwd": (_I32, [_P, _I64, _P, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _P, _I64, _F, c_uint64, _P]),
     "sn_gemm": (_I32, [_I32, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _I64, _I64, _I64, _I64, _P]),
+    "sn_gemm_bf16": (_I32, [_I32, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _I64, _I64, _I64, _I64, _I64, _P]),
+    "sn_cast_bf16": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P]),
     "sn_colsum": (_I32, [_P, _I64, _I64, _I64, _P, _F, _P]),
     "sn_recur_ws_bytes": (_I64, [_I64, _I64]),
     "sn_recur_fwd": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -169,3 +169,30 @@ def att_step_bwd(att1, att2, feat, wfull, bfull, gate_pre, alpha, ld_alpha, dctx
                                 float(bfull), _ptr(_req(gate_pre)), _ptr(alpha), ld_alpha, _ptr(_req(dctx)), ldc,
                                 _ptr(dalpha_extra), ld_da, nb, P, A, D, _ptr(datt2), _ptr(dgate_pre),
                                 _ptr(datt1), _ptr(dwfull), _ptr(dfeat), _stream()), "sn_att_step_bwd")
+
+
+def _bptr(t, off_elems, elem_size):
+    return ctypes.c_void_p(t.data_ptr() + elem_size * off_elems) if t is not None else None
+
+
+def gemm_bf16(op, A, B, M, N, K, lda, ldb, C=None, ldc=0, Cb=None, ldcb=0, bias=None, beta=0.0, batch=1,
+              sA=0, sB=0, sC=0, sCb=0, sBias=0, a_off=0, b_off=0, c_off=0, cb_off=0, bias_off=0):
+    """tcgen05 GEMM: A, B bf16; C fp32 and/or Cb bf16.  Offsets in elements of the respective tensor."""
+    _req(A, torch.bfloat16); _req(B, torch.bfloat16)
+    check(lib().sn_gemm_bf16(op, M, N, K, _bptr(A, a_off, 2), lda, _bptr(B, b_off, 2), ldb,
+                             _bptr(C, c_off, 4), ldc, _bptr(Cb, cb_off, 2), ldcb, _bptr(bias, bias_off, 4),
+                             float(beta), batch, sA, sB, sC, sCb, sBias, _stream()), "sn_gemm_bf16")
+
+
+def cast_bf16(src, R, C, lds, dst, Cp, ldd, src_off=0, dst_off=0):
+    check(lib().sn_cast_bf16(_bptr(_req(src), src_off, 4), R, C, lds, _bptr(dst, dst_off, 2), Cp, ldd, _stream()),
+          "sn_cast_bf16")
+
+
+def to_bf16_padded(x, pad_to=8):
+    """bf16 copy of a contiguous fp32 [R,C] matrix with C padded up to a multiple of ``pad_to`` (zeros)."""
+    R, C = x.shape
+    Cp = (C + pad_to - 1) // pad_to * pad_to
+    out = torch.empty(R, Cp, dtype=torch.bfloat16, device=x.device)
+    cast_bf16(x, R, C, x.stride(0), out, Cp, Cp)
+    return out

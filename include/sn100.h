@@ -78,6 +78,18 @@ int32_t sn_gemm(int32_t op, int64_t M, int64_t N, int64_t K, const float* A, int
                 const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, float beta,
                 int32_t batch, int64_t strideA, int64_t strideB, int64_t strideC, int64_t strideBias,
                 void* stream);
+/* The same GEMM on the tcgen05 tensor cores (SN_PREC_BF16): A, B are bf16 (row-major, leading dimensions
+ * and group strides multiples of 8 elements, 16-byte aligned bases -- the TMA rules), accumulation is
+ * fp32 in TMEM, the result is written as fp32 (C, may be NULL) and/or bf16 (Cb, may be NULL).
+ * 1..4 groups.  TMA-fed (cp.async.bulk.tensor, 128B swizzle), K/M/N tails zero-filled / masked. */
+int32_t sn_gemm_bf16(int32_t op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                     const void* B, int64_t ldb, float* C, int64_t ldc, void* Cb, int64_t ldcb,
+                     const float* bias, float beta, int32_t batch, int64_t strideA, int64_t strideB,
+                     int64_t strideC, int64_t strideCb, int64_t strideBias, void* stream);
+/* fp32 [R,C] (row pitch lds) -> bf16 [R,Cp] (row pitch ldd), columns C..Cp zero-filled (weight shadows and
+ * activation operands of sn_gemm_bf16; Cp pads K to the TMA 16-byte rule, e.g. E=300 -> 304) */
+int32_t sn_cast_bf16(const float* src, int64_t R, int64_t C, int64_t lds, void* dst, int64_t Cp,
+                     int64_t ldd, void* stream);
 /* column sums (bias gradients): out[n] = sum_m X[m,n] + beta*out[n] */
 int32_t sn_colsum(const float* X, int64_t M, int64_t N, int64_t ldx, float* out, float beta,
                   void* stream);

@@ -172,3 +172,43 @@ def test_recurrence_segmented_equals_one_launch(ops):
             ops.recur_fwd(0, H, B, d["bs"], d["off"], t0, t1, XP, W, None, h_init, Hall, None, None, None, cst)
         outs.append(Hall)
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("op", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (96, 136, 72), (1920, 2048, 304), (257, 640, 1920),
+                                   (2048, 512, 1920), (1920, 10000, 512)])
+def test_gemm_tcgen05_bf16(ops, op, M, N, K):
+    """tcgen05/TMEM/TMA GEMM vs float64 matmul of the same bf16-rounded operands (fp32-accumulate error only)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N * 3 + K * 7 + op)
+    pad = lambda v: (v + 7) // 8 * 8
+    if op == 2:
+        A = torch.randn(K, pad(M), device="cuda", generator=g).bfloat16()
+    else:
+        A = torch.randn(M, pad(K), device="cuda", generator=g).bfloat16()
+    if op == 0:
+        B = torch.randn(N, pad(K), device="cuda", generator=g).bfloat16()
+    else:
+        B = torch.randn(K, pad(N), device="cuda", generator=g).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    C0 = torch.randn(M, N, device="cuda", generator=g)
+    C = C0.clone()
+    Cb = torch.zeros(M, pad(N), device="cuda", dtype=torch.bfloat16)
+    ops.gemm_bf16(op, A, B, M, N, K, A.stride(0), B.stride(0), C=C, ldc=N, Cb=Cb, ldcb=Cb.stride(0), bias=bias, beta=0.5)
+    a = A.double()[:, :K] if op != 2 else A.double()[:, :M].t()
+    b = B.double()[:, :K].t() if op == 0 else B.double()[:, :N]
+    want = a @ b + bias.double() + 0.5 * C0.double()
+    assert _rel(C, want) < 1e-5
+    assert _rel(Cb[:, :N].float(), want) < 6e-3
+
+
+def test_gemm_tcgen05_grouped(ops):
+    n, F, H = 200, 512, 512
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(n, 4 * F, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(4, H, F, device="cuda", generator=g) / 16).bfloat16()
+    bias = torch.randn(4 * H, device="cuda", generator=g)
+    C = torch.zeros(n, 4 * H, device="cuda")
+    ops.gemm_bf16(0, A, B, n, H, F, 4 * F, F, C=C, ldc=4 * H, bias=bias, batch=4, sA=F, sB=H * F, sC=H, sBias=H)
+    want = torch.cat([A[:, i * F:(i + 1) * F].double() @ B[i].double().t() + bias[i * H:(i + 1) * H].double()
+                      for i in range(4)], 1)
+    assert _rel(C, want) < 1e-5
