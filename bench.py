@@ -177,6 +177,9 @@ def run_gpu(args):
     torch.manual_seed(0)                        # identical weights on every rank
     dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5).to(dev)
     dec.train()
+    dec.set_precision(args.precision)
+    arith = "bf16 operands on tcgen05, fp32 accumulate (recurrence/softmax/Adam fp32)" if args.precision == "bf16" \
+        else "f32 FFMA"
     opt = sn.FusedClampAdam(dec, lr=5e-4, grad_clip=0.5)
     trainer = sn.DataParallelTrainer(dec, opt)
     cap_h, lens, feat_h = port.synthetic_batch(B_PER_GPU, T, V, E=E, ragged=False, seed=rank)
@@ -253,7 +256,8 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, "f32 FFMA"),
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(world, arith),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "timing": "wall clock incl. python, pinned H2D of captions+features, D2H loss, sync per step"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
@@ -339,6 +343,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -83,10 +83,32 @@ class _LogitsFn(torch.autograd.Function):
         return dHall, None, None
 
 
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
 class _DecoderBase(nn.Module):
     """Shared host logic of the non-attention decoders."""
 
     cell = ops.CELL_FACTORED
+    precision = "fp32"
+
+    def set_precision(self, precision):
+        """"fp32": every GEMM in fp32 FFMA (reference-exact mode, <=1e-5).  "bf16": GEMM operands in bf16 on
+        the tcgen05 tensor cores, fp32 accumulation in TMEM; recurrence state, gate math, softmax/NLL,
+        gradients-as-accumulated, master weights and Adam moments stay fp32."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        return self
+
+    @property
+    def bf16(self):
+        return self.precision == "bf16"
+
+    def _shadow(self, w, rows=None, cols=None):
+        """bf16 operand copy of a 2-D fp32 weight view, K padded to a multiple of 8 (TMA 16-byte rule)."""
+        return ops.to_bf16_padded(w)
 
     # ---- arena ----------------------------------------------------------------------------------
     def _arena_groups(self):
@@ -164,6 +186,7 @@ class _DecoderBase(nn.Module):
                             c.p_drop, c.seed)
         c.X = X
         c.XP = torch.empty(N, 4 * H, dtype=torch.float32, device=dev)
+        c.w16 = {}      # bf16 weight shadows of this call (refreshed every forward)
         self._input_projection(c, X, mode, 0, N)
         c.Hall = torch.empty(N, H, dtype=torch.float32, device=dev)
         c.Call = torch.empty(N, H, dtype=torch.float32, device=dev) if save else None
@@ -232,7 +255,12 @@ class _DecoderBase(nn.Module):
         ops.recur_bwd(self.cell, H, B, d["bs"], d["off"], 0, T, Whh, None, c.Call, c.gates, dHall, dZ, dh, dc)
         # dW_hh = dZ^T Hprev ; d b_hh = colsum(dZ)
         gW, gbW = self._recurrent_grads(gbuf)
-        ops.gemm(ops.OP_TN, dZ, c.Hprev, gW, 4 * H, H, N, 4 * H, H, H)
+        if self.bf16:
+            c.dZb = ops.to_bf16_padded(dZ)
+            Hpb = ops.to_bf16_padded(c.Hprev)
+            ops.gemm_bf16(ops.OP_TN, c.dZb, Hpb, 4 * H, H, N, 4 * H, H, C=gW, ldc=H)
+        else:
+            ops.gemm(ops.OP_TN, dZ, c.Hprev, gW, 4 * H, H, N, 4 * H, H, H)
         ops.colsum(dZ, N, 4 * H, 4 * H, gbW)
         dX = self._input_projection_bwd(c, dZ, gbuf)
         gE = a.block([self._emb_name()], emb.weight.shape, grad=True) if gbuf is a.gflat else \
@@ -253,6 +281,14 @@ class _DecoderBase(nn.Module):
     # ---- vocabulary projection ---------------------------------------------------------------------
     def _vocab_logits(self, Hall):
         out = self._out()
+        if self.bf16:
+            V, H = out.weight.shape
+            N = Hall.shape[0]
+            Hb = ops.to_bf16_padded(Hall.contiguous())
+            Wb = ops.to_bf16_padded(out.weight)
+            logits = torch.empty(N, V, dtype=torch.float32, device=Hall.device)
+            ops.gemm_bf16(ops.OP_NT, Hb, Wb, N, V, H, Hb.stride(0), Wb.stride(0), C=logits, ldc=V, bias=out.bias)
+            return logits
         return ops.linear_nt(Hall.contiguous(), out.weight, out.bias)
 
     def _vocab_backward(self, Hall, dlogits, gbuf):
@@ -263,8 +299,15 @@ class _DecoderBase(nn.Module):
         gC = self._gview(gbuf, [wn], (V, H))
         gb = self._gview(gbuf, [bn], (V,))
         dHall = torch.empty(N, H, dtype=torch.float32, device=Hall.device)
-        ops.gemm(ops.OP_NN, dlogits, out.weight, dHall, N, H, V, dlogits.stride(0), H, H)
-        ops.gemm(ops.OP_TN, dlogits, Hall, gC, V, H, N, dlogits.stride(0), H, H)
+        if self.bf16:
+            dLb = ops.to_bf16_padded(dlogits)
+            Hb = ops.to_bf16_padded(Hall.contiguous())
+            Wb = ops.to_bf16_padded(out.weight)
+            ops.gemm_bf16(ops.OP_NN, dLb, Wb, N, H, V, dLb.stride(0), Wb.stride(0), C=dHall, ldc=H)
+            ops.gemm_bf16(ops.OP_TN, dLb, Hb, V, H, N, dLb.stride(0), Hb.stride(0), C=gC, ldc=H)
+        else:
+            ops.gemm(ops.OP_NN, dlogits, out.weight, dHall, N, H, V, dlogits.stride(0), H, H)
+            ops.gemm(ops.OP_TN, dlogits, Hall, gC, V, H, N, dlogits.stride(0), H, H)
         ops.colsum(dlogits, N, V, dlogits.stride(0), gb)
         return dHall
 
@@ -424,13 +467,31 @@ class DecoderFactoredLSTM(_DecoderBase):
         H, F = self.hidden_size, self.factored_size
         Ein = X.shape[1]
         dev = X.device
-        if r0 == 0 and n == X.shape[0]:
+        if r0 == 0 and n == X.shape[0] and not self.bf16:
             c.A1 = torch.empty(n, 4 * F, dtype=torch.float32, device=dev)
             c.A2 = torch.empty(n, 4 * F, dtype=torch.float32, device=dev)
-        A1, A2 = c.A1, c.A2
+        A1, A2 = c.__dict__.get("A1"), c.__dict__.get("A2")
         Vc, bV = self._stack("V_", (4 * F, Ein)), self._stack("V_", (4 * F,), bias=True)
         Sc, bS = self._style_stack(mode, (4 * F, F)), self._style_stack(mode, (4 * F,), bias=True)
         Uc, bU = self._stack("U_", (4 * H, F)), self._stack("U_", (4 * H,), bias=True)
+        if self.bf16:
+            w16 = c.__dict__.setdefault("w16", {})
+            if "V" not in w16:
+                w16["V"], w16["S"], w16["U"] = self._shadow(Vc), self._shadow(Sc), self._shadow(Uc)
+            Vb, Sb, Ub = w16["V"], w16["S"], w16["U"]
+            Ep, Fp = Vb.stride(0), Sb.stride(0)
+            if r0 == 0 and n == X.shape[0]:
+                c.Xb = torch.empty(n, Ep, dtype=torch.bfloat16, device=dev)
+                c.A1 = torch.empty(n, 4 * F, dtype=torch.bfloat16, device=dev)
+                c.A2 = torch.empty(n, 4 * F, dtype=torch.bfloat16, device=dev)
+            ops.cast_bf16(X, n, Ein, Ein, c.Xb, Ep, Ep, src_off=r0 * Ein, dst_off=r0 * Ep)
+            ops.gemm_bf16(ops.OP_NT, c.Xb, Vb, n, 4 * F, Ep, Ep, Ep, Cb=c.A1, ldcb=4 * F, bias=bV, a_off=r0 * Ep,
+                          cb_off=r0 * 4 * F)
+            ops.gemm_bf16(ops.OP_NT, c.A1, Sb, n, F, F, 4 * F, Fp, Cb=c.A2, ldcb=4 * F, bias=bS, batch=4, sA=F,
+                          sB=F * Fp, sCb=F, sBias=F, a_off=r0 * 4 * F, cb_off=r0 * 4 * F)
+            ops.gemm_bf16(ops.OP_NT, c.A2, Ub, n, H, F, 4 * F, Fp, C=c.XP, ldc=4 * H, bias=bU, batch=4, sA=F,
+                          sB=H * Fp, sC=H, sBias=H, a_off=r0 * 4 * F, c_off=r0 * 4 * H)
+            return
         ops.gemm(ops.OP_NT, X, Vc, A1, n, 4 * F, Ein, Ein, Ein, 4 * F, bias=bV, a_off=r0 * Ein,
                  c_off=r0 * 4 * F)
         ops.gemm(ops.OP_NT, A1, Sc, A2, n, F, F, 4 * F, F, 4 * F, bias=bS, batch=4, sA=F, sB=F * F, sC=F,
@@ -449,6 +510,8 @@ class DecoderFactoredLSTM(_DecoderBase):
         gV, gbV = self._stack("V_", (4 * F, Ein), gbuf=gbuf), self._stack("V_", (4 * F,), gbuf=gbuf, bias=True)
         gS, gbS = self._style_stack(mode, (4 * F, F), gbuf=gbuf), self._style_stack(mode, (4 * F,), gbuf=gbuf, bias=True)
         gU, gbU = self._stack("U_", (4 * H, F), gbuf=gbuf), self._stack("U_", (4 * H,), gbuf=gbuf, bias=True)
+        if self.bf16:
+            return self._input_projection_bwd_bf16(c, dZ, gV, gbV, gS, gbS, gU, gbU)
         # U stage: dU_g = dZ_g^T A2_g ; dbU = colsum(dZ) ; dA2_g = dZ_g U_g
         ops.gemm(ops.OP_TN, dZ, c.A2, gU, H, F, N, 4 * H, 4 * F, F, batch=4, sA=H, sB=F, sC=H * F)
         ops.colsum(dZ, N, 4 * H, 4 * H, gbU)
@@ -464,6 +527,32 @@ class DecoderFactoredLSTM(_DecoderBase):
         ops.colsum(dA1, N, 4 * F, 4 * F, gbV)
         dX = torch.empty(N, Ein, dtype=torch.float32, device=dev)
         ops.gemm(ops.OP_NN, dA1, Vc, dX, N, Ein, 4 * F, 4 * F, Ein, Ein)
+        return dX
+
+    def _input_projection_bwd_bf16(self, c, dZ, gV, gbV, gS, gbS, gU, gbU):
+        """Backward of the factored chain with every GEMM on tcgen05 (bf16 operands, fp32 results)."""
+        H, F = self.hidden_size, self.factored_size
+        N, Ein = c.X.shape
+        dev = dZ.device
+        Vb, Sb, Ub = c.w16["V"], c.w16["S"], c.w16["U"]
+        Ep, Fp = Vb.stride(0), Sb.stride(0)
+        dZb = c.dZb
+        f32 = dict(dtype=torch.float32, device=dev)
+        b16 = dict(dtype=torch.bfloat16, device=dev)
+        ops.gemm_bf16(ops.OP_TN, dZb, c.A2, H, F, N, 4 * H, 4 * F, C=gU, ldc=F, batch=4, sA=H, sB=F, sC=H * F)
+        ops.colsum(dZ, N, 4 * H, 4 * H, gbU)
+        dA2, dA2b = torch.empty(N, 4 * F, **f32), torch.empty(N, 4 * F, **b16)
+        ops.gemm_bf16(ops.OP_NN, dZb, Ub, N, F, H, 4 * H, Fp, C=dA2, ldc=4 * F, Cb=dA2b, ldcb=4 * F, batch=4, sA=H,
+                      sB=H * Fp, sC=F, sCb=F)
+        ops.gemm_bf16(ops.OP_TN, dA2b, c.A1, F, F, N, 4 * F, 4 * F, C=gS, ldc=F, batch=4, sA=F, sB=F, sC=F * F)
+        ops.colsum(dA2, N, 4 * F, 4 * F, gbS)
+        dA1, dA1b = dA2, torch.empty(N, 4 * F, **b16)      # dA2 (fp32) is dead after its colsum: reuse
+        ops.gemm_bf16(ops.OP_NN, dA2b, Sb, N, F, F, 4 * F, Fp, C=dA1, ldc=4 * F, Cb=dA1b, ldcb=4 * F, batch=4, sA=F,
+                      sB=F * Fp, sC=F, sCb=F)
+        ops.gemm_bf16(ops.OP_TN, dA1b, c.Xb, 4 * F, Ein, N, 4 * F, Ep, C=gV, ldc=Ein)
+        ops.colsum(dA1, N, 4 * F, 4 * F, gbV)
+        dX = torch.empty(N, Ein, **f32)
+        ops.gemm_bf16(ops.OP_NN, dA1b, Vb, N, Ein, 4 * F, 4 * F, Ep, C=dX, ldc=Ein)
         return dX
 
     # -- reference surface ---------------------------------------------------------------------------
@@ -535,6 +624,18 @@ class DecoderRNN(_DecoderBase):
         """XP = x W_ih^T + b_ih (the first addmm of nn.LSTMCell, nic/model.py:77)."""
         H = self.hidden_size
         Ein = X.shape[1]
+        if self.bf16:
+            w16 = c.__dict__.setdefault("w16", {})
+            if "Wih" not in w16:
+                w16["Wih"] = self._shadow(self.lstm.weight_ih)
+            Wb = w16["Wih"]
+            Ep = Wb.stride(0)
+            if r0 == 0 and n == X.shape[0]:
+                c.Xb = torch.empty(n, Ep, dtype=torch.bfloat16, device=X.device)
+            ops.cast_bf16(X, n, Ein, Ein, c.Xb, Ep, Ep, src_off=r0 * Ein, dst_off=r0 * Ep)
+            ops.gemm_bf16(ops.OP_NT, c.Xb, Wb, n, 4 * H, Ep, Ep, Ep, C=c.XP, ldc=4 * H, bias=self.lstm.bias_ih,
+                          a_off=r0 * Ep, c_off=r0 * 4 * H)
+            return
         ops.gemm(ops.OP_NT, X, self.lstm.weight_ih, c.XP, n, 4 * H, Ein, Ein, Ein, 4 * H,
                  bias=self.lstm.bias_ih, a_off=r0 * Ein, c_off=r0 * 4 * H)
 
@@ -543,9 +644,16 @@ class DecoderRNN(_DecoderBase):
         N, Ein = c.X.shape
         gW = self._gview(gbuf, ["lstm.weight_ih"], (4 * H, Ein))
         gb = self._gview(gbuf, ["lstm.bias_ih"], (4 * H,))
+        dX = torch.empty(N, Ein, dtype=torch.float32, device=dZ.device)
+        if self.bf16:
+            Wb = c.w16["Wih"]
+            Ep = Wb.stride(0)
+            ops.gemm_bf16(ops.OP_TN, c.dZb, c.Xb, 4 * H, Ein, N, 4 * H, Ep, C=gW, ldc=Ein)
+            ops.colsum(dZ, N, 4 * H, 4 * H, gb)
+            ops.gemm_bf16(ops.OP_NN, c.dZb, Wb, N, Ein, 4 * H, 4 * H, Ep, C=dX, ldc=Ein)
+            return dX
         ops.gemm(ops.OP_TN, dZ, c.X, gW, 4 * H, Ein, N, 4 * H, Ein, Ein)
         ops.colsum(dZ, N, 4 * H, 4 * H, gb)
-        dX = torch.empty(N, Ein, dtype=torch.float32, device=dZ.device)
         ops.gemm(ops.OP_NN, dZ, self.lstm.weight_ih, dX, N, Ein, 4 * H, 4 * H, Ein, Ein)
         return dX
 

@@ -227,3 +227,52 @@ def test_oracle_parity_baseline_size(which):
         if p.grad is not None:
             assert rel_l2(p.grad.cpu(), g_auto[n].cpu()) < 1e-6, n
     assert torch.equal(stats["argmax"].cpu(), out_ref.argmax(1))
+
+
+@pytest.mark.parametrize("which,B,T,V,E,H,F", [
+    ("factored", 24, 9, 1000, 44, 64, 72),
+    ("factored", 96, 20, 10000, 300, 512, 512),
+    ("nic", 64, 20, 10000, 300, 512, 512),
+])
+def test_bf16_mode_within_2e2(which, B, T, V, E, H, F):
+    """bf16-in / fp32-accumulate mode (tcgen05 GEMMs): loss, logits and every gradient within 2e-2 relative
+    of the float64 oracle (BASELINE.json north_star tolerance)."""
+    import icei_b200 as sn
+    from oracle import port
+    torch.manual_seed(1)
+    torch.set_default_dtype(torch.float64)
+    try:
+        ref = port.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0) if which == "factored" else \
+            port.DecoderRNN(E, H, V, 1, dropout=0.0)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0) if which == "factored" else \
+        sn.DecoderRNN(E, H, V, 1, dropout=0.0)
+    kw = {"mode": "sad"} if which == "factored" else {}
+    dec.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    dec = dec.cuda().train().set_precision("bf16")
+    cap, lens, feats = port.synthetic_batch(B, T, V, E=E, ragged=True, seed=4)
+    tgt = port.pack_targets(cap, lens)
+    out_ref = ref(cap, lens, feats.double(), teacher_forcing_ratio=1.0, **kw)
+    loss_ref = port.caption_loss(out_ref, tgt)
+    ref.zero_grad(); loss_ref.backward()
+    out = dec(cap.cuda(), lens, feats.cuda(), teacher_forcing_ratio=1.0, **kw)
+    loss = port.caption_loss(out, tgt.cuda())
+    dec.zero_grad(); loss.backward()
+    assert rel_l2(out.detach().cpu(), out_ref.detach()) < 2e-2
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    gref = {n: p.grad for n, p in ref.named_parameters()}
+    worst = 0.0
+    for n, p in dec.named_parameters():
+        if gref[n] is None:
+            assert p.grad is None, n
+        else:
+            e = rel_l2(p.grad.cpu(), gref[n])
+            worst = max(worst, e)
+            assert e < 2e-2, (n, e)
+    dec.zero_grad()
+    loss2, _ = dec.forward_loss(cap.cuda(), lens, feats.cuda(), **kw)
+    assert abs(loss2.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    for n, p in dec.named_parameters():
+        if p.grad is not None:
+            assert rel_l2(p.grad.cpu(), gref[n]) < 2e-2, n
