@@ -90,6 +90,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def synthetic_batch(B, Tlen, vocab, embed, seed):
+    """SURVEY.md section 8d inputs: captions ~ randint(4,V), column 0 = <start>=1, last = <end>=2, fixed length
+    T (N = B*T tokens), features ~ N(0,1) [B,E] (what EncoderCNN's Linear+BN emits)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    cap = torch.randint(4, vocab, (B, Tlen), generator=g)
+    cap[:, 0] = 1
+    cap[:, -1] = 2
+    return cap, [Tlen] * B, torch.randn(B, embed, generator=g)
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks sampler
 # ------------------------------------------------------------------------------------------------
@@ -107,7 +118,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -161,7 +172,6 @@ def run_gpu(args):
     import torch.distributed as dist
     import icei_b200 as sn
     from icei_b200 import ops
-    from oracle import port   # synthetic-input generator only (shared with the CPU baseline)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -182,7 +192,7 @@ def run_gpu(args):
         else "f32 FFMA"
     opt = sn.FusedClampAdam(dec, lr=5e-4, grad_clip=0.5)
     trainer = sn.DataParallelTrainer(dec, opt)
-    cap_h, lens, feat_h = port.synthetic_batch(B_PER_GPU, T, V, E=E, ragged=False, seed=rank)
+    cap_h, lens, feat_h = synthetic_batch(B_PER_GPU, T, V, E, seed=rank)
     cap_pin, feat_pin = cap_h.pin_memory(), feat_h.pin_memory()
     cap_d, feat_d = cap_pin.to(dev), feat_pin.to(dev)
     loss_pin = torch.zeros(1).pin_memory()
@@ -338,7 +348,7 @@ def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

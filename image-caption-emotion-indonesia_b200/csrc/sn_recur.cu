@@ -44,7 +44,7 @@ struct RecurArgs {
 
 __device__ __forceinline__ void wait_flag(const int* flag, int target) {
   if (threadIdx.x == 0) {
-    while (sn::ld_acquire(flag) < target) { __nanosleep(20); }
+    while (sn::ld_acquire(flag) < target) { }
   }
   __syncthreads();
 }
@@ -81,18 +81,22 @@ __device__ __forceinline__ void matvec_accum(const float* __restrict__ Ws, int l
   }
 }
 
-// stage rows [r0, r0+G) x cols [k0, k0+KC) of a [*, ld] global matrix into smem (zeros past nrows)
-__device__ __forceinline__ void stage_rows(float* __restrict__ INs, int ldi, const float* __restrict__ src,
-                                           int64_t ld, int nrows, int G, int k0, int KC, bool coherent_l2) {
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// asynchronous staging of rows [0,nrows) x cols [k0,k0+KC) into smem (L2-coherent .cg path, all copies of
+// a thread in flight at once); rows past nrows are left untouched (their results are never stored)
+__device__ __forceinline__ void stage_rows_async(float* __restrict__ INs, int ldi, const float* __restrict__ src,
+                                                 int64_t ld, int nrows, int k0, int KC) {
   const int vec_per_row = KC >> 2;
-  for (int i = threadIdx.x; i < G * vec_per_row; i += NT) {
+  for (int i = threadIdx.x; i < nrows * vec_per_row; i += NT) {
     int r = i / vec_per_row, c = (i - r * vec_per_row) << 2;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < nrows && src) {
-      const float4* p = reinterpret_cast<const float4*>(src + (int64_t)r * ld + k0 + c);
-      v = coherent_l2 ? __ldcg(p) : __ldg(p);
-    }
-    *reinterpret_cast<float4*>(INs + r * ldi + c) = v;
+    cp_async16(INs + r * ldi + c, src + (int64_t)r * ld + k0 + c);
   }
 }
 
@@ -118,26 +122,49 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_kernel(RecurArgs a) {
   }
   __syncthreads();
 
+  constexpr int NSLOT = (SW + 3) / 4;     // samples of a group this lane finishes: s = kl + 4*j
   for (int t = a.t0; t < a.t1; ++t) {
     const int bt = a.bs[t];
     const int nv = min(max(bt - sb0, 0), a.BB);
     int* flag_t = a.flags + bb * a.T + t;
     if (nv > 0) {
+      const int64_t row0 = (int64_t)a.off[t] + sb0;
+      const int sw0 = warp * SW;
+      // ---- prefetch everything that does not depend on h_{t-1}: XP (+bias) and c_{t-1} of this lane's
+      //      (sample, unit) slots of the first group -- in flight while we wait for the other CTAs
+      float pz[NSLOT][4], pc[NSLOT];
+#pragma unroll
+      for (int j = 0; j < NSLOT; ++j) {
+        const int sl = sw0 + kl + 4 * j;
+        pc[j] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pz[j][q] = 0.f;
+        if (kl + 4 * j < SW && sl < min(G, nv)) {
+          const float* xp = a.XP + (row0 + sl) * 4 * H + u0 + rl;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) pz[j][q] = __ldg(xp + q * H) + (a.bhh ? __ldg(a.bhh + q * H + u0 + rl) : 0.f);
+          pc[j] = a.c_state[(int64_t)(sb0 + sl) * H + u0 + rl];
+        }
+      }
       const float* hsrc;
-      int64_t row_prev0 = 0;
-      bool coherent = false;
       if (t == a.t0) {
         hsrc = a.h_init ? a.h_init + (int64_t)sb0 * H : nullptr;
       } else {
-        row_prev0 = (int64_t)a.off[t - 1] + sb0;
-        hsrc = a.Hall + row_prev0 * H;
-        coherent = true;
+        hsrc = a.Hall + ((int64_t)a.off[t - 1] + sb0) * H;
         wait_flag(a.flags + bb * a.T + (t - 1), a.n_ub);
       }
-      const int64_t row0 = (int64_t)a.off[t] + sb0;
       for (int g0 = 0; g0 < nv; g0 += G) {
         const int ng = min(G, nv - g0);
-        stage_rows(INs, ldw, hsrc ? hsrc + (int64_t)g0 * H : nullptr, H, ng, G, 0, H, coherent);
+        if (hsrc) {
+          stage_rows_async(INs, ldw, hsrc + (int64_t)g0 * H, H, ng, 0, H);
+          cp_async_commit();
+          cp_async_wait<0>();
+        } else {
+          for (int i = tid; i < ng * (H >> 2); i += NT) {
+            int r = i / (H >> 2), c = (i - r * (H >> 2)) << 2;
+            *reinterpret_cast<float4*>(INs + r * ldw + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         __syncthreads();
         if (a.Hprev) {
           for (int i = tid; i < ng * UB; i += NT) {
@@ -150,7 +177,6 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_kernel(RecurArgs a) {
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int s = 0; s < SW; ++s) acc[j][s] = 0.f;
-        const int sw0 = warp * SW;
         if (sw0 < ng) matvec_accum<4, SW>(Ws, ldw, 0, INs, ldw, H, rl, kl, sw0, acc);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -167,20 +193,24 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_kernel(RecurArgs a) {
             const int sl = g0 + sw0 + s;             // sample index inside the batch block
             const int64_t row = row0 + sl;
             const int u = u0 + rl;
-            const float* xp = a.XP + row * 4 * H + u;
-            float zi = acc[0][s] + xp[0];
-            float zf = acc[1][s] + xp[H];
-            float z2 = acc[2][s] + xp[2 * H];
-            float z3 = acc[3][s] + xp[3 * H];
-            if (a.bhh) {
-              zi += a.bhh[u]; zf += a.bhh[H + u]; z2 += a.bhh[2 * H + u]; z3 += a.bhh[3 * H + u];
-            }
-            float zo = a.cell == SN_CELL_LSTM ? z3 : z2;
-            float zc = a.cell == SN_CELL_LSTM ? z2 : z3;
-            float gi = sn::sigmoidf_(zi), gf = sn::sigmoidf_(zf), go = sn::sigmoidf_(zo), gc = tanhf(zc);
+            float z0, z1, z2, z3, cprev;
             float* cst = a.c_state + (int64_t)(sb0 + sl) * H + u;
-            float c = gf * (*cst) + gi * gc;
-            float h = a.cell == SN_CELL_LSTM ? go * tanhf(c) : go * c;
+            if (g0 == 0) {
+              z0 = pz[s >> 2][0]; z1 = pz[s >> 2][1]; z2 = pz[s >> 2][2]; z3 = pz[s >> 2][3];
+              cprev = pc[s >> 2];
+            } else {
+              const float* xp = a.XP + row * 4 * H + u;
+              z0 = xp[0]; z1 = xp[H]; z2 = xp[2 * H]; z3 = xp[3 * H];
+              if (a.bhh) { z0 += a.bhh[u]; z1 += a.bhh[H + u]; z2 += a.bhh[2 * H + u]; z3 += a.bhh[3 * H + u]; }
+              cprev = *cst;
+            }
+            const float zi = acc[0][s] + z0, zf = acc[1][s] + z1;
+            const float za = acc[2][s] + z2, zb = acc[3][s] + z3;
+            const float zo = a.cell == SN_CELL_LSTM ? zb : za;
+            const float zc = a.cell == SN_CELL_LSTM ? za : zb;
+            const float gi = sn::sigmoidf_(zi), gf = sn::sigmoidf_(zf), go = sn::sigmoidf_(zo), gc = tanhf(zc);
+            const float c = gf * cprev + gi * gc;
+            const float h = a.cell == SN_CELL_LSTM ? go * tanhf(c) : go * c;
             *cst = c;
             a.Hall[row * H + u] = h;
             if (a.Call) a.Call[row * H + u] = c;
@@ -197,20 +227,29 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_kernel(RecurArgs a) {
   }
 }
 
+// K chunk of dZ_{t+1} staged per pipeline stage (double buffered): largest power of two <= 256 dividing 4H
+__host__ __device__ inline int bwd_kc(int H) {
+  int kc = 256;
+  while ((4 * H) % kc != 0) kc >>= 1;
+  return kc;
+}
+
 template <int SW>
 __global__ void __launch_bounds__(NT, 1) recur_bwd_kernel(RecurArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int H = a.H, K = 4 * H, ldw = K + 4;
   constexpr int G = NW * SW;
-  const int KC = H;                  // K chunk staged per pass
+  const int KC = bwd_kc(H);
   const int ldi = KC + 4;
-  float* Ws = smem;                  // [8][ldw]   Ws[u][k] = Whh[k, u0+u]
-  float* INs = smem + UB * ldw;      // [G][ldi]
+  float* Ws = smem;                        // [8][ldw]   Ws[u][k] = Whh[k, u0+u]
+  float* INs0 = smem + UB * ldw;           // [2][G][ldi]
+  float* INs1 = INs0 + G * ldi;
   const int ub = blockIdx.x % a.n_ub, bb = blockIdx.x / a.n_ub;
   const int u0 = ub * UB, sb0 = bb * a.BB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rl = lane & 7, kl = lane >> 3;
   const int pos_o = a.cell == SN_CELL_LSTM ? 3 : 2, pos_c = a.cell == SN_CELL_LSTM ? 2 : 3;
+  constexpr int NSLOT = (SW + 3) / 4;
 
   for (int i = tid; i < K * UB; i += NT) {
     int k = i >> 3, u = i & 7;
@@ -223,32 +262,64 @@ __global__ void __launch_bounds__(NT, 1) recur_bwd_kernel(RecurArgs a) {
     const bool tail = (t < a.t0);
     const int bt = tail ? a.bs[a.t0] : a.bs[t];
     const int nv = min(max(bt - sb0, 0), a.BB);
-    // samples that receive a recurrent gradient from step t+1
-    const int bnext = (t + 1 < a.t1) ? a.bs[t + 1] : 0;
+    const int bnext = (t + 1 < a.t1) ? a.bs[t + 1] : 0;   // samples with a recurrent gradient from t+1
     const int nrec = min(max(bnext - sb0, 0), a.BB);
     if (tail) {
-      // samples beyond b_{t0} get zero carry
       for (int i = tid; i < a.BB * UB; i += NT) {
         int s = i >> 3, u = i & 7;
         if (s >= nrec && sb0 + s < a.B) a.dh_carry[(int64_t)(sb0 + s) * H + u0 + u] = 0.f;
       }
     }
     if (nv > 0) {
-      if (nrec > 0) wait_flag(a.flags + bb * a.T + (t + 1), a.n_ub);
       const int64_t row0 = tail ? 0 : (int64_t)a.off[t] + sb0;
       const int64_t rown0 = (t + 1 < a.t1) ? (int64_t)a.off[t + 1] + sb0 : 0;
+      const int sw0 = warp * SW;
+      // ---- prefetch the step-local operands of this lane's slots (independent of dZ_{t+1})
+      float p_g[NSLOT][4], p_c[NSLOT], p_cp[NSLOT], p_dh[NSLOT], p_dc[NSLOT];
+#pragma unroll
+      for (int j = 0; j < NSLOT; ++j) {
+        const int sl = sw0 + kl + 4 * j;
+        p_c[j] = p_cp[j] = p_dh[j] = p_dc[j] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) p_g[j][q] = 0.f;
+        if (!tail && kl + 4 * j < SW && sl < min(G, nv)) {
+          const int u = u0 + rl;
+          const int64_t row = row0 + sl;
+          const int64_t sidx = (int64_t)(sb0 + sl) * H + u;
+          const float* gp = a.gates + row * K + u;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) p_g[j][q] = __ldg(gp + q * H);
+          p_c[j] = __ldg(a.Call + row * H + u);
+          if (t > 0) p_cp[j] = __ldg(a.Call + ((int64_t)a.off[t - 1] + sb0 + sl) * H + u);
+          else p_cp[j] = a.c_init ? __ldg(a.c_init + sidx) : 0.f;
+          p_dh[j] = __ldg(a.dHall + row * H + u);
+          p_dc[j] = a.dc_carry[sidx];
+        }
+      }
+      if (nrec > 0) wait_flag(a.flags + bb * a.T + (t + 1), a.n_ub);
       for (int g0 = 0; g0 < nv; g0 += G) {
         const int ng = min(G, nv - g0);
         const int ngrec = min(max(nrec - g0, 0), G);
         float acc[1][SW];
 #pragma unroll
         for (int s = 0; s < SW; ++s) acc[0][s] = 0.f;
-        const int sw0 = warp * SW;
         if (ngrec > 0) {
-          for (int k0 = 0; k0 < K; k0 += KC) {
-            stage_rows(INs, ldi, a.dZ + (rown0 + g0) * K, K, ngrec, G, k0, KC, true);
+          const float* src = a.dZ + (rown0 + g0) * K;
+          const int nchunk = K / KC;
+          stage_rows_async(INs0, ldi, src, K, ngrec, 0, KC);
+          cp_async_commit();
+          for (int ci = 0; ci < nchunk; ++ci) {
+            float* cur = (ci & 1) ? INs1 : INs0;
+            float* nxt = (ci & 1) ? INs0 : INs1;
+            if (ci + 1 < nchunk) {
+              stage_rows_async(nxt, ldi, src, K, ngrec, (ci + 1) * KC, KC);
+              cp_async_commit();
+              cp_async_wait<1>();
+            } else {
+              cp_async_wait<0>();
+            }
             __syncthreads();
-            if (sw0 < ngrec) matvec_accum<1, SW>(Ws, ldw, k0, INs, ldi, KC, rl, kl, sw0, acc);
+            if (sw0 < ngrec) matvec_accum<1, SW>(Ws, ldw, ci * KC, cur, ldi, KC, rl, kl, sw0, acc);
             __syncthreads();
           }
 #pragma unroll
@@ -272,14 +343,23 @@ __global__ void __launch_bounds__(NT, 1) recur_bwd_kernel(RecurArgs a) {
             }
             if (t == a.t1 - 1) dh_rec = a.dh_carry[sidx];
             const int64_t row = row0 + sl;
-            const float* gp = a.gates + row * K + u;
-            const float gi = gp[0], gf = gp[H], go = gp[pos_o * H], gc = gp[pos_c * H];
-            const float c = a.Call[row * H + u];
-            float cprev;
-            if (t > 0) cprev = a.Call[((int64_t)a.off[t - 1] + sb0 + sl) * H + u];
-            else cprev = a.c_init ? a.c_init[sidx] : 0.f;
-            const float dh = a.dHall[row * H + u] + dh_rec;
-            float dcar = a.dc_carry[sidx];
+            float gi, gf, go, gc, c, cprev, dhl, dcar;
+            if (g0 == 0) {
+              const int j = s >> 2;
+              gi = p_g[j][0]; gf = p_g[j][1];
+              go = a.cell == SN_CELL_LSTM ? p_g[j][3] : p_g[j][2];
+              gc = a.cell == SN_CELL_LSTM ? p_g[j][2] : p_g[j][3];
+              c = p_c[j]; cprev = p_cp[j]; dhl = p_dh[j]; dcar = p_dc[j];
+            } else {
+              const float* gp = a.gates + row * K + u;
+              gi = gp[0]; gf = gp[H]; go = gp[pos_o * H]; gc = gp[pos_c * H];
+              c = a.Call[row * H + u];
+              if (t > 0) cprev = a.Call[((int64_t)a.off[t - 1] + sb0 + sl) * H + u];
+              else cprev = a.c_init ? a.c_init[sidx] : 0.f;
+              dhl = a.dHall[row * H + u];
+              dcar = a.dc_carry[sidx];
+            }
+            const float dh = dhl + dh_rec;
             float d_o, dc;
             if (a.cell == SN_CELL_LSTM) {
               float tc = tanhf(c);
@@ -324,7 +404,8 @@ int32_t make_plan(bool bwd, int64_t H, int64_t B, Plan* p) {
   int best = 0;
   for (int i = 0; i < 3; ++i) {
     int sw = cands[i];
-    size_t smem = bwd ? ((size_t)UB * (4 * H + 4) + (size_t)NW * sw * (H + 4)) * 4
+    const int64_t kc = bwd_kc((int)H);
+    size_t smem = bwd ? ((size_t)UB * (4 * H + 4) + (size_t)2 * NW * sw * (kc + 4)) * 4
                       : ((size_t)32 * (H + 4) + (size_t)NW * sw * (H + 4)) * 4;
     if (smem > (size_t)d.smem_optin) continue;
     // smallest SW whose group covers the batch block, else the largest that fits

@@ -1,0 +1,144 @@
+"""CPU-only tests: host logic of the drop-in (packing plans, arena layout, range merging, sharding), the
+C-ABI library (loads, exports every symbol include/sn100.h declares -- no compute calls without a GPU), and
+the loud failure of the product path when there is no CUDA device."""
+import os
+import re
+import ctypes
+
+import pytest
+import torch
+
+import icei_b200 as sn
+from icei_b200 import _lib
+from icei_b200.arena import ParamArena
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported_and_bound():
+    hdr = open(os.path.join(ROOT, "include", "sn100.h")).read()
+    declared = set(re.findall(r"\b(sn_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "libsn100.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert _lib.load().sn_version() == 100
+
+
+def test_no_cpu_fallback():
+    dec = sn.DecoderFactoredLSTM(12, 16, 16, 53, 1)
+    cap = torch.randint(4, 53, (3, 5))
+    with pytest.raises(RuntimeError):
+        dec(cap, [5, 4, 3], torch.randn(3, 12), teacher_forcing_ratio=1.0)
+    with pytest.raises(RuntimeError):
+        sn.ops.linear_nt(torch.randn(4, 4), torch.randn(4, 4))
+
+
+@pytest.mark.parametrize("lengths", [[7], [5, 5, 5], [9, 7, 7, 4, 1], [20] * 96, list(range(30, 0, -1))])
+def test_pack_plan_matches_pack_padded_sequence(lengths):
+    plan = sn.get_plan(lengths)
+    B, T = len(lengths), max(lengths)
+    x = torch.arange(B * T).view(B, T)
+    packed = torch.nn.utils.rnn.pack_padded_sequence(x, lengths, batch_first=True)
+    assert plan.bs == packed.batch_sizes.tolist()
+    assert plan.N == sum(lengths) == packed.data.numel()
+    got = x[torch.from_numpy(plan.row_b_np).long(), torch.from_numpy(plan.row_t_np).long()]
+    assert torch.equal(got, packed.data)
+    for t in range(plan.T):
+        assert plan.off[t] == sum(plan.bs[:t])
+    assert sn.get_plan(lengths) is plan     # cached
+
+
+def test_pack_plan_rejects_bad_lengths():
+    with pytest.raises(RuntimeError):
+        sn.batch_sizes_from_lengths([3, 5])
+    with pytest.raises(RuntimeError):
+        sn.batch_sizes_from_lengths([3, 0])
+    with pytest.raises(ValueError):
+        sn.batch_sizes_from_lengths([])
+
+
+def test_shard_lengths_sorted_and_balanced():
+    lengths = sorted([20, 19, 19, 17, 15, 15, 12, 11, 9, 9, 7, 5, 5, 4, 3, 2], reverse=True)
+    seen = []
+    for r in range(4):
+        idx, ls = sn.shard_lengths(lengths, 4, r)
+        assert ls == sorted(ls, reverse=True)
+        sn.batch_sizes_from_lengths(ls)
+        seen += idx
+    assert sorted(seen) == list(range(len(lengths)))
+
+
+@pytest.mark.parametrize("make", [
+    lambda: sn.DecoderFactoredLSTM(12, 16, 20, 53, 1),
+    lambda: sn.DecoderRNN(12, 16, 53, 1),
+    lambda: sn.DecoderFactoredLSTMAtt(16, 12, 16, 20, 53, 1, feature_size=24),
+    lambda: sn.DecoderRNNAtt(16, 12, 16, 53, 1, feature_size=24),
+])
+def test_arena_binding_and_state_dict_interchange(make):
+    torch.manual_seed(0)
+    dec = make()
+    ref_sd = {k: v.clone() for k, v in dec.state_dict().items()}
+    a = dec.arena()
+    assert a.bound()
+    for n, p in dec.named_parameters():                      # values survive, storage is the arena
+        assert torch.equal(p.data, ref_sd[n])
+        assert p.data_ptr() == a.flat.data_ptr() + 4 * a.offset[n]
+        assert a.offset[n] % 1 == 0
+    # groups are contiguous stacks
+    for g, (start, n) in zip(a.groups, a.group_span):
+        assert start % 64 == 0
+        assert sum(a.numel[x] for x in g) == n
+    # load_state_dict copies in place: still bound
+    dec.load_state_dict({k: v + 1 for k, v in ref_sd.items()})
+    assert a.bound()
+    # .double().float() replaces storages: re-bind on demand, values kept
+    dec2 = make()
+    dec2.load_state_dict(ref_sd)
+    dec2.arena()
+    dec2.double().float()
+    a2 = dec2.arena()
+    assert a2.bound() and a2.version == 2
+    for n, p in dec2.named_parameters():
+        assert torch.equal(p.data, ref_sd[n])
+
+
+def test_reference_parameter_names():
+    """The drop-in keeps the reference's parameter names and shapes (checkpoint interchange)."""
+    from oracle import port
+    pairs = [
+        (sn.DecoderFactoredLSTM(12, 16, 20, 53, 1), port.DecoderFactoredLSTM(12, 16, 20, 53, 1)),
+        (sn.DecoderRNN(12, 16, 53, 1), port.DecoderRNN(12, 16, 53, 1)),
+        (sn.DecoderFactoredLSTMAtt(16, 12, 16, 20, 53, 1, feature_size=24),
+         port.DecoderFactoredLSTMAtt(16, 12, 16, 20, 53, 1, feature_size=24)),
+        (sn.DecoderRNNAtt(16, 12, 16, 53, 1, feature_size=24), port.DecoderRNNAtt(16, 12, 16, 53, 1, feature_size=24)),
+    ]
+    for mine, ref in pairs:
+        a = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+        b = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+        assert a == b
+        mine.load_state_dict(ref.state_dict())
+    assert len(pairs[0][0].state_dict()) == 59 and len(pairs[2][0].state_dict()) == 89
+
+
+def test_merged_ranges_and_grad_ranges():
+    dec = sn.DecoderFactoredLSTM(12, 16, 20, 53, 1)
+    a = dec.arena()
+    names = dec._seq_grad_names("happy") + list(dec._out_names())
+    rs = sn.merged_ranges(a, names)
+    covered = sum(n for _, n in rs)
+    assert covered >= sum(a.numel[n] for n in names)
+    # inactive styles are not covered
+    for o, n in rs:
+        for s in ("S_ff", "S_sad_i", "S_angry_c"):
+            off = a.offset[s + ".weight"]
+            assert not (o <= off < o + n), s
+    # publish + grad_ranges round trip
+    a.publish_grads(names, a.gflat)
+    items, foreign = a.grad_ranges()
+    assert not foreign and {n for _, _, n in items} == set(names)
+    assert dec.S_sad_i.weight.grad is None and dec.S_happy_i.weight.grad is not None
+    dec.S_happy_i.weight.grad = torch.zeros_like(dec.S_happy_i.weight)   # a foreign gradient tensor
+    items, foreign = a.grad_ranges()
+    assert foreign == ["S_happy_i.weight"]
