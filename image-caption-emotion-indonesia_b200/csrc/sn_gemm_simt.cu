@@ -114,21 +114,30 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
   }
 }
 
+constexpr int CS_ROWS = 128;   // rows per CTA: enough CTAs to fill the machine even for narrow matrices
+
+__global__ void colsum_scale_kernel(float* __restrict__ out, int64_t N, float beta) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[i] *= beta;
+}
+
+// grid (ceil(N/32), ceil(M/CS_ROWS)); block 32 columns x 8 row lanes; partial sums -> one atomicAdd per column
 __global__ void colsum_kernel(const float* __restrict__ X, int64_t M, int64_t N, int64_t ldx,
-                              float* __restrict__ out, float beta) {
-  // block = 32 columns x 8 row-lanes; rows strided by 8*gridDim.y ... one block owns its columns fully
+                              float* __restrict__ out) {
   __shared__ float part[8][33];
-  int col = blockIdx.x * 32 + threadIdx.x;
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS;
+  const int64_t r1 = r0 + CS_ROWS < M ? r0 + CS_ROWS : M;
   float s = 0.f;
   if (col < N)
-    for (int64_t m = threadIdx.y; m < M; m += 8) s += X[m * ldx + col];
+    for (int64_t m = r0 + threadIdx.y; m < r1; m += 8) s += X[m * ldx + col];
   part[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && col < N) {
     float t = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += part[j][threadIdx.x];
-    out[col] = t + (beta != 0.f ? beta * out[col] : 0.f);
+    atomicAdd(out + col, t);
   }
 }
 
@@ -159,7 +168,14 @@ extern "C" int32_t sn_colsum(const float* X, int64_t M, int64_t N, int64_t ldx, 
                              void* stream) {
   SN_REQUIRE(M >= 0 && N >= 0, "sn_colsum: bad dims");
   if (N == 0) return 0;
-  dim3 grid((unsigned)((N + 31) / 32)), block(32, 8);
-  colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(X, M, N, ldx, out, beta);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (beta == 0.f) {
+    SN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st));
+  } else if (beta != 1.f) {
+    colsum_scale_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(out, N, beta);
+  }
+  if (M == 0) return sn::check_launch("sn_colsum");
+  dim3 grid((unsigned)((N + 31) / 32), (unsigned)((M + CS_ROWS - 1) / CS_ROWS)), block(32, 8);
+  colsum_kernel<<<grid, block, 0, st>>>(X, M, N, ldx, out);
   return sn::check_launch("sn_colsum");
 }

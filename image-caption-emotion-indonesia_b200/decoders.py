@@ -195,13 +195,24 @@ class _DecoderBase(nn.Module):
         c_state = torch.zeros(B, H, dtype=torch.float32, device=dev)
         c.aux_argmax = None
         Whh, bhh = self._recurrent_weights()
+        use_tc = self.bf16 and H % 32 == 0
+        c.Hb = c.Hpb = None
+        if use_tc:
+            c.w16["Whh"] = self._shadow(Whh)
+            c.Hb = torch.empty(N, H, dtype=torch.bfloat16, device=dev)
+            c.Hpb = torch.empty(N, H, dtype=torch.bfloat16, device=dev) if save else None
+            c.Hprev = None
 
         def run(t0, t1):
             h_init = None
             if t0 > 0:
                 h_init = c.Hall[plan.off[t0 - 1]:]
-            ops.recur_fwd(self.cell, H, B, d["bs"], d["off"], t0, t1, c.XP, Whh, bhh, h_init, c.Hall,
-                          c.Call, c.Hprev, c.gates, c_state)
+            if use_tc:
+                ops.recur_fwd_bf16(self.cell, H, B, d["bs"], d["off"], t0, t1, c.XP, c.w16["Whh"], bhh, h_init,
+                                   c.Hall, c.Hb, c.Hpb, c.Call, c.gates, c_state)
+            else:
+                ops.recur_fwd(self.cell, H, B, d["bs"], d["off"], t0, t1, c.XP, Whh, bhh, h_init, c.Hall,
+                              c.Call, c.Hprev, c.gates, c_state)
 
         if all_tf:
             run(0, T)
@@ -252,9 +263,17 @@ class _DecoderBase(nn.Module):
         dZ = torch.empty(N, 4 * H, dtype=torch.float32, device=dev)
         dh = torch.zeros(B, H, dtype=torch.float32, device=dev)
         dc = torch.zeros(B, H, dtype=torch.float32, device=dev)
+        gW, gbW = self._recurrent_grads(gbuf)
+        if c.Hpb is not None:
+            c.dZb = torch.empty(N, 4 * H, dtype=torch.bfloat16, device=dev)
+            ops.recur_bwd_bf16(self.cell, H, B, d["bs"], d["off"], 0, T, c.w16["Whh"], None, c.Call, c.gates, dHall,
+                               dZ, c.dZb, dh, dc)
+            ops.gemm_bf16(ops.OP_TN, c.dZb, c.Hpb, 4 * H, H, N, 4 * H, H, C=gW, ldc=H)
+            ops.colsum(dZ, N, 4 * H, 4 * H, gbW)
+            dX = self._input_projection_bwd(c, dZ, gbuf)
+            return self._embedding_bwd(c, dX, gbuf, need_dfeat)
         ops.recur_bwd(self.cell, H, B, d["bs"], d["off"], 0, T, Whh, None, c.Call, c.gates, dHall, dZ, dh, dc)
         # dW_hh = dZ^T Hprev ; d b_hh = colsum(dZ)
-        gW, gbW = self._recurrent_grads(gbuf)
         if self.bf16:
             c.dZb = ops.to_bf16_padded(dZ)
             Hpb = ops.to_bf16_padded(c.Hprev)
@@ -263,8 +282,16 @@ class _DecoderBase(nn.Module):
             ops.gemm(ops.OP_TN, dZ, c.Hprev, gW, 4 * H, H, N, 4 * H, H, H)
         ops.colsum(dZ, N, 4 * H, 4 * H, gbW)
         dX = self._input_projection_bwd(c, dZ, gbuf)
-        gE = a.block([self._emb_name()], emb.weight.shape, grad=True) if gbuf is a.gflat else \
-            gbuf[a.offset[self._emb_name()]:a.offset[self._emb_name()] + emb.weight.numel()].view(emb.weight.shape)
+        return self._embedding_bwd(c, dX, gbuf, need_dfeat)
+
+    def _embedding_bwd(self, c, dX, gbuf, need_dfeat):
+        plan = c.plan
+        dev = dX.device
+        d = plan.dev(dev)
+        N, B = plan.N, plan.B
+        emb = self._emb()
+        E = emb.weight.shape[1]
+        gE = self._gview(gbuf, [self._emb_name()], emb.weight.shape)
         gE.zero_()
         dfeat = torch.empty(B, E, dtype=torch.float32, device=dev) if (need_dfeat and c.has_feat) else None
         ops.gather_pack_bwd(c.captions, gE, dfeat, c.has_feat, d["row_b"], d["row_t"], c.tok_override, N, dX,
@@ -279,19 +306,20 @@ class _DecoderBase(nn.Module):
         return gbuf[o:o + n].view(shape)
 
     # ---- vocabulary projection ---------------------------------------------------------------------
-    def _vocab_logits(self, Hall):
+    def _vocab_logits(self, Hall, Hb=None):
         out = self._out()
         if self.bf16:
             V, H = out.weight.shape
             N = Hall.shape[0]
-            Hb = ops.to_bf16_padded(Hall.contiguous())
+            if Hb is None:
+                Hb = ops.to_bf16_padded(Hall.contiguous())
             Wb = ops.to_bf16_padded(out.weight)
             logits = torch.empty(N, V, dtype=torch.float32, device=Hall.device)
             ops.gemm_bf16(ops.OP_NT, Hb, Wb, N, V, H, Hb.stride(0), Wb.stride(0), C=logits, ldc=V, bias=out.bias)
             return logits
         return ops.linear_nt(Hall.contiguous(), out.weight, out.bias)
 
-    def _vocab_backward(self, Hall, dlogits, gbuf):
+    def _vocab_backward(self, Hall, dlogits, gbuf, Hb=None):
         out = self._out()
         V, H = out.weight.shape
         N = Hall.shape[0]
@@ -301,7 +329,8 @@ class _DecoderBase(nn.Module):
         dHall = torch.empty(N, H, dtype=torch.float32, device=Hall.device)
         if self.bf16:
             dLb = ops.to_bf16_padded(dlogits)
-            Hb = ops.to_bf16_padded(Hall.contiguous())
+            if Hb is None:
+                Hb = ops.to_bf16_padded(Hall.contiguous())
             Wb = ops.to_bf16_padded(out.weight)
             ops.gemm_bf16(ops.OP_NN, dLb, Wb, N, H, V, dLb.stride(0), Wb.stride(0), C=dHall, ldc=H)
             ops.gemm_bf16(ops.OP_TN, dLb, Hb, V, H, N, dLb.stride(0), Hb.stride(0), C=gC, ldc=H)
@@ -350,7 +379,7 @@ class _DecoderBase(nn.Module):
                     raise ValueError("forward_loss: pass `targets` when features is None (language-only "
                                      "pass: inputs captions[:, :-1], targets packed captions[:, 1:])")
                 targets = self._default_targets(captions, plan, True)
-            logits = self._vocab_logits(c.Hall)
+            logits = self._vocab_logits(c.Hall, c.Hb)
             row_loss = torch.empty(N, dtype=torch.float32, device=dev)
             argmax = torch.empty(N, dtype=torch.int64, device=dev)
             top5 = torch.empty(N, dtype=torch.int32, device=dev)
@@ -362,7 +391,7 @@ class _DecoderBase(nn.Module):
             ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
             if backward:
                 gbuf = self._grad_target(c.grad_names + list(self._out_names()))
-                dHall = self._vocab_backward(c.Hall, logits, gbuf)
+                dHall = self._vocab_backward(c.Hall, logits, gbuf, c.Hb)
                 if grad_hook is not None and gbuf is self.arena().gflat:
                     grad_hook(list(self._out_names()))       # bucket 0 is final: overlap its all-reduce
                 need_dfeat = features is not None and features.requires_grad

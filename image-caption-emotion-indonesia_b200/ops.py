@@ -196,3 +196,19 @@ def to_bf16_padded(x, pad_to=8):
     out = torch.empty(R, Cp, dtype=torch.bfloat16, device=x.device)
     cast_bf16(x, R, C, x.stride(0), out, Cp, Cp)
     return out
+
+
+def recur_fwd_bf16(cell, H, B, bs, off, t0, t1, XP, Whh_b, bhh, h_init, Hall, Hb, Hprevb, Call, gates, c_state):
+    ws = _recur_ws(XP.device, t1 + 1)
+    check(lib().sn_recur_fwd_bf16(cell, H, B, _ptr(bs), _ptr(off), t0, t1, _ptr(_req(XP)),
+                                  _ptr(_req(Whh_b, torch.bfloat16)), _ptr(bhh), _ptr(h_init), _ptr(Hall),
+                                  _ptr(_req(Hb, torch.bfloat16)), _ptr(Hprevb), _ptr(Call), _ptr(gates),
+                                  _ptr(c_state), _ptr(ws), _stream()), "sn_recur_fwd_bf16")
+
+
+def recur_bwd_bf16(cell, H, B, bs, off, t0, t1, Whh_b, c_init, Call, gates, dHall, dZ, dZb, dh_carry, dc_carry):
+    ws = _recur_ws(dZb.device, t1 + 1)
+    check(lib().sn_recur_bwd_bf16(cell, H, B, _ptr(bs), _ptr(off), t0, t1, _ptr(_req(Whh_b, torch.bfloat16)),
+                                  _ptr(c_init), _ptr(Call), _ptr(gates), _ptr(_req(dHall)), _ptr(dZ),
+                                  _ptr(_req(dZb, torch.bfloat16)), _ptr(dh_carry), _ptr(dc_carry), _ptr(ws),
+                                  _stream()), "sn_recur_bwd_bf16")

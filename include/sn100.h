@@ -125,6 +125,23 @@ int32_t sn_recur_bwd(int32_t cell, int64_t H, int64_t B, const int32_t* batch_si
                      const float* c_init, const float* Call, const float* gates, const float* dHall,
                      float* dZ, float* dh_carry, float* dc_carry, void* ws, void* stream);
 
+/* bf16-mode variants of K3: W_hh (bf16 copy, [4H,H]) and the inter-SM exchange (h_t / dZ_t) are bf16, the
+ * per-step contraction runs on the tensor cores with fp32 accumulation; state, gates and gradients fp32.
+ *   Hb [N,H] bf16     h_t per packed row (output; exchange buffer and operand of the vocab projection)
+ *   Hprevb [N,H] bf16 h_{t-1} per packed row (output, may be NULL)
+ *   Hall [N,H] fp32   optional fp32 copy of h_t (may be NULL)
+ *   dZb [N,4H] bf16   output: dXP in bf16 (exchange buffer and GEMM operand); dZ fp32 copy optional (NULL ok) */
+int32_t sn_recur_fwd_bf16(int32_t cell, int64_t H, int64_t B, const int32_t* batch_sizes,
+                          const int32_t* offsets, int32_t t0, int32_t t1, const float* XP,
+                          const void* Whh_bf16, const float* bhh, const float* h_init, float* Hall,
+                          void* Hb, void* Hprevb, float* Call, float* gates, float* c_state, void* ws,
+                          void* stream);
+int32_t sn_recur_bwd_bf16(int32_t cell, int64_t H, int64_t B, const int32_t* batch_sizes,
+                          const int32_t* offsets, int32_t t0, int32_t t1, const void* Whh_bf16,
+                          const float* c_init, const float* Call, const float* gates,
+                          const float* dHall, float* dZ, void* dZb, float* dh_carry, float* dc_carry,
+                          void* ws, void* stream);
+
 /* ---- K5/K6: log-softmax + NLL (+ gradient) over logits, arg-max, top-5 ------------------------
  * replaces nn.CrossEntropyLoss (train_multitask.py:134,383), output.max(1) (model.py:190) and
  * utils.accuracy top-5 (utils.py:127-140).

@@ -212,3 +212,66 @@ def test_gemm_tcgen05_grouped(ops):
     want = torch.cat([A[:, i * F:(i + 1) * F].double() @ B[i].double().t() + bias[i * H:(i + 1) * H].double()
                       for i in range(4)], 1)
     assert _rel(C, want) < 1e-5
+
+
+@pytest.mark.parametrize("cell", [0, 1])
+@pytest.mark.parametrize("B,H,lengths", [
+    (5, 32, [7, 6, 4, 3, 3]),
+    (96, 512, None),
+    (64, 256, "ragged"),
+    (200, 64, "ragged"),
+])
+def test_recurrence_bf16_fwd_bwd(ops, cell, B, H, lengths):
+    """bf16 tensor-core K3 against a float64 unroll that applies the same bf16 rounding to W_hh and to the
+    exchanged h / dZ (so the comparison isolates the kernel, tolerance 2e-3) ."""
+    import icei_b200
+    T = 9
+    g = torch.Generator().manual_seed(B * 7 + H + cell + 100)
+    if lengths is None:
+        lengths = [T] * B
+    elif lengths == "ragged":
+        lengths = sorted(torch.randint(2, T + 1, (B,), generator=g).tolist(), reverse=True)
+        lengths[0] = T
+    plan = icei_b200.get_plan(lengths)
+    d = plan.dev("cuda")
+    N, T = plan.N, plan.T
+    XP = (torch.randn(N, 4 * H, generator=g) * 0.7).cuda()
+    W = (torch.randn(4 * H, H, generator=g) / H ** 0.5).cuda()
+    Wb = W.bfloat16().contiguous()
+    bhh = (torch.randn(4 * H, generator=g) * 0.1).cuda()
+    dH = torch.randn(N, H, generator=g).cuda()
+    Hall = torch.empty(N, H, device="cuda"); Call = torch.empty(N, H, device="cuda")
+    Hb = torch.empty(N, H, device="cuda", dtype=torch.bfloat16); Hpb = torch.empty_like(Hb)
+    gates = torch.empty(N, 4 * H, device="cuda")
+    cst = torch.zeros(B, H, device="cuda")
+    ops.recur_fwd_bf16(cell, H, B, d["bs"], d["off"], 0, T, XP, Wb, bhh, None, Hall, Hb, Hpb, Call, gates, cst)
+    dZ = torch.empty(N, 4 * H, device="cuda"); dZb = torch.empty(N, 4 * H, device="cuda", dtype=torch.bfloat16)
+    dh = torch.zeros(B, H, device="cuda"); dc = torch.zeros(B, H, device="cuda")
+    ops.recur_bwd_bf16(cell, H, B, d["bs"], d["off"], 0, T, Wb, None, Call, gates, dH, dZ, dZb, dh, dc)
+    torch.cuda.synchronize()
+    # reference with the same roundings: h and W_hh rounded to bf16 where they enter the contraction
+    w = Wb.double().cpu()
+    b = bhh.double().cpu()
+    xp = XP.double().cpu()
+    h = torch.zeros(B, H, dtype=torch.float64); c = torch.zeros(B, H, dtype=torch.float64)
+    hs = []
+    for t, bt in enumerate(plan.bs):
+        hq = h[:bt].bfloat16().double()
+        z = xp[plan.off[t]:plan.off[t] + bt] + hq @ w.t() + b
+        if cell == 0:
+            i, f, o, gg = z[:, :H], z[:, H:2 * H], z[:, 2 * H:3 * H], z[:, 3 * H:]
+        else:
+            i, f, gg, o = z[:, :H], z[:, H:2 * H], z[:, 2 * H:3 * H], z[:, 3 * H:]
+        c = torch.sigmoid(f) * c[:bt] + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * (c if cell == 0 else torch.tanh(c))
+        hs.append(h)
+    hall = torch.cat(hs, 0)
+    assert _rel(Hall.cpu(), hall) < 2e-3
+    assert _rel(Hb.float().cpu(), hall) < 6e-3
+    # backward vs the fp32 kernel on the same saved activations (only the dZ exchange is rounded)
+    dZ32 = torch.empty(N, 4 * H, device="cuda")
+    dh2 = torch.zeros(B, H, device="cuda"); dc2 = torch.zeros(B, H, device="cuda")
+    ops.recur_bwd(cell, H, B, d["bs"], d["off"], 0, T, Wb.float(), None, Call, gates, dH, dZ32, dh2, dc2)
+    assert _rel(dZ, dZ32) < 1e-2
+    assert _rel(dZb.float(), dZ32) < 1.5e-2
+    assert _rel(dh, dh2) < 1e-2 and _rel(dc, dc2) < 1e-2
