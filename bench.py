@@ -200,13 +200,26 @@ def run_gpu(args):
     random.seed(0)
     flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device=dev)   # 512 MiB > L2
 
+    graphed = None
+    launches_per_step = None
+    if not args.no_graph:
+        # the whole step (fwd + loss + bwd [+ all-reduce] + clamp/Adam) captured once, replayed per step
+        ops.LAUNCHES[0] = 0
+        graphed = sn.GraphedTrainStep(trainer, cap_d, lens, feat_d, warmup=3, mode=MODE, teacher_forcing_ratio=1.0)
+        launches_per_step = ops.LAUNCHES[0] // 4          # 3 warm-up runs + 1 capture run
+
     def step_resident():
+        if graphed is not None:
+            return graphed()
         return trainer.step(cap_d, lens, feat_d, mode=MODE, teacher_forcing_ratio=1.0)
 
     def step_e2e():
-        c = cap_pin.to(dev, non_blocking=True)
-        f = feat_pin.to(dev, non_blocking=True)
-        loss, _ = trainer.step(c, lens, f, mode=MODE, teacher_forcing_ratio=1.0)
+        if graphed is not None:
+            loss, _ = graphed(cap_pin, feat_pin)          # pinned host -> static device buffers, then replay
+        else:
+            c = cap_pin.to(dev, non_blocking=True)
+            f = feat_pin.to(dev, non_blocking=True)
+            loss, _ = trainer.step(c, lens, f, mode=MODE, teacher_forcing_ratio=1.0)
         loss_pin.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_pin[0])
@@ -234,7 +247,7 @@ def run_gpu(args):
         e1.record()
         evs.append((e0, e1))
     barrier()
-    launches = ops.LAUNCHES[0]
+    launches = ops.LAUNCHES[0] if graphed is None else launches_per_step * args.steps
     ms = sum(a.elapsed_time(b) for a, b in evs)
     clocks = sampler.stop()
     t_local = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -270,7 +283,8 @@ def run_gpu(args):
             "config": workload_config(world, arith),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "timing": "wall clock incl. python, pinned H2D of captions+features, D2H loss, sync per step"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
+            "gpu_launches": launches, "launch_mode": "cuda-graph replay of the captured step" if graphed is not None
+            else "eager (python-issued launches)", "clocks": clocks, "roofline": roof, "kernels": kernels,
         }
     if world > 1:
         dist.barrier()
@@ -284,23 +298,19 @@ def run_gpu(args):
 
 
 def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src):
-    """Per-kernel device time (CUDA events, L2 flushed) of the dominant HBM-bound kernels of one step, and
-    the roofline object for the dominant one.  ALGORITHMIC bytes per launch as defined in DESIGN.md."""
+    """Per-kernel device time (CUDA events, L2 flushed) of the HBM-bound kernels of one step, the roofline
+    object for the dominant one, and a large-batch point of the same kernel (B=4096/GPU) where the serial
+    chain no longer hides the memory system.  ALGORITHMIC bytes per launch as defined in DESIGN.md."""
     import torch
     import icei_b200 as sn
     from icei_b200 import ops
     dev = cap_d.device
-    plan = sn.get_plan(lens)
-    d = plan.dev(dev)
-    N, B, TT = plan.N, plan.B, plan.T
     f32 = dict(dtype=torch.float32, device=dev)
-    XP = torch.randn(N, 4 * H, **f32)
-    Whh, bhh = dec._recurrent_weights()
-    Hall, Call, Hprev = torch.empty(N, H, **f32), torch.empty(N, H, **f32), torch.empty(N, H, **f32)
-    gates = torch.empty(N, 4 * H, **f32)
-    dH = torch.randn(N, H, **f32)
-    dZ = torch.empty(N, 4 * H, **f32)
+    b16 = dict(dtype=torch.bfloat16, device=dev)
     flush = torch.empty(64 * 1024 * 1024, **f32)
+    bf16 = dec.bf16
+    Whh, bhh = dec._recurrent_weights()
+    Wb = Whh.bfloat16().contiguous()
 
     def timeit(fn, reps=5):
         fn()
@@ -313,14 +323,49 @@ def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src):
             tot += e0.elapsed_time(e1)
         return tot / reps
 
-    def fwd():
-        cst = torch.zeros(B, H, **f32)
-        ops.recur_fwd(dec.cell, H, B, d["bs"], d["off"], 0, TT, XP, Whh, bhh, None, Hall, Call, Hprev, gates, cst)
+    def recur_pair(lengths):
+        plan = sn.get_plan(lengths)
+        d = plan.dev(dev)
+        N, B, TT = plan.N, plan.B, plan.T
+        XP = torch.randn(N, 4 * H, **f32)
+        Hall, Call = torch.empty(N, H, **f32), torch.empty(N, H, **f32)
+        gates = torch.empty(N, 4 * H, **f32)
+        dH = torch.randn(N, H, **f32)
+        dZ = torch.empty(N, 4 * H, **f32)
+        if bf16:
+            Hb, Hpb, dZb = torch.empty(N, H, **b16), torch.empty(N, H, **b16), torch.empty(N, 4 * H, **b16)
 
-    def bwd():
-        dh, dc = torch.zeros(B, H, **f32), torch.zeros(B, H, **f32)
-        ops.recur_bwd(dec.cell, H, B, d["bs"], d["off"], 0, TT, Whh, None, Call, gates, dH, dZ, dh, dc)
+            def fwd():
+                cst = torch.zeros(B, H, **f32)
+                ops.recur_fwd_bf16(dec.cell, H, B, d["bs"], d["off"], 0, TT, XP, Wb, bhh, None, Hall, Hb, Hpb, Call,
+                                   gates, cst)
 
+            def bwd():
+                dh, dc = torch.zeros(B, H, **f32), torch.zeros(B, H, **f32)
+                ops.recur_bwd_bf16(dec.cell, H, B, d["bs"], d["off"], 0, TT, Wb, None, Call, gates, dH, dZ, dZb, dh, dc)
+            # XP + c in/out + gates + h fp32 + h bf16 x2 ; W_hh bf16 once
+            by_f = N * H * (16 + 8 + 16 + 4 + 4) + 4 * H * H * 2
+            by_b = N * H * (16 + 16 + 8 + 4 + 8 + 8) + 4 * H * H * 2
+            names = ("recur_fwd_bf16_kernel", "recur_bwd_bf16_kernel")
+        else:
+            Hprev = torch.empty(N, H, **f32)
+
+            def fwd():
+                cst = torch.zeros(B, H, **f32)
+                ops.recur_fwd(dec.cell, H, B, d["bs"], d["off"], 0, TT, XP, Whh, bhh, None, Hall, Call, Hprev, gates, cst)
+
+            def bwd():
+                dh, dc = torch.zeros(B, H, **f32), torch.zeros(B, H, **f32)
+                ops.recur_bwd(dec.cell, H, B, d["bs"], d["off"], 0, TT, Whh, None, Call, gates, dH, dZ, dh, dc)
+            by_f = N * H * 48 + 4 * H * H * 4
+            by_b = N * H * 52 + 4 * H * H * 4
+            names = ("recur_fwd_kernel", "recur_bwd_kernel")
+        t_f, t_b = timeit(fwd), timeit(bwd)
+        return {names[0]: {"ms": t_f, "alg_bytes": by_f, "gbs": by_f / t_f / 1e6},
+                names[1]: {"ms": t_b, "alg_bytes": by_b, "gbs": by_b / t_b / 1e6}}
+
+    kernels = recur_pair(lens)
+    N = sum(lens)
     logits = torch.randn(N, V, **f32)
     tgt = torch.randint(0, V, (N,), device=dev)
     rl = torch.empty(N, **f32)
@@ -328,20 +373,29 @@ def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src):
     def smx():
         ops.softmax_nll(logits, N, V, targets=tgt, row_loss=rl, dlogits=logits, grad_scale=1.0 / N)
 
-    t_f, t_b, t_s = timeit(fwd), timeit(bwd), timeit(smx)
-    by_f = N * H * 48 + 4 * H * H * 4          # XP + h,c in/out + saved gates, + W_hh once
-    by_b = N * H * (16 + 16 + 4 + 8 + 8) + 4 * H * H * 4   # gates + dZ + dHall + c_t,c_{t-1} + dc carry
-    by_s = N * V * 8                           # logits read + gradient written in place
-    kernels = {
-        "recur_fwd_kernel": {"ms": t_f, "alg_bytes": by_f, "gbs": by_f / t_f / 1e6},
-        "recur_bwd_kernel": {"ms": t_b, "alg_bytes": by_b, "gbs": by_b / t_b / 1e6},
-        "softmax_nll_kernel": {"ms": t_s, "alg_bytes": by_s, "gbs": by_s / t_s / 1e6},
-    }
-    dom = max(("recur_fwd_kernel", "recur_bwd_kernel"), key=lambda k: kernels[k]["ms"])
+    t_s = timeit(smx)
+    kernels["softmax_nll_kernel"] = {"ms": t_s, "alg_bytes": N * V * 8, "gbs": N * V * 8 / t_s / 1e6}
+    a = dec.arena()
+    npar = a.total
+    m_, v_ = torch.zeros_like(a.flat), torch.zeros_like(a.flat)
+    pcopy, gcopy = a.flat.clone(), torch.randn_like(a.flat) * 0.01
+
+    def adam():
+        ops.adam_clamp(pcopy, gcopy, m_, v_, [(0, npar)], [1e-3], [0.1], 0.9, 0.999, 1e-8, 0.5)
+
+    t_a = timeit(adam)
+    kernels["adam_clamp_kernel"] = {"ms": t_a, "alg_bytes": npar * 28, "gbs": npar * 28 / t_a / 1e6}
+    del logits, m_, v_, pcopy, gcopy
+    big = recur_pair([T] * 4096)
+    dom = max((k for k in kernels if k.startswith("recur")), key=lambda k: kernels[k]["ms"])
     ach = kernels[dom]["gbs"]
     roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
             "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-            "note": "latency-bound at B=96 (T serial steps with an inter-SM exchange each); see DESIGN.md"}
+            "note": "latency-bound at B=96: T serial steps, each with an inter-SM exchange through L2 (DESIGN.md 4). "
+                    "Same kernel at B=4096/GPU (bandwidth regime): %.0f GB/s = %.2f of peak"
+                    % (big[dom]["gbs"], big[dom]["gbs"] / hbm_peak),
+            "large_batch": {"B": 4096, "achieved": big[dom]["gbs"], "frac": big[dom]["gbs"] / hbm_peak}}
+    kernels["large_batch_B4096"] = big
     return roof, kernels
 
 
@@ -352,6 +406,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every launch from python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     args = ap.parse_args()

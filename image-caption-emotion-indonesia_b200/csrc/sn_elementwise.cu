@@ -14,7 +14,8 @@ __global__ void gather_pack_fwd_kernel(const int64_t* __restrict__ captions, int
                                        const int32_t* __restrict__ row_b, const int32_t* __restrict__ row_t,
                                        const int32_t* __restrict__ tok_override, int64_t N,
                                        float* __restrict__ X, int64_t ldx, float p, float inv_keep,
-                                       uint64_t seed) {
+                                       uint64_t seed, const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;
   // one warp per packed row
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= N) return;
@@ -40,7 +41,8 @@ __global__ void gather_pack_bwd_kernel(const int64_t* __restrict__ captions, int
                                        const int32_t* __restrict__ row_t,
                                        const int32_t* __restrict__ tok_override, int64_t N,
                                        const float* __restrict__ dX, int64_t ldx, float p, float inv_keep,
-                                       uint64_t seed) {
+                                       uint64_t seed, const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= N) return;
   int lane = threadIdx.x & 31;
@@ -168,24 +170,67 @@ struct AdamRanges {
   static constexpr int MAX = 48;
   int64_t off[MAX], len[MAX];
   float step_size[MAX], bc2_sqrt[MAX];
+  int step_idx[MAX];              // device-step mode: index into steps_dev
   int64_t chunk_start[MAX + 1];   // prefix of per-range chunk counts
   int n;
 };
+
+// device-step mode: bump the step counter of every range's parameter and derive the bias-corrected
+// coefficients exactly like torch.optim.Adam does on the host (double precision)
+__global__ void adam_prepare_kernel(AdamRanges R, int32_t* __restrict__ steps, const float* __restrict__ lr,
+                                    float* __restrict__ coef, float beta1, float beta2) {
+  int r = threadIdx.x;
+  if (r >= R.n) return;
+  int st = steps[R.step_idx[r]] + 1;
+  steps[R.step_idx[r]] = st;
+  double bc1 = 1.0 - pow((double)beta1, (double)st);
+  double bc2 = 1.0 - pow((double)beta2, (double)st);
+  coef[2 * r] = (float)((double)(*lr) / bc1);
+  coef[2 * r + 1] = (float)sqrt(bc2);
+}
 constexpr int ADAM_CHUNK = 4096;   // elements per CTA-iteration
 
 __global__ void __launch_bounds__(256) adam_clamp_kernel(float* __restrict__ p, float* __restrict__ g,
                                                          float* __restrict__ m, float* __restrict__ v,
-                                                         AdamRanges R, float beta1, float beta2, float eps,
-                                                         float clip) {
+                                                         AdamRanges R, const float* __restrict__ coef, float beta1,
+                                                         float beta2, float eps, float clip) {
   const int64_t total_chunks = R.chunk_start[R.n];
   for (int64_t ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
     int r = 0;
     while (ch >= R.chunk_start[r + 1]) ++r;
     const int64_t base = R.off[r] + (ch - R.chunk_start[r]) * ADAM_CHUNK;
     const int64_t end = R.off[r] + R.len[r];
-    const float ss = R.step_size[r], bc = R.bc2_sqrt[r];
-#pragma unroll 4
-    for (int64_t i = base + threadIdx.x; i < base + ADAM_CHUNK && i < end; i += 256) {
+    const float ss = coef ? coef[2 * r] : R.step_size[r], bc = coef ? coef[2 * r + 1] : R.bc2_sqrt[r];
+    const int64_t lim = base + ADAM_CHUNK < end ? base + ADAM_CHUNK : end;
+    if ((base & 3) == 0 && lim - base == ADAM_CHUNK) {
+      // full, 16-byte aligned chunk: 128-bit loads/stores, 4 independent elements per thread per pass
+#pragma unroll
+      for (int it = 0; it < ADAM_CHUNK / (256 * 4); ++it) {
+        const int64_t i = base + (int64_t)(it * 256 + threadIdx.x) * 4;
+        float4 g4 = *reinterpret_cast<const float4*>(g + i);
+        float4 m4 = *reinterpret_cast<const float4*>(m + i);
+        float4 v4 = *reinterpret_cast<const float4*>(v + i);
+        float4 p4 = *reinterpret_cast<const float4*>(p + i);
+        float* gp = &g4.x; float* mp = &m4.x; float* vp = &v4.x; float* pp = &p4.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float gi = gp[e];
+          if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+          gp[e] = gi;
+          float mi = mp[e] + (1.f - beta1) * (gi - mp[e]);
+          float vi = vp[e] * beta2 + (1.f - beta2) * gi * gi;
+          float denom = sqrtf(vi) / bc + eps;
+          pp[e] = pp[e] - ss * (mi / denom);
+          mp[e] = mi; vp[e] = vi;
+        }
+        if (clip > 0.f) *reinterpret_cast<float4*>(g + i) = g4;       // clamp_ is in place (utils.py:60)
+        *reinterpret_cast<float4*>(m + i) = m4;
+        *reinterpret_cast<float4*>(v + i) = v4;
+        *reinterpret_cast<float4*>(p + i) = p4;
+      }
+      continue;
+    }
+    for (int64_t i = base + threadIdx.x; i < lim; i += 256) {
       float gi = g[i];
       if (clip > 0.f) { gi = fminf(fmaxf(gi, -clip), clip); g[i] = gi; }   // clamp_ is in place (utils.py:60)
       float mi = m[i], vi = v[i];
@@ -215,7 +260,8 @@ extern "C" {
 int32_t sn_gather_pack_fwd(const int64_t* captions, int64_t cap_ld, const float* table, int64_t E,
                            const float* features, int64_t feat_ld, int32_t has_feat,
                            const int32_t* row_b, const int32_t* row_t, const int32_t* tok_override,
-                           int64_t N, float* X, int64_t ldx, float p_drop, uint64_t seed, void* stream) {
+                           int64_t N, float* X, int64_t ldx, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                           void* stream) {
   SN_REQUIRE(N >= 0 && E > 0 && ldx >= E, "sn_gather_pack_fwd: bad dims N=%lld E=%lld ldx=%lld", (long long)N, (long long)E, (long long)ldx);
   SN_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "sn_gather_pack_fwd: dropout p=%f out of [0,1)", p_drop);
   SN_REQUIRE(!has_feat || features, "sn_gather_pack_fwd: has_feat without features");
@@ -224,14 +270,15 @@ int32_t sn_gather_pack_fwd(const int64_t* captions, int64_t cap_ld, const float*
   unsigned grid = (unsigned)((N + 7) / 8);
   gather_pack_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(captions, cap_ld, table, (int)E, features, feat_ld,
                                                                  has_feat, row_b, row_t, tok_override, N, X, ldx,
-                                                                 p_drop, inv_keep, seed);
+                                                                 p_drop, inv_keep, seed, seed_dev);
   return sn::check_launch("sn_gather_pack_fwd");
 }
 
 int32_t sn_gather_pack_bwd(const int64_t* captions, int64_t cap_ld, float* dtable, int64_t E,
                            float* dfeatures, int64_t feat_ld, int32_t has_feat, const int32_t* row_b,
                            const int32_t* row_t, const int32_t* tok_override, int64_t N,
-                           const float* dX, int64_t ldx, float p_drop, uint64_t seed, void* stream) {
+                           const float* dX, int64_t ldx, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                           void* stream) {
   SN_REQUIRE(N >= 0 && E > 0 && ldx >= E, "sn_gather_pack_bwd: bad dims");
   SN_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "sn_gather_pack_bwd: dropout p=%f out of [0,1)", p_drop);
   if (N == 0) return 0;
@@ -239,7 +286,7 @@ int32_t sn_gather_pack_bwd(const int64_t* captions, int64_t cap_ld, float* dtabl
   unsigned grid = (unsigned)((N + 7) / 8);
   gather_pack_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(captions, cap_ld, dtable, (int)E, dfeatures, feat_ld,
                                                                  has_feat, row_b, row_t, tok_override, N, dX, ldx,
-                                                                 p_drop, inv_keep, seed);
+                                                                 p_drop, inv_keep, seed, seed_dev);
   return sn::check_launch("sn_gather_pack_bwd");
 }
 
@@ -289,11 +336,36 @@ int32_t sn_adam_clamp(float* p, float* g, float* m, float* v, int32_t n_ranges, 
     if (chunks == 0) continue;
     int64_t cap = (int64_t)sn::dev_info().sm_count * 8;
     unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
-    adam_clamp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, R, beta1, beta2, eps, clip);
+    adam_clamp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, R, nullptr, beta1, beta2, eps, clip);
     int32_t rc = sn::check_launch("sn_adam_clamp");
     if (rc) return rc;
   }
   return 0;
+}
+
+int32_t sn_adam_clamp_dev(float* p, float* g, float* m, float* v, int32_t n_ranges, const int64_t* ranges,
+                          const int32_t* step_idx, int32_t* steps_dev, const float* lr_dev, float* coef_ws,
+                          float beta1, float beta2, float eps, float clip, void* stream) {
+  SN_REQUIRE(n_ranges >= 0 && n_ranges <= AdamRanges::MAX, "sn_adam_clamp_dev: at most %d ranges per call", AdamRanges::MAX);
+  SN_REQUIRE(steps_dev && lr_dev && coef_ws, "sn_adam_clamp_dev: null argument");
+  if (n_ranges == 0) return 0;
+  AdamRanges R;
+  R.n = n_ranges;
+  R.chunk_start[0] = 0;
+  for (int i = 0; i < n_ranges; ++i) {
+    R.off[i] = ranges[2 * i]; R.len[i] = ranges[2 * i + 1]; R.step_idx[i] = step_idx[i];
+    R.step_size[i] = 0.f; R.bc2_sqrt[i] = 1.f;
+    SN_REQUIRE(R.off[i] >= 0 && R.len[i] >= 0, "sn_adam_clamp_dev: bad range %d", i);
+    R.chunk_start[i + 1] = R.chunk_start[i] + (R.len[i] + ADAM_CHUNK - 1) / ADAM_CHUNK;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_prepare_kernel<<<1, 64, 0, st>>>(R, steps_dev, lr_dev, coef_ws, beta1, beta2);
+  int64_t chunks = R.chunk_start[R.n];
+  if (chunks == 0) return sn::check_launch("sn_adam_clamp_dev");
+  int64_t cap = (int64_t)sn::dev_info().sm_count * 8;
+  unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
+  adam_clamp_kernel<<<grid, 256, 0, st>>>(p, g, m, v, R, coef_ws, beta1, beta2, eps, clip);
+  return sn::check_launch("sn_adam_clamp_dev");
 }
 
 int32_t sn_mean_pixels(const float* feat, int64_t B, int64_t P, int64_t D, float* out, void* stream) {

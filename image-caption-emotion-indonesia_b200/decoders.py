@@ -133,6 +133,20 @@ class _DecoderBase(nn.Module):
     def _publish(self, names, gbuf):
         self.arena().publish_grads(names, gbuf)
 
+    def _next_seed(self, dev, p_drop):
+        """Dropout randomness = hash(seed + device counter, row, col).  The counter lives in device memory
+        and is bumped by a (graph-capturable) device op once per forward, so CUDA-graph replays draw a fresh
+        mask every step."""
+        base = int(self.__dict__.get("_seed", 0x5EED)) * 1000003
+        if p_drop <= 0.0:
+            return base, None
+        sd = self.__dict__.get("_seed_dev")
+        if sd is None or sd.device != dev:
+            sd = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.__dict__["_seed_dev"] = sd
+        sd.add_(1)
+        return base, sd
+
     def _check_inputs(self, captions, features):
         if not captions.is_cuda:
             raise ops._lib.SnError("decoder inputs must be CUDA tensors: this path has no CPU fallback")
@@ -168,8 +182,7 @@ class _DecoderBase(nn.Module):
         c = _Ctx()
         c.plan, c.mode, c.has_feat, c.captions = plan, mode, has_feat, captions
         c.p_drop = float(self.dropout.p) if self.training else 0.0
-        self.__dict__["_calls"] = self.__dict__.get("_calls", 0) + 1
-        c.seed = (int(self.__dict__.get("_seed", 0x5EED)) * 1000003 + self._calls) & 0xFFFFFFFFFFFF
+        c.seed, c.seed_dev = self._next_seed(dev, c.p_drop)
         feats = None
         if has_feat:
             feats = features.detach()
@@ -183,7 +196,7 @@ class _DecoderBase(nn.Module):
             c.tok_override = torch.full((N,), -1, dtype=torch.int32, device=dev)
         X = torch.empty(N, E, dtype=torch.float32, device=dev)
         ops.gather_pack_fwd(captions, emb.weight, feats, has_feat, d["row_b"], d["row_t"], None, N, X,
-                            c.p_drop, c.seed)
+                            c.p_drop, c.seed, seed_dev=c.seed_dev)
         c.X = X
         c.XP = torch.empty(N, 4 * H, dtype=torch.float32, device=dev)
         c.w16 = {}      # bf16 weight shadows of this call (refreshed every forward)
@@ -241,7 +254,7 @@ class _DecoderBase(nn.Module):
                         pred = am[:bp].to(torch.int32)
                     c.tok_override[r0:r0 + bt] = pred[:bt]
                     ops.gather_pack_fwd(captions, emb.weight, feats, has_feat, d["row_b"], d["row_t"],
-                                        c.tok_override, bt, X, c.p_drop, c.seed, row_off=r0)
+                                        c.tok_override, bt, X, c.p_drop, c.seed, row_off=r0, seed_dev=c.seed_dev)
                     self._input_projection(c, X, mode, r0, bt)
                     run(t, t + 1)
                     t += 1
@@ -295,7 +308,7 @@ class _DecoderBase(nn.Module):
         gE.zero_()
         dfeat = torch.empty(B, E, dtype=torch.float32, device=dev) if (need_dfeat and c.has_feat) else None
         ops.gather_pack_bwd(c.captions, gE, dfeat, c.has_feat, d["row_b"], d["row_t"], c.tok_override, N, dX,
-                            c.p_drop, c.seed)
+                            c.p_drop, c.seed, seed_dev=c.seed_dev)
         if dfeat is not None and c.feat_shape is not None:
             dfeat = dfeat.view(c.feat_shape)
         return dfeat

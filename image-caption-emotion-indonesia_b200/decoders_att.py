@@ -104,8 +104,7 @@ class _AttBase(_DecoderBase):
         c.plan, c.mode, c.captions, c.has_feat = plan, mode, captions, False
         c.feats, c.P = feats, P
         c.p_drop = float(self.dropout.p) if self.training else 0.0
-        self.__dict__["_calls"] = self.__dict__.get("_calls", 0) + 1
-        c.seed = (int(self.__dict__.get("_seed", 0x5EED)) * 1000003 + self._calls) & 0xFFFFFFFFFFFF
+        c.seed, c.seed_dev = self._next_seed(dev, c.p_drop)
         f32 = dict(dtype=torch.float32, device=dev)
         # hoisted, time-invariant pieces
         c.mean = torch.empty(B, D, **f32)
@@ -116,7 +115,8 @@ class _AttBase(_DecoderBase):
         all_tf = all(coins)
         c.tok_override = None if all_tf else torch.full((N,), -1, dtype=torch.int32, device=dev)
         c.X = torch.empty(N, E, **f32)
-        ops.gather_pack_fwd(captions, emb.weight, None, False, d["row_b"], d["row_t"], None, N, c.X, c.p_drop, c.seed)
+        ops.gather_pack_fwd(captions, emb.weight, None, False, d["row_b"], d["row_t"], None, N, c.X, c.p_drop, c.seed,
+                            seed_dev=c.seed_dev)
         c.XP = torch.empty(N, 4 * H, **f32)
         self._proj_embed_part(c, 0, N)
         c.CTX = torch.empty(N, D, **f32)
@@ -151,7 +151,7 @@ class _AttBase(_DecoderBase):
                     pred = am[:bp].to(torch.int32)
                 c.tok_override[r0:r0 + n] = pred[:n]
                 ops.gather_pack_fwd(captions, emb.weight, None, False, d["row_b"], d["row_t"], c.tok_override, n,
-                                    c.X, c.p_drop, c.seed, row_off=r0)
+                                    c.X, c.p_drop, c.seed, row_off=r0, seed_dev=c.seed_dev)
                 self._proj_embed_part(c, r0, n)
             ops.gemm(ops.OP_NT, hprev, att.decoder_att.weight, c.att2, n, A, H, H, H, A, bias=att.decoder_att.bias,
                      c_off=r0 * A)
@@ -225,7 +225,8 @@ class _AttBase(_DecoderBase):
         dX = self._proj_weight_grads(c, dZ, gbuf)
         gE = self._gview(gbuf, [self._emb_name()], emb.weight.shape)
         gE.zero_()
-        ops.gather_pack_bwd(c.captions, gE, None, False, d["row_b"], d["row_t"], c.tok_override, N, dX, c.p_drop, c.seed)
+        ops.gather_pack_bwd(c.captions, gE, None, False, d["row_b"], d["row_t"], c.tok_override, N, dX, c.p_drop, c.seed,
+                            seed_dev=c.seed_dev)
         if need_dfeat:
             dmean = torch.empty(B, D, **f32)
             ops.gemm(ops.OP_NN, dh, self.init_h.weight, dmean, B, D, H, H, D, D)

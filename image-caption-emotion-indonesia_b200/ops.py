@@ -71,7 +71,7 @@ def colsum(X, M, N, ldx, out, beta=0.0, x_off=0, out_off=0):
 
 
 def gather_pack_fwd(captions, table, features, has_feat, row_b, row_t, tok_override, N, X, p_drop, seed,
-                    row_off=0):
+                    row_off=0, seed_dev=None):
     E = table.shape[1]
     cap = _req(captions, torch.int64)
     ro4 = 4 * row_off
@@ -82,10 +82,11 @@ def gather_pack_fwd(captions, table, features, has_feat, row_b, row_t, tok_overr
         ctypes.c_void_p(row_b.data_ptr() + ro4), ctypes.c_void_p(row_t.data_ptr() + ro4),
         ctypes.c_void_p(tok_override.data_ptr() + ro4) if tok_override is not None else None,
         N, ctypes.c_void_p(X.data_ptr() + 4 * row_off * X.stride(0)), X.stride(0), float(p_drop),
-        ctypes.c_uint64(seed), _stream()), "sn_gather_pack_fwd")
+        ctypes.c_uint64(seed), _ptr(seed_dev), _stream()), "sn_gather_pack_fwd")
 
 
-def gather_pack_bwd(captions, dtable, dfeatures, has_feat, row_b, row_t, tok_override, N, dX, p_drop, seed):
+def gather_pack_bwd(captions, dtable, dfeatures, has_feat, row_b, row_t, tok_override, N, dX, p_drop, seed,
+                    seed_dev=None):
     E = dtable.shape[1]
     cap = _req(captions, torch.int64)
     check(lib().sn_gather_pack_bwd(
@@ -93,7 +94,8 @@ def gather_pack_bwd(captions, dtable, dfeatures, has_feat, row_b, row_t, tok_ove
         _ptr(dfeatures) if dfeatures is not None else None,
         dfeatures.stride(0) if dfeatures is not None else 0, 1 if has_feat else 0,
         _ptr(row_b), _ptr(row_t), _ptr(tok_override) if tok_override is not None else None,
-        N, _ptr(_req(dX)), dX.stride(0), float(p_drop), ctypes.c_uint64(seed), _stream()), "sn_gather_pack_bwd")
+        N, _ptr(_req(dX)), dX.stride(0), float(p_drop), ctypes.c_uint64(seed), _ptr(seed_dev), _stream()),
+          "sn_gather_pack_bwd")
 
 
 _ws_cache = {}
@@ -212,3 +214,20 @@ def recur_bwd_bf16(cell, H, B, bs, off, t0, t1, Whh_b, c_init, Call, gates, dHal
                                   _ptr(c_init), _ptr(Call), _ptr(gates), _ptr(_req(dHall)), _ptr(dZ),
                                   _ptr(_req(dZb, torch.bfloat16)), _ptr(dh_carry), _ptr(dc_carry), _ptr(ws),
                                   _stream()), "sn_recur_bwd_bf16")
+
+
+def adam_clamp_dev(p, g, m, v, ranges, step_idx, steps_dev, lr_dev, coef_ws, beta1, beta2, eps, clip):
+    """Clamp + Adam with step counters / learning rate in device memory (CUDA-graph replayable)."""
+    n = len(ranges)
+    for i0 in range(0, n, 48):
+        k = min(48, n - i0)
+        R = (ctypes.c_int64 * (2 * k))()
+        S = (ctypes.c_int32 * k)()
+        for i in range(k):
+            R[2 * i], R[2 * i + 1] = ranges[i0 + i]
+            S[i] = step_idx[i0 + i]
+        check(lib().sn_adam_clamp_dev(_ptr(_req(p)), _ptr(_req(g)), _ptr(_req(m)), _ptr(_req(v)), k,
+                                      ctypes.cast(R, ctypes.c_void_p), ctypes.cast(S, ctypes.c_void_p),
+                                      _ptr(steps_dev), _ptr(lr_dev),
+                                      ctypes.c_void_p(coef_ws.data_ptr() + 4 * 2 * i0), beta1, beta2, eps, clip,
+                                      _stream()), "sn_adam_clamp_dev")

@@ -55,19 +55,21 @@ int32_t sn_device_info(int32_t* sm_count, int32_t* smem_optin, int32_t* cc_major
  * row r -> sample row_b[r], step row_t[r].  has_feat: step 0 is the image feature row.
  * tok_override (optional, [N]): if >= 0 the row embeds that id instead (scheduled sampling feedback,
  * model.py:184) and is NOT dropped out.  X is [N, ldx] fp32; columns >= E are left untouched.
- * dropout: keep-prob 1-p, scale 1/(1-p), counter-based RNG (seed, row, col); p = 0 disables. */
+ * dropout: keep-prob 1-p, scale 1/(1-p), counter-based RNG (seed, row, col); p = 0 disables.
+ * seed_dev (optional, device): added to `seed` at run time -- lets a captured CUDA graph draw a fresh
+ * mask on every replay (the caller bumps the device counter once per step). */
 int32_t sn_gather_pack_fwd(const int64_t* captions, int64_t cap_ld, const float* table, int64_t E,
                            const float* features, int64_t feat_ld, int32_t has_feat,
                            const int32_t* row_b, const int32_t* row_t, const int32_t* tok_override,
                            int64_t N, float* X, int64_t ldx, float p_drop, uint64_t seed,
-                           void* stream);
+                           const uint64_t* seed_dev, void* stream);
 /* backward of the above: dtable[id] += dX*mask (atomic, duplicates accumulate like nn.Embedding's
  * dense gradient), dfeatures[b] = dX[row(b,0)] (may be NULL). */
 int32_t sn_gather_pack_bwd(const int64_t* captions, int64_t cap_ld, float* dtable, int64_t E,
                            float* dfeatures, int64_t feat_ld, int32_t has_feat,
                            const int32_t* row_b, const int32_t* row_t, const int32_t* tok_override,
                            int64_t N, const float* dX, int64_t ldx, float p_drop, uint64_t seed,
-                           void* stream);
+                           const uint64_t* seed_dev, void* stream);
 
 /* ---- K2: GEMM (all nn.Linear call sites: V_g/S_*_g/U_g model.py:119-150, C model.py:189-194,
  * encoder_att/decoder_att/f_beta/init_h/init_c model_att.py:59-61,192-193,283, LSTMCell's two
@@ -163,6 +165,14 @@ int32_t sn_reduce_sum(const float* x, int64_t N, float scale, float* out, int32_
 int32_t sn_adam_clamp(float* p, float* g, float* m, float* v, int32_t n_ranges,
                       const int64_t* ranges, const float* step_size, const float* bc2_sqrt,
                       float beta1, float beta2, float eps, float clip, void* stream);
+
+/* Same kernel with the per-parameter step counters and the learning rate in DEVICE memory, so the whole
+ * training step can be replayed from a CUDA graph: a prologue kernel increments steps_dev[step_idx[r]] and
+ * derives lr/(1-beta1^t), sqrt(1-beta2^t) in double precision into coef_ws (2*n_ranges floats). */
+int32_t sn_adam_clamp_dev(float* p, float* g, float* m, float* v, int32_t n_ranges,
+                          const int64_t* ranges, const int32_t* step_idx, int32_t* steps_dev,
+                          const float* lr_dev, float* coef_ws, float beta1, float beta2, float eps,
+                          float clip, void* stream);
 
 /* ---- K4: soft attention step (scores -> softmax over pixels -> context -> f_beta gate) ----------
  * replaces Attention.forward after the hoisted encoder_att GEMM (model_att.py:61-70) and the gate

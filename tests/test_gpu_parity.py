@@ -276,3 +276,30 @@ def test_bf16_mode_within_2e2(which, B, T, V, E, H, F):
     for n, p in dec.named_parameters():
         if p.grad is not None:
             assert rel_l2(p.grad.cpu(), gref[n]) < 2e-2, n
+
+
+def test_graphed_train_step_matches_eager():
+    """A CUDA-graph replay is a real training step: 3 replays == 3 eager steps (same weights afterwards)."""
+    import icei_b200 as sn
+    from oracle import port
+    V, E, H, F, B, T = 300, 28, 64, 72, 12, 8
+    torch.manual_seed(0)
+    make = lambda: sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0).cuda().train()
+    d1, d2 = make(), make()
+    d2.load_state_dict(d1.state_dict())
+    cap, lens, feats = port.synthetic_batch(B, T, V, E=E, ragged=True, seed=9)
+    cap, feats = cap.cuda(), feats.cuda()
+    t1 = sn.DataParallelTrainer(d1, sn.FusedClampAdam(d1, lr=1e-3))
+    t2 = sn.DataParallelTrainer(d2, sn.FusedClampAdam(d2, lr=1e-3))
+    g = sn.GraphedTrainStep(t2, cap, lens, feats, warmup=1, mode="happy", teacher_forcing_ratio=1.0)
+    n_eager = 1            # GraphedTrainStep ran 1 real warm-up step on d2 (the capture pass only records)
+    for _ in range(n_eager):
+        t1.step(cap, lens, feats, mode="happy", teacher_forcing_ratio=1.0)
+    for _ in range(3):
+        l1, _ = t1.step(cap, lens, feats, mode="happy", teacher_forcing_ratio=1.0)
+        l2, _ = g()
+    torch.cuda.synchronize()
+    assert abs(l1.item() - l2.item()) < 1e-5 * abs(l1.item())
+    for (n, p), (_, q) in zip(d1.named_parameters(), d2.named_parameters()):
+        assert rel_l2(q.detach().cpu(), p.detach().cpu()) < 1e-5, n
+    assert t2.optimizer.step_counts()["C.weight"] == 4 and t2.optimizer.step_counts()["S_sad_i.weight"] == 0
