@@ -20,10 +20,11 @@ SIGNATURES = {
     "sn_version": (_I32, []),
     "sn_last_error": (c_char_p, []),
     "sn_device_info": (_I32, [_P, _P, _P, _P]),
-    "sn_gather_pack_fwd": (_I32, [_P, _I64, _P, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _P, _I64, _F, c_uint64, _P, _P]),
+    "sn_gather_pack_fwd": (_I32, [_P, _I64, _P, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _P, _I64, _F, c_uint64, _P, _P, _I64, _P]),
     "sn_gather_pack_bwd": (_I32, [_P, _I64, _P, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _P, _I64, _F, c_uint64, _P, _P]),
     "sn_gemm": (_I32, [_I32, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _I64, _I64, _I64, _I64, _P]),
     "sn_gemm_bf16": (_I32, [_I32, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _I64, _I64, _I64, _I64, _I64, _P]),
+    "sn_gemm_bf16_splitk": (_I32, [_I32, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _I64, _I64, _I64, _I64, _I64, _I32, _P]),
     "sn_cast_bf16": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P]),
     "sn_colsum": (_I32, [_P, _I64, _I64, _I64, _P, _F, _P]),
     "sn_recur_ws_bytes": (_I64, [_I64, _I64]),
@@ -31,7 +32,8 @@ SIGNATURES = {
     "sn_recur_bwd": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sn_recur_fwd_bf16": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _I32] + [_P] * 12),
     "sn_recur_bwd_bf16": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _I32] + [_P] * 11),
-    "sn_softmax_nll": (_I32, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _F, _P, _P, _P]),
+    "sn_softmax_nll": (_I32, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _F, _P, _P, _P, _I64, _P]),
+    "sn_colsum_bf16": (_I32, [_P, _I64, _I64, _I64, _P, _F, _P]),
     "sn_reduce_sum": (_I32, [_P, _I64, _F, _P, _I32, _P]),
     "sn_adam_clamp": (_I32, [_P, _P, _P, _P, _I32, _P, _P, _P, _F, _F, _F, _F, _P]),
     "sn_adam_clamp_dev": (_I32, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P]),

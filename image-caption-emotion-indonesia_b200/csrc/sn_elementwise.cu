@@ -1,6 +1,8 @@
 // Memory-bound kernels of the hot path: K1 gather/dropout/pack, K5 log-softmax+NLL(+grad, argmax,
 // top-5), deterministic loss reduction, K7 fused clamp+Adam.  All HBM-bound: coalesced, 16-byte
 // vectorised where the layout allows, grids sized from the SM count.
+#include <cuda_bf16.h>
+
 #include "sn_common.cuh"
 
 namespace {
@@ -14,7 +16,8 @@ __global__ void gather_pack_fwd_kernel(const int64_t* __restrict__ captions, int
                                        const int32_t* __restrict__ row_b, const int32_t* __restrict__ row_t,
                                        const int32_t* __restrict__ tok_override, int64_t N,
                                        float* __restrict__ X, int64_t ldx, float p, float inv_keep,
-                                       uint64_t seed, const uint64_t* __restrict__ seed_dev) {
+                                       uint64_t seed, const uint64_t* __restrict__ seed_dev,
+                                       __nv_bfloat16* __restrict__ Xb, int64_t ldxb, int Ep) {
   if (seed_dev) seed += *seed_dev;
   // one warp per packed row
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -22,17 +25,22 @@ __global__ void gather_pack_fwd_kernel(const int64_t* __restrict__ captions, int
   int lane = threadIdx.x & 31;
   int b = row_b[row], t = row_t[row];
   int ov = tok_override ? tok_override[row] : -1;
-  float* dst = X + row * ldx;
+  float* dst = X ? X + row * ldx : nullptr;
+  __nv_bfloat16* dstb = Xb ? Xb + row * ldxb : nullptr;
+  const float* src;
+  float pp = 0.f;
   if (ov < 0 && has_feat && t == 0) {
-    const float* src = features + (int64_t)b * feat_ld;
-    for (int c = lane; c < E; c += 32) dst[c] = src[c];
-    return;
+    src = features + (int64_t)b * feat_ld;
+  } else {
+    int64_t tok = ov >= 0 ? (int64_t)ov : captions[(int64_t)b * cap_ld + (t - has_feat)];
+    src = table + tok * E;
+    pp = ov >= 0 ? 0.f : p;   // fed-back embeddings are not dropped out (model.py:184)
   }
-  int64_t tok = ov >= 0 ? (int64_t)ov : captions[(int64_t)b * cap_ld + (t - has_feat)];
-  const float* src = table + tok * E;
-  float pp = ov >= 0 ? 0.f : p;   // fed-back embeddings are not dropped out (model.py:184)
-  for (int c = lane; c < E; c += 32)
-    dst[c] = src[c] * sn::dropout_scale(seed, (uint32_t)row, (uint32_t)c, pp, inv_keep);
+  for (int c = lane; c < Ep; c += 32) {
+    float v = c < E ? src[c] * sn::dropout_scale(seed, (uint32_t)row, (uint32_t)c, pp, inv_keep) : 0.f;
+    if (dst && c < E) dst[c] = v;
+    if (dstb) dstb[c] = __float2bfloat16(v);     // columns E..Ep are the zero K-padding of the TMA operand
+  }
 }
 
 __global__ void gather_pack_bwd_kernel(const int64_t* __restrict__ captions, int64_t cap_ld,
@@ -73,7 +81,8 @@ __global__ void __launch_bounds__(256) softmax_nll_kernel(const float* __restric
                                                           const int64_t* __restrict__ targets,
                                                           float* __restrict__ row_loss, float* dlogits, int64_t ldd,
                                                           float grad_scale, int64_t* __restrict__ argmax,
-                                                          int32_t* __restrict__ top5hit, int use_smem) {
+                                                          int32_t* __restrict__ top5hit, int use_smem,
+                                                          __nv_bfloat16* __restrict__ dlb, int64_t lddb) {
   extern __shared__ float srow[];
   __shared__ float red_v[8];
   __shared__ int red_i[8];
@@ -136,13 +145,17 @@ __global__ void __launch_bounds__(256) softmax_nll_kernel(const float* __restric
     if (top5hit) top5hit[row] = a < 5 ? 1 : 0;
   }
   __syncthreads();
-  if (dlogits) {
+  if (dlogits || dlb) {
     const float lse = bc_f[1];
-    float* dst = dlogits + row * ldd;
+    float* dst = dlogits ? dlogits + row * ldd : nullptr;
+    __nv_bfloat16* dstb = dlb ? dlb + row * lddb : nullptr;
     for (int64_t c = tid; c < V; c += 256) {
       float pr = expf(rd[c] - lse);
-      dst[c] = (pr - (c == tgt ? 1.f : 0.f)) * grad_scale;
+      float gr = (pr - (c == tgt ? 1.f : 0.f)) * grad_scale;
+      if (dst) dst[c] = gr;
+      if (dstb) dstb[c] = __float2bfloat16(gr);
     }
+    if (dstb) for (int64_t c = V + tid; c < lddb; c += 256) dstb[c] = __float2bfloat16(0.f);
   }
 }
 
@@ -261,8 +274,10 @@ int32_t sn_gather_pack_fwd(const int64_t* captions, int64_t cap_ld, const float*
                            const float* features, int64_t feat_ld, int32_t has_feat,
                            const int32_t* row_b, const int32_t* row_t, const int32_t* tok_override,
                            int64_t N, float* X, int64_t ldx, float p_drop, uint64_t seed, const uint64_t* seed_dev,
-                           void* stream) {
-  SN_REQUIRE(N >= 0 && E > 0 && ldx >= E, "sn_gather_pack_fwd: bad dims N=%lld E=%lld ldx=%lld", (long long)N, (long long)E, (long long)ldx);
+                           void* Xb, int64_t ldxb, void* stream) {
+  SN_REQUIRE(N >= 0 && E > 0 && (X || Xb), "sn_gather_pack_fwd: bad dims N=%lld E=%lld", (long long)N, (long long)E);
+  SN_REQUIRE(!X || ldx >= E, "sn_gather_pack_fwd: ldx=%lld < E", (long long)ldx);
+  SN_REQUIRE(!Xb || ldxb >= E, "sn_gather_pack_fwd: ldxb=%lld < E", (long long)ldxb);
   SN_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "sn_gather_pack_fwd: dropout p=%f out of [0,1)", p_drop);
   SN_REQUIRE(!has_feat || features, "sn_gather_pack_fwd: has_feat without features");
   if (N == 0) return 0;
@@ -270,7 +285,8 @@ int32_t sn_gather_pack_fwd(const int64_t* captions, int64_t cap_ld, const float*
   unsigned grid = (unsigned)((N + 7) / 8);
   gather_pack_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(captions, cap_ld, table, (int)E, features, feat_ld,
                                                                  has_feat, row_b, row_t, tok_override, N, X, ldx,
-                                                                 p_drop, inv_keep, seed, seed_dev);
+                                                                 p_drop, inv_keep, seed, seed_dev,
+                                                                 (__nv_bfloat16*)Xb, ldxb, Xb ? (int)ldxb : (int)E);
   return sn::check_launch("sn_gather_pack_fwd");
 }
 
@@ -292,8 +308,9 @@ int32_t sn_gather_pack_bwd(const int64_t* captions, int64_t cap_ld, float* dtabl
 
 int32_t sn_softmax_nll(const float* logits, int64_t N, int64_t V, int64_t ld, const int64_t* targets,
                        float* row_loss, float* dlogits, int64_t ldd, float grad_scale, int64_t* argmax,
-                       int32_t* top5hit, void* stream) {
+                       int32_t* top5hit, void* dlogits_bf16, int64_t lddb, void* stream) {
   SN_REQUIRE(N >= 0 && V > 0 && ld >= V, "sn_softmax_nll: bad dims");
+  SN_REQUIRE(!dlogits_bf16 || lddb >= V, "sn_softmax_nll: lddb < V");
   if (N == 0) return 0;
   size_t smem = (size_t)V * sizeof(float);
   int use_smem = smem <= 200 * 1024;
@@ -305,7 +322,8 @@ int32_t sn_softmax_nll(const float* logits, int64_t N, int64_t V, int64_t ld, co
     }
   }
   softmax_nll_kernel<<<(unsigned)N, 256, use_smem ? smem : 0, (cudaStream_t)stream>>>(
-      logits, V, ld, targets, row_loss, dlogits, ldd, grad_scale, argmax, top5hit, use_smem);
+      logits, V, ld, targets, row_loss, dlogits, ldd, grad_scale, argmax, top5hit, use_smem,
+      (__nv_bfloat16*)dlogits_bf16, lddb);
   return sn::check_launch("sn_softmax_nll");
 }
 

@@ -1,6 +1,8 @@
 // fp32 FFMA GEMM (SN_PREC_F32): the exact-fp32 arithmetic path and the validation reference for the
 // tcgen05 GEMMs.  128x128x8 tiles, 256 threads, 8x8 register micro-tiles, generic operand strides so
 // that NT / NN / TN all run without materialised transposes.
+#include <cuda_bf16.h>
+
 #include "sn_common.cuh"
 
 namespace {
@@ -122,7 +124,11 @@ __global__ void colsum_scale_kernel(float* __restrict__ out, int64_t N, float be
 }
 
 // grid (ceil(N/32), ceil(M/CS_ROWS)); block 32 columns x 8 row lanes; partial sums -> one atomicAdd per column
-__global__ void colsum_kernel(const float* __restrict__ X, int64_t M, int64_t N, int64_t ldx,
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename TIn>
+__global__ void colsum_kernel(const TIn* __restrict__ X, int64_t M, int64_t N, int64_t ldx,
                               float* __restrict__ out) {
   __shared__ float part[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
@@ -130,7 +136,7 @@ __global__ void colsum_kernel(const float* __restrict__ X, int64_t M, int64_t N,
   const int64_t r1 = r0 + CS_ROWS < M ? r0 + CS_ROWS : M;
   float s = 0.f;
   if (col < N)
-    for (int64_t m = r0 + threadIdx.y; m < r1; m += 8) s += X[m * ldx + col];
+    for (int64_t m = r0 + threadIdx.y; m < r1; m += 8) s += to_f(X[m * ldx + col]);
   part[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && col < N) {
@@ -164,8 +170,9 @@ extern "C" int32_t sn_gemm(int32_t op, int64_t M, int64_t N, int64_t K, const fl
   return sn::check_launch("sn_gemm");
 }
 
-extern "C" int32_t sn_colsum(const float* X, int64_t M, int64_t N, int64_t ldx, float* out, float beta,
-                             void* stream) {
+namespace {
+template <typename TIn>
+int32_t colsum_launch(const TIn* X, int64_t M, int64_t N, int64_t ldx, float* out, float beta, void* stream) {
   SN_REQUIRE(M >= 0 && N >= 0, "sn_colsum: bad dims");
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -176,6 +183,17 @@ extern "C" int32_t sn_colsum(const float* X, int64_t M, int64_t N, int64_t ldx, 
   }
   if (M == 0) return sn::check_launch("sn_colsum");
   dim3 grid((unsigned)((N + 31) / 32), (unsigned)((M + CS_ROWS - 1) / CS_ROWS)), block(32, 8);
-  colsum_kernel<<<grid, block, 0, st>>>(X, M, N, ldx, out);
+  colsum_kernel<TIn><<<grid, block, 0, st>>>(X, M, N, ldx, out);
   return sn::check_launch("sn_colsum");
+}
+}  // namespace
+
+extern "C" int32_t sn_colsum(const float* X, int64_t M, int64_t N, int64_t ldx, float* out, float beta,
+                             void* stream) {
+  return colsum_launch<float>(X, M, N, ldx, out, beta, stream);
+}
+
+extern "C" int32_t sn_colsum_bf16(const void* X, int64_t M, int64_t N, int64_t ldx, float* out, float beta,
+                                  void* stream) {
+  return colsum_launch<__nv_bfloat16>((const __nv_bfloat16*)X, M, N, ldx, out, beta, stream);
 }

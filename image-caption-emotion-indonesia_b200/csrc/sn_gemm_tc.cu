@@ -35,6 +35,7 @@ struct TmaSet { CUtensorMap m[4]; };
 
 struct TcArgs {
   int M, N, K;
+  int splits;                      // split-K factor (>1: fp32 atomic accumulation into a zeroed C)
   int a_mn_major, b_mn_major;     // 0: K-major tile, 1: MN-major tile
   float* C; __nv_bfloat16* Cb; int64_t ldc, ldcb;
   const float* bias; float beta;
@@ -119,9 +120,12 @@ gemm_tc_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ Tma
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = blockIdx.z;
+  const int grp = blockIdx.z / g.splits, split = blockIdx.z - grp * g.splits;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int num_kb = (g.K + BK - 1) / BK;
+  const int total_kb = (g.K + BK - 1) / BK;
+  const int kb_begin = (int)(((int64_t)total_kb * split) / g.splits);
+  const int kb_end = (int)(((int64_t)total_kb * (split + 1)) / g.splits);
+  const int num_kb = kb_end - kb_begin;
   const CUtensorMap* map_a = &tma_a.m[grp];
   const CUtensorMap* map_b = &tma_b.m[grp];
 
@@ -149,7 +153,7 @@ gemm_tc_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ Tma
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
         mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
-        const int k0 = kb * BK;
+        const int k0 = (kb_begin + kb) * BK;
         if (!g.a_mn_major) {
           tma_load_2d(sa, map_a, full0 + 8 * s, k0, m0);                 // box {64 k, 128 rows}
         } else {
@@ -198,11 +202,21 @@ gemm_tc_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ Tma
     const int row = m0 + q * 32 + lane;
     float* Cg = g.C ? g.C + grp * g.strideC : nullptr;
     __nv_bfloat16* Cbg = g.Cb ? g.Cb + grp * g.strideCb : nullptr;
-    const float* bias = g.bias ? g.bias + grp * g.strideBias : nullptr;
+    const float* bias = (g.bias && split == 0) ? g.bias + grp * g.strideBias : nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+      if (g.splits > 1) {
+        // split-K: partial tile -> fp32 reduction in L2 (C was zeroed by the host wrapper)
+        if (row < g.M && num_kb > 0) {
+          float* dst = Cg + (int64_t)row * g.ldc + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < g.N) atomicAdd(dst + j, __uint_as_float(r[j]) + (bias ? bias[n0 + c0 + j] : 0.f));
+        }
+        continue;
+      }
       if (row < g.M) {
         const int nb = n0 + c0;
         if (nb + 32 <= g.N) {
@@ -303,10 +317,25 @@ int32_t encode_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t row
 
 }  // namespace
 
+extern "C" int32_t sn_gemm_bf16_splitk(int32_t op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                                       const void* B, int64_t ldb, float* C, int64_t ldc, void* Cb, int64_t ldcb,
+                                       const float* bias, float beta, int32_t batch, int64_t strideA, int64_t strideB,
+                                       int64_t strideC, int64_t strideCb, int64_t strideBias, int32_t splits,
+                                       void* stream);
+
 extern "C" int32_t sn_gemm_bf16(int32_t op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                                 int64_t ldb, float* C, int64_t ldc, void* Cb, int64_t ldcb, const float* bias, float beta,
                                 int32_t batch, int64_t strideA, int64_t strideB, int64_t strideC, int64_t strideCb,
                                 int64_t strideBias, void* stream) {
+  return sn_gemm_bf16_splitk(op, M, N, K, A, lda, B, ldb, C, ldc, Cb, ldcb, bias, beta, batch, strideA, strideB, strideC,
+                             strideCb, strideBias, 1, stream);
+}
+
+extern "C" int32_t sn_gemm_bf16_splitk(int32_t op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                                       const void* B, int64_t ldb, float* C, int64_t ldc, void* Cb, int64_t ldcb,
+                                       const float* bias, float beta, int32_t batch, int64_t strideA, int64_t strideB,
+                                       int64_t strideC, int64_t strideCb, int64_t strideBias, int32_t splits,
+                                       void* stream) {
   SN_REQUIRE(op >= 0 && op <= 2, "sn_gemm_bf16: bad op %d", op);
   SN_REQUIRE(batch >= 1 && batch <= 4, "sn_gemm_bf16: 1..4 groups supported, got %d", batch);
   SN_REQUIRE(M >= 0 && N >= 0 && K > 0, "sn_gemm_bf16: bad dims");
@@ -316,9 +345,37 @@ extern "C" int32_t sn_gemm_bf16(int32_t op, int64_t M, int64_t N, int64_t K, con
              "sn_gemm_bf16: bf16 leading dimensions / group strides must be multiples of 8 elements (TMA 16-byte rule): "
              "lda=%lld ldb=%lld", (long long)lda, (long long)ldb);
   SN_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "sn_gemm_bf16: operands must be 16-byte aligned");
+  const int64_t total_kb = (K + BK - 1) / BK;
+  if (splits <= 0) {
+    // auto: fill ~2 waves of the 148 SMs when the tile count alone cannot (fp32 output, no beta only)
+    const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * batch;
+    splits = 1;
+    if (!Cb && beta == 0.f && tiles < 100 && total_kb >= 8) {
+      int64_t want = (2 * (int64_t)sn::dev_info().sm_count + tiles / 2) / tiles;
+      int64_t cap = total_kb / 4;
+      if (want > cap) want = cap;
+      if (want > 8) want = 8;
+      if (want > 1) splits = (int)want;
+    }
+  }
+  if (splits > total_kb) splits = (int)total_kb;
+  if (splits < 1) splits = 1;
+  if (splits > 1) {
+    SN_REQUIRE(C && !Cb && beta == 0.f, "sn_gemm_bf16: split-K needs an fp32-only output and beta == 0");
+    // zero the output tile range (row pitch ldc): one memset per group when rows are dense, else per row
+    for (int gi = 0; gi < batch; ++gi) {
+      float* base = C + gi * strideC;
+      if (ldc == N) {
+        SN_CUDA(cudaMemsetAsync(base, 0, sizeof(float) * (size_t)M * (size_t)N, (cudaStream_t)stream));
+      } else {
+        SN_CUDA(cudaMemset2DAsync(base, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M,
+                                  (cudaStream_t)stream));
+      }
+    }
+  }
   TmaSet ta, tb;
   TcArgs g;
-  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.M = (int)M; g.N = (int)N; g.K = (int)K; g.splits = splits;
   g.a_mn_major = (op == SN_OP_TN) ? 1 : 0;
   g.b_mn_major = (op == SN_OP_NT) ? 0 : 1;
   g.C = C; g.Cb = (__nv_bfloat16*)Cb; g.ldc = ldc; g.ldcb = ldcb; g.bias = bias; g.beta = beta;
@@ -340,7 +397,7 @@ extern "C" int32_t sn_gemm_bf16(int32_t op, int64_t M, int64_t N, int64_t K, con
     SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch);
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)(batch * splits));
   gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ta, tb, g);
   return sn::check_launch("sn_gemm_bf16");
 }

@@ -50,10 +50,7 @@ __device__ __forceinline__ void wait_flag(const int* flag, int target) {
 }
 __device__ __forceinline__ void signal_flag(int* flag) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    sn::red_release_add(flag, 1);
-  }
+  if (threadIdx.x == 0) sn::red_release_add(flag, 1);   // release.gpu: cumulative over the CTA's writes (bar.sync above)
 }
 
 // acc[j][s] += sum_k Ws[(j*8+rl)][k] * INs[(sw0+s)][k] over this lane's k subset of [0,KC)

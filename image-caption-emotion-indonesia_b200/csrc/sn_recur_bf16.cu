@@ -39,7 +39,7 @@ __device__ __forceinline__ void wait_flag(const int* flag, int target) {
 }
 __device__ __forceinline__ void signal_flag(int* flag) {
   __syncthreads();
-  if (threadIdx.x == 0) { __threadfence(); sn::red_release_add(flag, 1); }
+  if (threadIdx.x == 0) sn::red_release_add(flag, 1);   // release.gpu: cumulative over the CTA's writes (bar.sync above)
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);

@@ -194,12 +194,19 @@ class _DecoderBase(nn.Module):
         c.tok_override = None
         if not all_tf:
             c.tok_override = torch.full((N,), -1, dtype=torch.int32, device=dev)
-        X = torch.empty(N, E, dtype=torch.float32, device=dev)
+        c.Ein = E
+        c.w16 = {}      # bf16 weight shadows of this call (refreshed every forward)
+        if self.bf16:
+            # bf16 mode: the packed input rows are produced directly as the K-padded bf16 GEMM operand
+            X = None
+            c.Xb = torch.empty(N, _pad8(E), dtype=torch.bfloat16, device=dev)
+        else:
+            X = torch.empty(N, E, dtype=torch.float32, device=dev)
+            c.Xb = None
         ops.gather_pack_fwd(captions, emb.weight, feats, has_feat, d["row_b"], d["row_t"], None, N, X,
-                            c.p_drop, c.seed, seed_dev=c.seed_dev)
+                            c.p_drop, c.seed, seed_dev=c.seed_dev, Xb=c.Xb)
         c.X = X
         c.XP = torch.empty(N, 4 * H, dtype=torch.float32, device=dev)
-        c.w16 = {}      # bf16 weight shadows of this call (refreshed every forward)
         self._input_projection(c, X, mode, 0, N)
         c.Hall = torch.empty(N, H, dtype=torch.float32, device=dev)
         c.Call = torch.empty(N, H, dtype=torch.float32, device=dev) if save else None
@@ -254,7 +261,8 @@ class _DecoderBase(nn.Module):
                         pred = am[:bp].to(torch.int32)
                     c.tok_override[r0:r0 + bt] = pred[:bt]
                     ops.gather_pack_fwd(captions, emb.weight, feats, has_feat, d["row_b"], d["row_t"],
-                                        c.tok_override, bt, X, c.p_drop, c.seed, row_off=r0, seed_dev=c.seed_dev)
+                                        c.tok_override, bt, X, c.p_drop, c.seed, row_off=r0, seed_dev=c.seed_dev,
+                                        Xb=c.Xb)
                     self._input_projection(c, X, mode, r0, bt)
                     run(t, t + 1)
                     t += 1
@@ -327,12 +335,13 @@ class _DecoderBase(nn.Module):
             if Hb is None:
                 Hb = ops.to_bf16_padded(Hall.contiguous())
             Wb = ops.to_bf16_padded(out.weight)
+            self.__dict__["_out_w16"] = Wb          # reused by the matching backward of this step
             logits = torch.empty(N, V, dtype=torch.float32, device=Hall.device)
             ops.gemm_bf16(ops.OP_NT, Hb, Wb, N, V, H, Hb.stride(0), Wb.stride(0), C=logits, ldc=V, bias=out.bias)
             return logits
         return ops.linear_nt(Hall.contiguous(), out.weight, out.bias)
 
-    def _vocab_backward(self, Hall, dlogits, gbuf, Hb=None):
+    def _vocab_backward(self, Hall, dlogits, gbuf, Hb=None, dLb=None):
         out = self._out()
         V, H = out.weight.shape
         N = Hall.shape[0]
@@ -341,12 +350,19 @@ class _DecoderBase(nn.Module):
         gb = self._gview(gbuf, [bn], (V,))
         dHall = torch.empty(N, H, dtype=torch.float32, device=Hall.device)
         if self.bf16:
-            dLb = ops.to_bf16_padded(dlogits)
+            have_b16 = dLb is not None
+            if not have_b16:
+                dLb = ops.to_bf16_padded(dlogits)
             if Hb is None:
                 Hb = ops.to_bf16_padded(Hall.contiguous())
-            Wb = ops.to_bf16_padded(out.weight)
+            Wb = self.__dict__.pop("_out_w16", None) if dLb is not None and have_b16 else None
+            if Wb is None:
+                Wb = ops.to_bf16_padded(out.weight)
             ops.gemm_bf16(ops.OP_NN, dLb, Wb, N, H, V, dLb.stride(0), Wb.stride(0), C=dHall, ldc=H)
             ops.gemm_bf16(ops.OP_TN, dLb, Hb, V, H, N, dLb.stride(0), Hb.stride(0), C=gC, ldc=H)
+            if have_b16:
+                ops.colsum_bf16(dLb, N, V, dLb.stride(0), gb)
+                return dHall
         else:
             ops.gemm(ops.OP_NN, dlogits, out.weight, dHall, N, H, V, dlogits.stride(0), H, H)
             ops.gemm(ops.OP_TN, dlogits, Hall, gC, V, H, N, dlogits.stride(0), H, H)
@@ -397,14 +413,18 @@ class _DecoderBase(nn.Module):
             argmax = torch.empty(N, dtype=torch.int64, device=dev)
             top5 = torch.empty(N, dtype=torch.int32, device=dev)
             denom = float(n_global if n_global is not None else N)
+            dLb = None
+            if backward and self.bf16:
+                # the gradient leaves the softmax kernel directly as the bf16 GEMM operand (no fp32 copy)
+                dLb = torch.empty(N, _pad8(V), dtype=torch.bfloat16, device=dev)
             ops.softmax_nll(logits, N, V, targets=targets, row_loss=row_loss,
-                            dlogits=logits if backward else None, grad_scale=1.0 / denom, argmax=argmax,
-                            top5hit=top5)
+                            dlogits=logits if (backward and dLb is None) else None, grad_scale=1.0 / denom,
+                            argmax=argmax, top5hit=top5, dlogits_bf16=dLb)
             loss = torch.empty(1, dtype=torch.float32, device=dev)
             ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
             if backward:
                 gbuf = self._grad_target(c.grad_names + list(self._out_names()))
-                dHall = self._vocab_backward(c.Hall, logits, gbuf, c.Hb)
+                dHall = self._vocab_backward(c.Hall, logits, gbuf, c.Hb, dLb)
                 if grad_hook is not None and gbuf is self.arena().gflat:
                     grad_hook(list(self._out_names()))       # bucket 0 is final: overlap its all-reduce
                 need_dfeat = features is not None and features.requires_grad
@@ -417,9 +437,15 @@ class _DecoderBase(nn.Module):
         return loss, {"argmax": argmax, "top5hit": top5, "n_tokens": N}
 
     def _default_targets(self, captions, plan, has_feat):
+        """Packed targets = what pack_padded_sequence(captions, lengths)[0] holds (train_multitask.py:377-379):
+        one gather through a flat (b*T + t) index cached with the plan."""
         d = plan.dev(captions.device)
-        t = d["row_t"].long() if has_feat else d["row_t"].long() + 1
-        return captions[d["row_b"].long(), t].contiguous()
+        key = "tgt_idx_%d_%d" % (captions.shape[1], 0 if has_feat else 1)
+        idx = d.get(key)
+        if idx is None:
+            idx = (d["row_b"].long() * captions.shape[1] + d["row_t"].long() + (0 if has_feat else 1)).contiguous()
+            d[key] = idx
+        return captions.reshape(-1).index_select(0, idx)
 
 
 class DecoderFactoredLSTM(_DecoderBase):
@@ -507,9 +533,10 @@ class DecoderFactoredLSTM(_DecoderBase):
         if mode not in STYLES:
             raise ValueError("mode name wrong: %r (expected one of %s)" % (mode, STYLES))
         H, F = self.hidden_size, self.factored_size
-        Ein = X.shape[1]
-        dev = X.device
-        if r0 == 0 and n == X.shape[0] and not self.bf16:
+        Ein = X.shape[1] if X is not None else c.Ein
+        dev = c.XP.device
+        full = (r0 == 0 and n == c.XP.shape[0])
+        if full and not self.bf16:
             c.A1 = torch.empty(n, 4 * F, dtype=torch.float32, device=dev)
             c.A2 = torch.empty(n, 4 * F, dtype=torch.float32, device=dev)
         A1, A2 = c.__dict__.get("A1"), c.__dict__.get("A2")
@@ -522,11 +549,13 @@ class DecoderFactoredLSTM(_DecoderBase):
                 w16["V"], w16["S"], w16["U"] = self._shadow(Vc), self._shadow(Sc), self._shadow(Uc)
             Vb, Sb, Ub = w16["V"], w16["S"], w16["U"]
             Ep, Fp = Vb.stride(0), Sb.stride(0)
-            if r0 == 0 and n == X.shape[0]:
-                c.Xb = torch.empty(n, Ep, dtype=torch.bfloat16, device=dev)
+            if full:
+                if X is not None:
+                    c.Xb = torch.empty(n, Ep, dtype=torch.bfloat16, device=dev)
                 c.A1 = torch.empty(n, 4 * F, dtype=torch.bfloat16, device=dev)
                 c.A2 = torch.empty(n, 4 * F, dtype=torch.bfloat16, device=dev)
-            ops.cast_bf16(X, n, Ein, Ein, c.Xb, Ep, Ep, src_off=r0 * Ein, dst_off=r0 * Ep)
+            if X is not None:
+                ops.cast_bf16(X, n, Ein, Ein, c.Xb, Ep, Ep, src_off=r0 * Ein, dst_off=r0 * Ep)
             ops.gemm_bf16(ops.OP_NT, c.Xb, Vb, n, 4 * F, Ep, Ep, Ep, Cb=c.A1, ldcb=4 * F, bias=bV, a_off=r0 * Ep,
                           cb_off=r0 * 4 * F)
             ops.gemm_bf16(ops.OP_NT, c.A1, Sb, n, F, F, 4 * F, Fp, Cb=c.A2, ldcb=4 * F, bias=bS, batch=4, sA=F,
@@ -543,7 +572,7 @@ class DecoderFactoredLSTM(_DecoderBase):
 
     def _input_projection_bwd(self, c, dZ, gbuf):
         H, F = self.hidden_size, self.factored_size
-        N, Ein = c.X.shape
+        N, Ein = dZ.shape[0], c.Ein
         dev = dZ.device
         mode = c.mode
         Vc = self._stack("V_", (4 * F, Ein))
@@ -574,7 +603,7 @@ class DecoderFactoredLSTM(_DecoderBase):
     def _input_projection_bwd_bf16(self, c, dZ, gV, gbV, gS, gbS, gU, gbU):
         """Backward of the factored chain with every GEMM on tcgen05 (bf16 operands, fp32 results)."""
         H, F = self.hidden_size, self.factored_size
-        N, Ein = c.X.shape
+        N, Ein = dZ.shape[0], c.Ein
         dev = dZ.device
         Vb, Sb, Ub = c.w16["V"], c.w16["S"], c.w16["U"]
         Ep, Fp = Vb.stride(0), Sb.stride(0)
@@ -665,16 +694,17 @@ class DecoderRNN(_DecoderBase):
     def _input_projection(self, c, X, mode, r0, n):
         """XP = x W_ih^T + b_ih (the first addmm of nn.LSTMCell, nic/model.py:77)."""
         H = self.hidden_size
-        Ein = X.shape[1]
+        Ein = X.shape[1] if X is not None else c.Ein
         if self.bf16:
             w16 = c.__dict__.setdefault("w16", {})
             if "Wih" not in w16:
                 w16["Wih"] = self._shadow(self.lstm.weight_ih)
             Wb = w16["Wih"]
             Ep = Wb.stride(0)
-            if r0 == 0 and n == X.shape[0]:
-                c.Xb = torch.empty(n, Ep, dtype=torch.bfloat16, device=X.device)
-            ops.cast_bf16(X, n, Ein, Ein, c.Xb, Ep, Ep, src_off=r0 * Ein, dst_off=r0 * Ep)
+            if X is not None:
+                if r0 == 0 and n == X.shape[0]:
+                    c.Xb = torch.empty(n, Ep, dtype=torch.bfloat16, device=X.device)
+                ops.cast_bf16(X, n, Ein, Ein, c.Xb, Ep, Ep, src_off=r0 * Ein, dst_off=r0 * Ep)
             ops.gemm_bf16(ops.OP_NT, c.Xb, Wb, n, 4 * H, Ep, Ep, Ep, C=c.XP, ldc=4 * H, bias=self.lstm.bias_ih,
                           a_off=r0 * Ep, c_off=r0 * 4 * H)
             return
@@ -683,7 +713,7 @@ class DecoderRNN(_DecoderBase):
 
     def _input_projection_bwd(self, c, dZ, gbuf):
         H = self.hidden_size
-        N, Ein = c.X.shape
+        N, Ein = dZ.shape[0], c.Ein
         gW = self._gview(gbuf, ["lstm.weight_ih"], (4 * H, Ein))
         gb = self._gview(gbuf, ["lstm.bias_ih"], (4 * H,))
         dX = torch.empty(N, Ein, dtype=torch.float32, device=dZ.device)

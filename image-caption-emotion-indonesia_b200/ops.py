@@ -71,7 +71,8 @@ def colsum(X, M, N, ldx, out, beta=0.0, x_off=0, out_off=0):
 
 
 def gather_pack_fwd(captions, table, features, has_feat, row_b, row_t, tok_override, N, X, p_drop, seed,
-                    row_off=0, seed_dev=None):
+                    row_off=0, seed_dev=None, Xb=None):
+    """X (fp32, may be None) and/or Xb (bf16, K-padded) receive the packed input rows."""
     E = table.shape[1]
     cap = _req(captions, torch.int64)
     ro4 = 4 * row_off
@@ -81,8 +82,16 @@ def gather_pack_fwd(captions, table, features, has_feat, row_b, row_t, tok_overr
         1 if has_feat else 0,
         ctypes.c_void_p(row_b.data_ptr() + ro4), ctypes.c_void_p(row_t.data_ptr() + ro4),
         ctypes.c_void_p(tok_override.data_ptr() + ro4) if tok_override is not None else None,
-        N, ctypes.c_void_p(X.data_ptr() + 4 * row_off * X.stride(0)), X.stride(0), float(p_drop),
-        ctypes.c_uint64(seed), _ptr(seed_dev), _stream()), "sn_gather_pack_fwd")
+        N, ctypes.c_void_p(X.data_ptr() + 4 * row_off * X.stride(0)) if X is not None else None,
+        X.stride(0) if X is not None else 0, float(p_drop), ctypes.c_uint64(seed), _ptr(seed_dev),
+        ctypes.c_void_p(Xb.data_ptr() + 2 * row_off * Xb.stride(0)) if Xb is not None else None,
+        Xb.stride(0) if Xb is not None else 0, _stream()), "sn_gather_pack_fwd")
+
+
+def colsum_bf16(X, M, N, ldx, out, beta=0.0):
+    _req(X, torch.bfloat16); _req(out)
+    check(lib().sn_colsum_bf16(_ptr(X), M, N, ldx, _ptr(out), float(beta), _stream()), "sn_colsum_bf16")
+    return out
 
 
 def gather_pack_bwd(captions, dtable, dfeatures, has_feat, row_b, row_t, tok_override, N, dX, p_drop, seed,
@@ -126,12 +135,13 @@ def recur_bwd(cell, H, B, bs, off, t0, t1, Whh, c_init, Call, gates, dHall, dZ, 
 
 
 def softmax_nll(logits, N, V, targets=None, row_loss=None, dlogits=None, grad_scale=1.0, argmax=None,
-                top5hit=None, row_off=0):
+                top5hit=None, row_off=0, dlogits_bf16=None):
     ld = logits.stride(0)
     check(lib().sn_softmax_nll(
         ctypes.c_void_p(logits.data_ptr() + 4 * row_off * ld), N, V, ld, _ptr(targets), _ptr(row_loss),
         _ptr(dlogits), dlogits.stride(0) if dlogits is not None else 0, float(grad_scale), _ptr(argmax),
-        _ptr(top5hit), _stream()), "sn_softmax_nll")
+        _ptr(top5hit), _ptr(dlogits_bf16), dlogits_bf16.stride(0) if dlogits_bf16 is not None else 0,
+        _stream()), "sn_softmax_nll")
 
 
 def reduce_sum(x, N, scale, out, accumulate=False):
@@ -178,12 +188,14 @@ def _bptr(t, off_elems, elem_size):
 
 
 def gemm_bf16(op, A, B, M, N, K, lda, ldb, C=None, ldc=0, Cb=None, ldcb=0, bias=None, beta=0.0, batch=1,
-              sA=0, sB=0, sC=0, sCb=0, sBias=0, a_off=0, b_off=0, c_off=0, cb_off=0, bias_off=0):
-    """tcgen05 GEMM: A, B bf16; C fp32 and/or Cb bf16.  Offsets in elements of the respective tensor."""
+              sA=0, sB=0, sC=0, sCb=0, sBias=0, a_off=0, b_off=0, c_off=0, cb_off=0, bias_off=0, splits=1):
+    """tcgen05 GEMM: A, B bf16; C fp32 and/or Cb bf16.  Offsets in elements of the respective tensor.
+    splits: 1 = off (default: the atomic reduction epilogue costs more than it gains at these sizes, see
+    profiles/README.md r1_d), 0 = automatic, n = forced."""
     _req(A, torch.bfloat16); _req(B, torch.bfloat16)
-    check(lib().sn_gemm_bf16(op, M, N, K, _bptr(A, a_off, 2), lda, _bptr(B, b_off, 2), ldb,
-                             _bptr(C, c_off, 4), ldc, _bptr(Cb, cb_off, 2), ldcb, _bptr(bias, bias_off, 4),
-                             float(beta), batch, sA, sB, sC, sCb, sBias, _stream()), "sn_gemm_bf16")
+    check(lib().sn_gemm_bf16_splitk(op, M, N, K, _bptr(A, a_off, 2), lda, _bptr(B, b_off, 2), ldb,
+                                    _bptr(C, c_off, 4), ldc, _bptr(Cb, cb_off, 2), ldcb, _bptr(bias, bias_off, 4),
+                                    float(beta), batch, sA, sB, sC, sCb, sBias, splits, _stream()), "sn_gemm_bf16")
 
 
 def cast_bf16(src, R, C, lds, dst, Cp, ldd, src_off=0, dst_off=0):

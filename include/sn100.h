@@ -56,13 +56,15 @@ int32_t sn_device_info(int32_t* sm_count, int32_t* smem_optin, int32_t* cc_major
  * tok_override (optional, [N]): if >= 0 the row embeds that id instead (scheduled sampling feedback,
  * model.py:184) and is NOT dropped out.  X is [N, ldx] fp32; columns >= E are left untouched.
  * dropout: keep-prob 1-p, scale 1/(1-p), counter-based RNG (seed, row, col); p = 0 disables.
+ * Xb (optional): the same rows as bf16 [N, ldxb], columns E..ldxb zero-filled (K padding of the tcgen05
+ * operand); X may then be NULL.
  * seed_dev (optional, device): added to `seed` at run time -- lets a captured CUDA graph draw a fresh
  * mask on every replay (the caller bumps the device counter once per step). */
 int32_t sn_gather_pack_fwd(const int64_t* captions, int64_t cap_ld, const float* table, int64_t E,
                            const float* features, int64_t feat_ld, int32_t has_feat,
                            const int32_t* row_b, const int32_t* row_t, const int32_t* tok_override,
                            int64_t N, float* X, int64_t ldx, float p_drop, uint64_t seed,
-                           const uint64_t* seed_dev, void* stream);
+                           const uint64_t* seed_dev, void* Xb, int64_t ldxb, void* stream);
 /* backward of the above: dtable[id] += dX*mask (atomic, duplicates accumulate like nn.Embedding's
  * dense gradient), dfeatures[b] = dX[row(b,0)] (may be NULL). */
 int32_t sn_gather_pack_bwd(const int64_t* captions, int64_t cap_ld, float* dtable, int64_t E,
@@ -88,6 +90,14 @@ int32_t sn_gemm_bf16(int32_t op, int64_t M, int64_t N, int64_t K, const void* A,
                      const void* B, int64_t ldb, float* C, int64_t ldc, void* Cb, int64_t ldcb,
                      const float* bias, float beta, int32_t batch, int64_t strideA, int64_t strideB,
                      int64_t strideC, int64_t strideCb, int64_t strideBias, void* stream);
+/* split-K variant: the K loop is divided over `splits` CTAs per tile, partial tiles are reduced with fp32
+ * atomics into a zeroed C (fp32 output only, beta = 0).  splits = 0 picks a factor that fills ~2 waves of
+ * the SMs when the tile count alone cannot (weight-gradient GEMMs: few tiles, long K = tokens). */
+int32_t sn_gemm_bf16_splitk(int32_t op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                            const void* B, int64_t ldb, float* C, int64_t ldc, void* Cb, int64_t ldcb,
+                            const float* bias, float beta, int32_t batch, int64_t strideA,
+                            int64_t strideB, int64_t strideC, int64_t strideCb, int64_t strideBias,
+                            int32_t splits, void* stream);
 /* fp32 [R,C] (row pitch lds) -> bf16 [R,Cp] (row pitch ldd), columns C..Cp zero-filled (weight shadows and
  * activation operands of sn_gemm_bf16; Cp pads K to the TMA 16-byte rule, e.g. E=300 -> 304) */
 int32_t sn_cast_bf16(const float* src, int64_t R, int64_t C, int64_t lds, void* dst, int64_t Cp,
@@ -95,6 +105,8 @@ int32_t sn_cast_bf16(const float* src, int64_t R, int64_t C, int64_t lds, void* 
 /* column sums (bias gradients): out[n] = sum_m X[m,n] + beta*out[n] */
 int32_t sn_colsum(const float* X, int64_t M, int64_t N, int64_t ldx, float* out, float beta,
                   void* stream);
+int32_t sn_colsum_bf16(const void* X, int64_t M, int64_t N, int64_t ldx, float* out, float beta,
+                       void* stream);
 
 /* ---- K3: persistent recurrence (W_hh h + gates + cell), forward and reverse-time backward -----
  * replaces the hot loop stylenet/model.py:180-187 with forward_step's W_g(h_t)+sigmoid/tanh+cell
@@ -149,10 +161,11 @@ int32_t sn_recur_bwd_bf16(int32_t cell, int64_t H, int64_t B, const int32_t* bat
  * utils.accuracy top-5 (utils.py:127-140).
  * row_loss[N] = lse - logit[target]; dlogits = (softmax - onehot) * grad_scale (may alias logits, may
  * be NULL); argmax[N] lowest index on ties (torch.max); top5hit[N] = 1 if fewer than 5 logits exceed
- * the target's.  targets may be NULL (then only argmax is produced). */
+ * the target's.  targets may be NULL (then only argmax is produced).  dlogits_bf16 (optional, [N,lddb],
+ * columns V..lddb zero): the gradient as the bf16 operand of the two vocab-projection backward GEMMs. */
 int32_t sn_softmax_nll(const float* logits, int64_t N, int64_t V, int64_t ld, const int64_t* targets,
                        float* row_loss, float* dlogits, int64_t ldd, float grad_scale,
-                       int64_t* argmax, int32_t* top5hit, void* stream);
+                       int64_t* argmax, int32_t* top5hit, void* dlogits_bf16, int64_t lddb, void* stream);
 /* loss = scale * sum(row_loss[0..N)) (+ loss if accumulate), deterministic order, double sum */
 int32_t sn_reduce_sum(const float* x, int64_t N, float scale, float* out, int32_t accumulate,
                       void* stream);
