@@ -42,6 +42,22 @@ def single_step(dec, embedded, states, mode):
     return h_new, (h_new, c_new)
 
 
+def _vocab_step(dec, h_new, logits, cache):
+    """logits = C(h) for one decode step; bf16 mode runs it on tcgen05 with a cached bf16 copy of C."""
+    out = dec._out()
+    V, H = out.weight.shape
+    R = h_new.shape[0]
+    if dec.bf16 and H % 8 == 0:
+        if "Wb" not in cache:
+            cache["Wb"] = ops.to_bf16_padded(out.weight)
+            cache["hb"] = torch.empty(R, H, dtype=torch.bfloat16, device=h_new.device)
+        ops.cast_bf16(h_new, R, H, H, cache["hb"], H, H)
+        ops.gemm_bf16(ops.OP_NT, cache["hb"], cache["Wb"], R, V, H, H, cache["Wb"].stride(0), C=logits, ldc=V,
+                      bias=out.bias)
+    else:
+        ops.gemm(ops.OP_NT, h_new, out.weight, logits, R, V, H, H, H, V, bias=out.bias)
+
+
 class BeamState:
     def __init__(self, n_img, kmax, max_len, start_token, device):
         L = max_len + 2
@@ -105,6 +121,8 @@ def beam_sample(dec, features, start_token, end_token, k, mode, feed_image, sync
     dummy_cap = torch.zeros(1, 1, dtype=torch.int64, device=dev)
     bs1, off1 = _i32(dev, [R]), _i32(dev, [0])
     Whh, bhh = dec._recurrent_weights()
+    cache = {}
+    ctx.w16 = {}
     for step in range(1, dec.max_seq_length + 2):
         if feed_image and step == 1:
             ops.gather_pack_fwd(dummy_cap, emb.weight, feats, True, row_img, row_zero, None, R, X, 0.0, 0)
@@ -112,7 +130,7 @@ def beam_sample(dec, features, start_token, end_token, k, mode, feed_image, sync
             ops.gather_pack_fwd(dummy_cap, emb.weight, None, False, row_img, row_zero, st.prev_word, R, X, 0.0, 0)
         dec._input_projection(ctx, X, mode, 0, R)
         ops.recur_fwd(dec.cell, H, R, bs1, off1, 0, 1, ctx.XP, Whh, bhh, h, h_new, None, None, None, c)
-        ops.gemm(ops.OP_NT, h_new, out.weight, logits, R, V, H, H, H, V, bias=out.bias)
+        _vocab_step(dec, h_new, logits, cache)
         st.step(logits, step, end_token)
         idx = st.src_row.long()
         h = h_new.index_select(0, idx)
