@@ -28,12 +28,25 @@ METRIC = "decoder_train_tokens_per_sec"
 UNIT = "tokens/s"
 
 
-def workload_config(n_gpus, dtype):
+WORKLOAD = "factored"      # set from --workload: factored (configs[1], default) | att (configs[2]) | nic (configs[0] on GPU)
+WORKLOAD_TEXT = {
+    "factored": "configs[1]: StyleNet DecoderFactoredLSTM(embed 300, hidden 512, factored 512, vocab 10000), "
+                "mode=happy, teacher_forcing=1.0, dropout 0.5 on, fwd+bwd+clip(0.5)+Adam, T=20",
+    "att": "configs[2]: StyleNet DecoderFactoredLSTMAtt(attention 512, embed 300, hidden 512, factored 512, vocab 10000) "
+           "over a 7x7x2048 feature map, mode=happy, teacher_forcing=1.0, dropout 0.5 on, "
+           "CE + doubly-stochastic regulariser, fwd+bwd+clip(0.5)+Adam, T=20 (19 decoded steps)",
+    "nic": "configs[0] on the GPU: NIC DecoderRNN(embed 300, hidden 512, vocab 10000), B=64, teacher_forcing=1.0, "
+           "dropout 0.5 on, fwd+bwd+clip(0.5)+Adam, T=20",
+}
+
+
+def workload_config(n_gpus, dtype, tokens_per_gpu=None, batch=None):
+    tokens_per_gpu = tokens_per_gpu or B_PER_GPU * T
+    batch = batch or B_PER_GPU
     return {
-        "workload": "configs[1]: StyleNet DecoderFactoredLSTM(embed 300, hidden 512, factored 512, vocab 10000), "
-                    "mode=happy, teacher_forcing=1.0, dropout 0.5 on, fwd+bwd+clip(0.5)+Adam, T=20",
-        "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * n_gpus, "seq_len": T,
-        "tokens_per_step": B_PER_GPU * T * n_gpus, "parallelism": "dp%d" % n_gpus,
+        "workload": WORKLOAD_TEXT[WORKLOAD],
+        "batch_per_gpu": batch, "global_batch": batch * n_gpus, "seq_len": T,
+        "tokens_per_step": tokens_per_gpu * n_gpus, "parallelism": "dp%d" % n_gpus,
         "l2": "flushed between timed steps (512 MiB write); step working set ~0.5 GB > 126 MB L2",
         "arith": dtype,
     }
@@ -185,14 +198,30 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)                        # identical weights on every rank
-    dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5).to(dev)
+    if WORKLOAD == "att":
+        dec = sn.DecoderFactoredLSTMAtt(512, E, H, F, V, 1, dropout=0.5).to(dev)
+    elif WORKLOAD == "nic":
+        dec = sn.DecoderRNN(E, H, V, 1, dropout=0.5).to(dev)
+    else:
+        dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5).to(dev)
     dec.train()
     dec.set_precision(args.precision)
     arith = "bf16 operands on tcgen05, fp32 accumulate (recurrence/softmax/Adam fp32)" if args.precision == "bf16" \
         else "f32 FFMA"
     opt = sn.FusedClampAdam(dec, lr=5e-4, grad_clip=0.5)
     trainer = sn.DataParallelTrainer(dec, opt)
-    cap_h, lens, feat_h = synthetic_batch(B_PER_GPU, T, V, E, seed=rank)
+    bsz = 64 if WORKLOAD == "nic" else B_PER_GPU
+    cap_h, lens, feat_h = synthetic_batch(bsz, T, V, E, seed=rank)
+    step_kw = {"teacher_forcing_ratio": 1.0}
+    if WORKLOAD != "nic":
+        step_kw["mode"] = MODE
+    if WORKLOAD == "att":
+        feat_h = torch.randn(bsz, 7, 7, 2048, generator=torch.Generator().manual_seed(100 + rank))
+        full_cap = cap_h
+        cap_h = full_cap[:, :-1].contiguous()                  # inputs; targets = packed full[:, 1:]
+        lens = [l - 1 for l in lens]
+        tgt_idx = torch.cat([torch.arange(b) * T + (t + 1) for t, b in enumerate([bsz] * (T - 1))])
+        step_kw["targets"] = full_cap.reshape(-1)[tgt_idx].to(dev)
     cap_pin, feat_pin = cap_h.pin_memory(), feat_h.pin_memory()
     cap_d, feat_d = cap_pin.to(dev), feat_pin.to(dev)
     loss_pin = torch.zeros(1).pin_memory()
@@ -205,13 +234,13 @@ def run_gpu(args):
     if not args.no_graph:
         # the whole step (fwd + loss + bwd [+ all-reduce] + clamp/Adam) captured once, replayed per step
         ops.LAUNCHES[0] = 0
-        graphed = sn.GraphedTrainStep(trainer, cap_d, lens, feat_d, warmup=3, mode=MODE, teacher_forcing_ratio=1.0)
+        graphed = sn.GraphedTrainStep(trainer, cap_d, lens, feat_d, warmup=3, **step_kw)
         launches_per_step = ops.LAUNCHES[0] // 4          # 3 warm-up runs + 1 capture run
 
     def step_resident():
         if graphed is not None:
             return graphed()
-        return trainer.step(cap_d, lens, feat_d, mode=MODE, teacher_forcing_ratio=1.0)
+        return trainer.step(cap_d, lens, feat_d, **step_kw)
 
     def step_e2e():
         if graphed is not None:
@@ -219,7 +248,7 @@ def run_gpu(args):
         else:
             c = cap_pin.to(dev, non_blocking=True)
             f = feat_pin.to(dev, non_blocking=True)
-            loss, _ = trainer.step(c, lens, f, mode=MODE, teacher_forcing_ratio=1.0)
+            loss, _ = trainer.step(c, lens, f, **step_kw)
         loss_pin.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_pin[0])
@@ -275,12 +304,15 @@ def run_gpu(args):
     line = None
     if rank == 0:
         hbm_peak, tf_peak, peak_src = measured_peaks()
-        roof, kernels = kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src)
+        if WORKLOAD == "att":
+            roof, kernels = None, None
+        else:
+            roof, kernels = kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": workload_config(world, arith),
+            "config": workload_config(world, arith, n_tok_local, bsz),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "timing": "wall clock incl. python, pinned H2D of captions+features, D2H loss, sync per step"},
             "gpu_launches": launches, "launch_mode": "cuda-graph replay of the captured step" if graphed is not None
@@ -409,7 +441,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--workload", default="factored", choices=["factored", "att", "nic"])
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.impl == "reference":
         run_reference(args)
     else:

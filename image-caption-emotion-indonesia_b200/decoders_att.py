@@ -86,6 +86,24 @@ class _AttBase(_DecoderBase):
         return h, c
 
     # ---- forward -----------------------------------------------------------------------------------
+    def _tc_ok(self):
+        """bf16 mode needs TMA-legal operand shapes (every K and group offset a multiple of 8 elements)."""
+        dims = [self.hidden_size, self.attention_size, self.feature_size]
+        if hasattr(self, "factored_size"):
+            dims.append(self.factored_size)
+        return self.bf16 and self.hidden_size % 32 == 0 and all(x % 8 == 0 for x in dims)
+
+    def _lin(self, c, x, xb, w, wkey, bias, out, n, r0_out=0, x_off_rows=0):
+        """out[r0_out:r0_out+n] = x W^T + b for a small per-step Linear; tcgen05 in bf16 mode."""
+        N_out, K = w.shape
+        if c.tc:
+            wb = c.w16[wkey]
+            ops.gemm_bf16(ops.OP_NT, xb, wb, n, N_out, K, xb.stride(0), wb.stride(0), C=out, ldc=N_out, bias=bias,
+                          a_off=x_off_rows * xb.stride(0), c_off=r0_out * N_out)
+        else:
+            ops.gemm(ops.OP_NT, x, w, out, n, N_out, K, K, K, N_out, bias=bias, a_off=x_off_rows * K,
+                     c_off=r0_out * N_out)
+
     def _run_forward_att(self, plan, captions, features, coins, mode, save):
         a = self.arena()
         dev = captions.device
@@ -102,37 +120,63 @@ class _AttBase(_DecoderBase):
         att = self._att_module(mode)
         c = _Ctx()
         c.plan, c.mode, c.captions, c.has_feat = plan, mode, captions, False
-        c.feats, c.P = feats, P
+        c.feats, c.P, c.Ein = feats, P, E
+        c.tc = self._tc_ok()
+        c.w16 = {}
         c.p_drop = float(self.dropout.p) if self.training else 0.0
         c.seed, c.seed_dev = self._next_seed(dev, c.p_drop)
         f32 = dict(dtype=torch.float32, device=dev)
+        b16 = dict(dtype=torch.bfloat16, device=dev)
+        Whh, bhh = self._recurrent_weights()
         # hoisted, time-invariant pieces
         c.mean = torch.empty(B, D, **f32)
         ops.mean_pixels(feats, B, P, D, c.mean)
-        h0 = ops.linear_nt(c.mean, self.init_h.weight, self.init_h.bias)
-        c.c0 = ops.linear_nt(c.mean, self.init_c.weight, self.init_c.bias)
-        c.att1 = ops.linear_nt(feats.view(B * P, D), att.encoder_att.weight, att.encoder_att.bias)
+        h0 = torch.empty(B, H, **f32)
+        c.c0 = torch.empty(B, H, **f32)
+        c.att1 = torch.empty(B * P, A, **f32)
+        if c.tc:
+            for key, w in (("init_h", self.init_h.weight), ("init_c", self.init_c.weight), ("Wd", att.decoder_att.weight),
+                           ("We", att.encoder_att.weight), ("Wbeta", self.f_beta.weight), ("Whh", Whh)):
+                c.w16[key] = ops.to_bf16_padded(w)
+            c.meanb = ops.to_bf16_padded(c.mean)
+            c.featsb = ops.to_bf16_padded(feats.view(B * P, D))
+        else:
+            c.meanb = c.featsb = None
+        self._lin(c, c.mean, c.meanb, self.init_h.weight, "init_h", self.init_h.bias, h0, B)
+        self._lin(c, c.mean, c.meanb, self.init_c.weight, "init_c", self.init_c.bias, c.c0, B)
+        self._lin(c, feats.view(B * P, D), c.featsb, att.encoder_att.weight, "We", att.encoder_att.bias, c.att1, B * P)
         all_tf = all(coins)
         c.tok_override = None if all_tf else torch.full((N,), -1, dtype=torch.int32, device=dev)
-        c.X = torch.empty(N, E, **f32)
+        if c.tc:
+            c.X = None
+            c.Xb = torch.empty(N, (E + 7) // 8 * 8, **b16)
+        else:
+            c.X = torch.empty(N, E, **f32)
+            c.Xb = None
         ops.gather_pack_fwd(captions, emb.weight, None, False, d["row_b"], d["row_t"], None, N, c.X, c.p_drop, c.seed,
-                            seed_dev=c.seed_dev)
+                            seed_dev=c.seed_dev, Xb=c.Xb)
         c.XP = torch.empty(N, 4 * H, **f32)
+        self._proj_prepare(c)
         self._proj_embed_part(c, 0, N)
         c.CTX = torch.empty(N, D, **f32)
+        c.CTXb = torch.empty(N, D, **b16) if c.tc else None
         c.att2 = torch.empty(N, A, **f32)
         c.gate_pre = torch.empty(N, D, **f32)
         Tmax = max(plan.lengths)
         c.alphas = torch.zeros(B, Tmax, P, **f32)
         c.Hall = torch.empty(N, H, **f32)
         c.Call = torch.empty(N, H, **f32) if save else None
-        c.Hprev = torch.empty(N, H, **f32)
         c.gates = torch.empty(N, 4 * H, **f32) if save else None
+        if c.tc:
+            c.Hprev = None
+            c.Hb = torch.empty(N, H, **b16)
+            c.Hpb = torch.empty(N, H, **b16)
+            h0b = ops.to_bf16_padded(h0)
+        else:
+            c.Hprev = torch.empty(N, H, **f32)
+            c.Hb = c.Hpb = None
         c_state = c.c0.clone()
-        Whh, bhh = self._recurrent_weights()
         wfull = att.full_att.weight.view(-1)
-        c.bfull = float(att.full_att.bias.item()) if not save else None
-        bfull_t = att.full_att.bias
         out = self._out()
         V = out.weight.shape[0]
         pred = captions[:, 0].to(torch.int32).contiguous()
@@ -141,31 +185,49 @@ class _AttBase(_DecoderBase):
         # (model_att.py:63-65): it is passed as 0 to avoid a device->host read on the hot path.
         for t in range(T):
             n, r0 = plan.bs[t], plan.off[t]
-            hprev = h0 if t == 0 else c.Hall[plan.off[t - 1]:plan.off[t - 1] + n]
+            rp = plan.off[t - 1] if t > 0 else 0
+            hprev = h0 if t == 0 else c.Hall[rp:rp + n]
+            if c.tc:
+                hprev_b, hoff = (h0b, 0) if t == 0 else (c.Hb, rp)
+            else:
+                hprev_b, hoff = None, 0
             if not coins[t]:
                 if t > 0:
-                    bp, rp = plan.bs[t - 1], plan.off[t - 1]
+                    bp = plan.bs[t - 1]
                     lg = torch.empty(bp, V, **f32)
                     ops.gemm(ops.OP_NT, c.Hall, out.weight, lg, bp, V, H, H, H, V, bias=out.bias, a_off=rp * H)
                     ops.softmax_nll(lg, bp, V, argmax=am)
                     pred = am[:bp].to(torch.int32)
                 c.tok_override[r0:r0 + n] = pred[:n]
                 ops.gather_pack_fwd(captions, emb.weight, None, False, d["row_b"], d["row_t"], c.tok_override, n,
-                                    c.X, c.p_drop, c.seed, row_off=r0, seed_dev=c.seed_dev)
+                                    c.X, c.p_drop, c.seed, row_off=r0, seed_dev=c.seed_dev, Xb=c.Xb)
                 self._proj_embed_part(c, r0, n)
-            ops.gemm(ops.OP_NT, hprev, att.decoder_att.weight, c.att2, n, A, H, H, H, A, bias=att.decoder_att.bias,
-                     c_off=r0 * A)
-            ops.gemm(ops.OP_NT, hprev, self.f_beta.weight, c.gate_pre, n, D, H, H, H, D, bias=self.f_beta.bias,
-                     c_off=r0 * D)
+            self._lin(c, hprev, hprev_b, att.decoder_att.weight, "Wd", att.decoder_att.bias, c.att2, n, r0_out=r0,
+                      x_off_rows=hoff)
+            self._lin(c, hprev, hprev_b, self.f_beta.weight, "Wbeta", self.f_beta.bias, c.gate_pre, n, r0_out=r0,
+                      x_off_rows=hoff)
             ops.att_step_fwd(c.att1, c.att2[r0:], feats, wfull, 0.0, c.gate_pre[r0:], n, P, A, D,
                              c.alphas[:, t], Tmax * P, c.CTX[r0:], D)
+            if c.tc:
+                ops.cast_bf16(c.CTX, n, D, D, c.CTXb, D, D, src_off=r0 * D, dst_off=r0 * D)
             self._proj_step(c, r0, n)
-            ops.recur_fwd(self.cell, H, B, d["bs"], d["off"], t, t + 1, c.XP, Whh, bhh, hprev, c.Hall, c.Call,
-                          c.Hprev, c.gates, c_state)
+            if c.tc:
+                ops.recur_fwd_bf16(self.cell, H, B, d["bs"], d["off"], t, t + 1, c.XP, c.w16["Whh"], bhh, hprev, c.Hall,
+                                   c.Hb, c.Hpb, c.Call, c.gates, c_state)
+            else:
+                ops.recur_fwd(self.cell, H, B, d["bs"], d["off"], t, t + 1, c.XP, Whh, bhh, hprev, c.Hall, c.Call,
+                              c.Hprev, c.gates, c_state)
         c.grad_names = self._seq_grad_names(mode)
         return c
 
     # ---- backward ----------------------------------------------------------------------------------
+    def _tn(self, c, dY, dYb, Xf, Xb, out, M, Nn, K, lda, ldb, ldc, c_off=0):
+        """out[M,Nn] = dY^T X over K packed rows (a time-batched weight gradient)."""
+        if c.tc:
+            ops.gemm_bf16(ops.OP_TN, dYb, Xb, M, Nn, K, dYb.stride(0), Xb.stride(0), C=out, ldc=ldc, c_off=c_off)
+        else:
+            ops.gemm(ops.OP_TN, dY, Xf, out, M, Nn, K, lda, ldb, ldc, c_off=c_off)
+
     def _run_backward_att(self, c, dHall, dAlphas, gbuf, need_dfeat):
         a = self.arena()
         plan = c.plan
@@ -178,14 +240,18 @@ class _AttBase(_DecoderBase):
         att = self._att_module(c.mode)
         pre = self._att_prefix(c.mode)
         f32 = dict(dtype=torch.float32, device=dev)
+        b16 = dict(dtype=torch.bfloat16, device=dev)
         Whh, _ = self._recurrent_weights()
         wfull = att.full_att.weight.view(-1)
         dZ = torch.empty(N, 4 * H, **f32)
+        c.dZb = torch.empty(N, 4 * H, **b16) if c.tc else None
         dh = torch.zeros(B, H, **f32)
         dc = torch.zeros(B, H, **f32)
         c.dCTX = torch.empty(N, D, **f32)
         datt2 = torch.empty(N, A, **f32)
         dgate = torch.empty(N, D, **f32)
+        datt2b = torch.empty(N, A, **b16) if c.tc else None
+        dgateb = torch.empty(N, D, **b16) if c.tc else None
         datt1 = torch.zeros(B * P, A, **f32)
         gwf = self._gview(gbuf, [pre + "full_att.weight"], (A,))
         gwf.zero_()
@@ -198,26 +264,41 @@ class _AttBase(_DecoderBase):
         self._proj_bwd_begin(c, N)
         for t in range(T - 1, -1, -1):
             n, r0 = plan.bs[t], plan.off[t]
-            ops.recur_bwd(self.cell, H, B, d["bs"], d["off"], t, t + 1, Whh, c.c0, c.Call, c.gates, dHall, dZ, dh, dc)
+            if c.tc:
+                ops.recur_bwd_bf16(self.cell, H, B, d["bs"], d["off"], t, t + 1, c.w16["Whh"], c.c0, c.Call, c.gates,
+                                   dHall, dZ, c.dZb, dh, dc)
+            else:
+                ops.recur_bwd(self.cell, H, B, d["bs"], d["off"], t, t + 1, Whh, c.c0, c.Call, c.gates, dHall, dZ, dh, dc)
             self._proj_step_bwd(c, dZ, r0, n)        # -> c.dCTX rows
             ops.att_step_bwd(c.att1, c.att2[r0:], c.feats, wfull, 0.0, c.gate_pre[r0:], c.alphas[:, t], Tmax * P,
                              c.dCTX[r0:], D, dAl[:, t] if dAl is not None else None, Tmax * P, n, P, A, D,
                              datt2[r0:], dgate[r0:], datt1, gwf, dfeat)
             # into h_{t-1}: through decoder_att and f_beta
-            ops.gemm(ops.OP_NN, datt2, att.decoder_att.weight, dh, n, H, A, A, H, H, beta=1.0, a_off=r0 * A)
-            ops.gemm(ops.OP_NN, dgate, self.f_beta.weight, dh, n, H, D, D, H, H, beta=1.0, a_off=r0 * D)
+            if c.tc:
+                ops.cast_bf16(datt2, n, A, A, datt2b, A, A, src_off=r0 * A, dst_off=r0 * A)
+                ops.cast_bf16(dgate, n, D, D, dgateb, D, D, src_off=r0 * D, dst_off=r0 * D)
+                ops.gemm_bf16(ops.OP_NN, datt2b, c.w16["Wd"], n, H, A, A, H, C=dh, ldc=H, beta=1.0, a_off=r0 * A)
+                ops.gemm_bf16(ops.OP_NN, dgateb, c.w16["Wbeta"], n, H, D, D, H, C=dh, ldc=H, beta=1.0, a_off=r0 * D)
+            else:
+                ops.gemm(ops.OP_NN, datt2, att.decoder_att.weight, dh, n, H, A, A, H, H, beta=1.0, a_off=r0 * A)
+                ops.gemm(ops.OP_NN, dgate, self.f_beta.weight, dh, n, H, D, D, H, H, beta=1.0, a_off=r0 * D)
         # time-batched weight gradients
         gW, gbW = self._recurrent_grads(gbuf)
-        ops.gemm(ops.OP_TN, dZ, c.Hprev, gW, 4 * H, H, N, 4 * H, H, H)
+        if c.tc:
+            datt1b = ops.to_bf16_padded(datt1)
+        else:
+            datt1b = None
+        self._tn(c, dZ, c.dZb, c.Hprev, c.Hpb, gW, 4 * H, H, N, 4 * H, H, H)
         ops.colsum(dZ, N, 4 * H, 4 * H, gbW)
-        ops.gemm(ops.OP_TN, datt2, c.Hprev, self._gview(gbuf, [pre + "decoder_att.weight"], (A, H)), A, H, N, A, H, H)
+        self._tn(c, datt2, datt2b, c.Hprev, c.Hpb, self._gview(gbuf, [pre + "decoder_att.weight"], (A, H)), A, H, N, A, H, H)
         ops.colsum(datt2, N, A, A, self._gview(gbuf, [pre + "decoder_att.bias"], (A,)))
-        ops.gemm(ops.OP_TN, dgate, c.Hprev, self._gview(gbuf, ["f_beta.weight"], (D, H)), D, H, N, D, H, H)
+        self._tn(c, dgate, dgateb, c.Hprev, c.Hpb, self._gview(gbuf, ["f_beta.weight"], (D, H)), D, H, N, D, H, H)
         ops.colsum(dgate, N, D, D, self._gview(gbuf, ["f_beta.bias"], (D,)))
-        ops.gemm(ops.OP_TN, datt1, c.feats.view(B * P, D), self._gview(gbuf, [pre + "encoder_att.weight"], (A, D)),
-                 A, D, B * P, A, D, D)
+        self._tn(c, datt1, datt1b, c.feats.view(B * P, D), c.featsb,
+                 self._gview(gbuf, [pre + "encoder_att.weight"], (A, D)), A, D, B * P, A, D, D)
         ops.colsum(datt1, B * P, A, A, self._gview(gbuf, [pre + "encoder_att.bias"], (A,)))
-        # init_h / init_c: dh, dc now hold dL/dh0, dL/dc0
+        # init_h / init_c: dh, dc now hold dL/dh0, dL/dc0.  K = B rows only: kept in fp32 FFMA in both modes (these
+        # gradients sit at the end of the longest backward chain and are the most rounding-sensitive).
         ops.gemm(ops.OP_TN, dh, c.mean, self._gview(gbuf, ["init_h.weight"], (H, D)), H, D, B, H, D, D)
         ops.colsum(dh, B, H, H, self._gview(gbuf, ["init_h.bias"], (H,)))
         ops.gemm(ops.OP_TN, dc, c.mean, self._gview(gbuf, ["init_c.weight"], (H, D)), H, D, B, H, D, D)
@@ -392,19 +473,56 @@ class DecoderFactoredLSTMAtt(_AttBase):
         return names
 
     # -- projection pieces: V x = V[:, :E] emb + V[:, E:] ctx ----------------------------------------------
+    def _proj_prepare(self, c):
+        if not c.tc:
+            return
+        H, F, E, D = self.hidden_size, self.factored_size, self.embed_size, self.feature_size
+        Vc = self._stack("V_", (4 * F, E + D))
+        Ep = (E + 7) // 8 * 8
+        Vemb = torch.empty(4 * F, Ep, dtype=torch.bfloat16, device=Vc.device)
+        Vctx = torch.empty(4 * F, D, dtype=torch.bfloat16, device=Vc.device)
+        ops.cast_bf16(Vc, 4 * F, E, E + D, Vemb, Ep, Ep)
+        ops.cast_bf16(Vc, 4 * F, D, E + D, Vctx, D, D, src_off=E)
+        c.w16["Vemb"], c.w16["Vctx"] = Vemb, Vctx
+        c.w16["S"] = ops.to_bf16_padded(self._style_stack(c.mode, (4 * F, F)))
+        c.w16["U"] = ops.to_bf16_padded(self._stack("U_", (4 * H, F)))
+
     def _proj_embed_part(self, c, r0, n):
         H, F, E, D = self.hidden_size, self.factored_size, self.embed_size, self.feature_size
-        if r0 == 0 and n == c.X.shape[0]:
-            c.A1 = torch.empty(n, 4 * F, dtype=torch.float32, device=c.X.device)
-            c.A2 = torch.empty(n, 4 * F, dtype=torch.float32, device=c.X.device)
-        Vc, bV = self._stack("V_", (4 * F, E + D)), self._stack("V_", (4 * F,), bias=True)
+        dev = c.XP.device
+        if r0 == 0 and n == c.XP.shape[0]:
+            c.A1 = torch.empty(n, 4 * F, dtype=torch.float32, device=dev)
+            if c.tc:
+                c.A1b = torch.empty(n, 4 * F, dtype=torch.bfloat16, device=dev)
+                c.A2 = torch.empty(n, 4 * F, dtype=torch.bfloat16, device=dev)
+            else:
+                c.A2 = torch.empty(n, 4 * F, dtype=torch.float32, device=dev)
+        bV = self._stack("V_", (4 * F,), bias=True)
+        if c.tc:
+            Vb = c.w16["Vemb"]
+            Ep = Vb.stride(0)
+            ops.gemm_bf16(ops.OP_NT, c.Xb, Vb, n, 4 * F, Ep, Ep, Ep, C=c.A1, ldc=4 * F, bias=bV, a_off=r0 * Ep,
+                          c_off=r0 * 4 * F)
+            return
+        Vc = self._stack("V_", (4 * F, E + D))
         ops.gemm(ops.OP_NT, c.X, Vc, c.A1, n, 4 * F, E, E, E + D, 4 * F, bias=bV, a_off=r0 * E, c_off=r0 * 4 * F)
 
     def _proj_step(self, c, r0, n):
         H, F, E, D = self.hidden_size, self.factored_size, self.embed_size, self.feature_size
+        bS = self._style_stack(c.mode, (4 * F,), bias=True)
+        bU = self._stack("U_", (4 * H,), bias=True)
+        if c.tc:
+            Vx, Sb, Ub = c.w16["Vctx"], c.w16["S"], c.w16["U"]
+            ops.gemm_bf16(ops.OP_NT, c.CTXb, Vx, n, 4 * F, D, D, D, C=c.A1, ldc=4 * F, Cb=c.A1b, ldcb=4 * F, beta=1.0,
+                          a_off=r0 * D, c_off=r0 * 4 * F, cb_off=r0 * 4 * F)
+            ops.gemm_bf16(ops.OP_NT, c.A1b, Sb, n, F, F, 4 * F, F, Cb=c.A2, ldcb=4 * F, bias=bS, batch=4, sA=F, sB=F * F,
+                          sCb=F, sBias=F, a_off=r0 * 4 * F, cb_off=r0 * 4 * F)
+            ops.gemm_bf16(ops.OP_NT, c.A2, Ub, n, H, F, 4 * F, F, C=c.XP, ldc=4 * H, bias=bU, batch=4, sA=F, sB=H * F,
+                          sC=H, sBias=H, a_off=r0 * 4 * F, c_off=r0 * 4 * H)
+            return
         Vc = self._stack("V_", (4 * F, E + D))
-        Sc, bS = self._style_stack(c.mode, (4 * F, F)), self._style_stack(c.mode, (4 * F,), bias=True)
-        Uc, bU = self._stack("U_", (4 * H, F)), self._stack("U_", (4 * H,), bias=True)
+        Sc = self._style_stack(c.mode, (4 * F, F))
+        Uc = self._stack("U_", (4 * H, F))
         ops.gemm(ops.OP_NT, c.CTX, Vc, c.A1, n, 4 * F, D, D, E + D, 4 * F, beta=1.0, a_off=r0 * D, b_off=E,
                  c_off=r0 * 4 * F)
         ops.gemm(ops.OP_NT, c.A1, Sc, c.A2, n, F, F, 4 * F, F, 4 * F, bias=bS, batch=4, sA=F, sB=F * F, sC=F,
@@ -414,11 +532,23 @@ class DecoderFactoredLSTMAtt(_AttBase):
 
     def _proj_bwd_begin(self, c, N):
         F = self.factored_size
-        c.dA2 = torch.empty(N, 4 * F, dtype=torch.float32, device=c.X.device)
-        c.dA1 = torch.empty(N, 4 * F, dtype=torch.float32, device=c.X.device)
+        dev = c.XP.device
+        c.dA2 = torch.empty(N, 4 * F, dtype=torch.float32, device=dev)
+        c.dA1 = torch.empty(N, 4 * F, dtype=torch.float32, device=dev)
+        if c.tc:
+            c.dA2b = torch.empty(N, 4 * F, dtype=torch.bfloat16, device=dev)
+            c.dA1b = torch.empty(N, 4 * F, dtype=torch.bfloat16, device=dev)
 
     def _proj_step_bwd(self, c, dZ, r0, n):
         H, F, E, D = self.hidden_size, self.factored_size, self.embed_size, self.feature_size
+        if c.tc:
+            Vx, Sb, Ub = c.w16["Vctx"], c.w16["S"], c.w16["U"]
+            ops.gemm_bf16(ops.OP_NN, c.dZb, Ub, n, F, H, 4 * H, F, C=c.dA2, ldc=4 * F, Cb=c.dA2b, ldcb=4 * F, batch=4,
+                          sA=H, sB=H * F, sC=F, sCb=F, a_off=r0 * 4 * H, c_off=r0 * 4 * F, cb_off=r0 * 4 * F)
+            ops.gemm_bf16(ops.OP_NN, c.dA2b, Sb, n, F, F, 4 * F, F, C=c.dA1, ldc=4 * F, Cb=c.dA1b, ldcb=4 * F, batch=4,
+                          sA=F, sB=F * F, sC=F, sCb=F, a_off=r0 * 4 * F, c_off=r0 * 4 * F, cb_off=r0 * 4 * F)
+            ops.gemm_bf16(ops.OP_NN, c.dA1b, Vx, n, D, 4 * F, 4 * F, D, C=c.dCTX, ldc=D, a_off=r0 * 4 * F, c_off=r0 * D)
+            return
         Vc = self._stack("V_", (4 * F, E + D))
         Sc = self._style_stack(c.mode, (4 * F, F))
         Uc = self._stack("U_", (4 * H, F))
@@ -430,20 +560,29 @@ class DecoderFactoredLSTMAtt(_AttBase):
 
     def _proj_weight_grads(self, c, dZ, gbuf):
         H, F, E, D = self.hidden_size, self.factored_size, self.embed_size, self.feature_size
-        N = c.X.shape[0]
+        N = dZ.shape[0]
         mode = c.mode
-        Vc = self._stack("V_", (4 * F, E + D))
         gV, gbV = self._stack("V_", (4 * F, E + D), gbuf=gbuf), self._stack("V_", (4 * F,), gbuf=gbuf, bias=True)
         gS, gbS = self._style_stack(mode, (4 * F, F), gbuf=gbuf), self._style_stack(mode, (4 * F,), gbuf=gbuf, bias=True)
         gU, gbU = self._stack("U_", (4 * H, F), gbuf=gbuf), self._stack("U_", (4 * H,), gbuf=gbuf, bias=True)
-        ops.gemm(ops.OP_TN, dZ, c.A2, gU, H, F, N, 4 * H, 4 * F, F, batch=4, sA=H, sB=F, sC=H * F)
         ops.colsum(dZ, N, 4 * H, 4 * H, gbU)
-        ops.gemm(ops.OP_TN, c.dA2, c.A1, gS, F, F, N, 4 * F, 4 * F, F, batch=4, sA=F, sB=F, sC=F * F)
         ops.colsum(c.dA2, N, 4 * F, 4 * F, gbS)
-        ops.gemm(ops.OP_TN, c.dA1, c.X, gV, 4 * F, E, N, 4 * F, E, E + D)
-        ops.gemm(ops.OP_TN, c.dA1, c.CTX, gV, 4 * F, D, N, 4 * F, D, E + D, c_off=E)
         ops.colsum(c.dA1, N, 4 * F, 4 * F, gbV)
         dX = torch.empty(N, E, dtype=torch.float32, device=dZ.device)
+        if c.tc:
+            Vb = c.w16["Vemb"]
+            Ep = Vb.stride(0)
+            ops.gemm_bf16(ops.OP_TN, c.dZb, c.A2, H, F, N, 4 * H, 4 * F, C=gU, ldc=F, batch=4, sA=H, sB=F, sC=H * F)
+            ops.gemm_bf16(ops.OP_TN, c.dA2b, c.A1b, F, F, N, 4 * F, 4 * F, C=gS, ldc=F, batch=4, sA=F, sB=F, sC=F * F)
+            ops.gemm_bf16(ops.OP_TN, c.dA1b, c.Xb, 4 * F, E, N, 4 * F, Ep, C=gV, ldc=E + D)
+            ops.gemm_bf16(ops.OP_TN, c.dA1b, c.CTXb, 4 * F, D, N, 4 * F, D, C=gV, ldc=E + D, c_off=E)
+            ops.gemm_bf16(ops.OP_NN, c.dA1b, Vb, N, E, 4 * F, 4 * F, Ep, C=dX, ldc=E)
+            return dX
+        Vc = self._stack("V_", (4 * F, E + D))
+        ops.gemm(ops.OP_TN, dZ, c.A2, gU, H, F, N, 4 * H, 4 * F, F, batch=4, sA=H, sB=F, sC=H * F)
+        ops.gemm(ops.OP_TN, c.dA2, c.A1, gS, F, F, N, 4 * F, 4 * F, F, batch=4, sA=F, sB=F, sC=F * F)
+        ops.gemm(ops.OP_TN, c.dA1, c.X, gV, 4 * F, E, N, 4 * F, E, E + D)
+        ops.gemm(ops.OP_TN, c.dA1, c.CTX, gV, 4 * F, D, N, 4 * F, D, E + D, c_off=E)
         ops.gemm(ops.OP_NN, c.dA1, Vc, dX, N, E, 4 * F, 4 * F, E + D, E)
         return dX
 
@@ -532,13 +671,35 @@ class DecoderRNNAtt(_AttBase):
         ops.gemm(ops.OP_NT, X, self.lstm.weight_ih, c.XP, n, 4 * H, Ein, Ein, Ein, 4 * H, bias=self.lstm.bias_ih,
                  a_off=r0 * Ein, c_off=r0 * 4 * H)
 
+    def _proj_prepare(self, c):
+        if not c.tc:
+            return
+        H, E, D = self.hidden_size, self.embed_size, self.feature_size
+        W = self.lstm.weight_ih
+        Ep = (E + 7) // 8 * 8
+        Wemb = torch.empty(4 * H, Ep, dtype=torch.bfloat16, device=W.device)
+        Wctx = torch.empty(4 * H, D, dtype=torch.bfloat16, device=W.device)
+        ops.cast_bf16(W, 4 * H, E, E + D, Wemb, Ep, Ep)
+        ops.cast_bf16(W, 4 * H, D, E + D, Wctx, D, D, src_off=E)
+        c.w16["Wemb"], c.w16["Wctx"] = Wemb, Wctx
+
     def _proj_embed_part(self, c, r0, n):
         H, E, D = self.hidden_size, self.embed_size, self.feature_size
+        if c.tc:
+            Wb = c.w16["Wemb"]
+            Ep = Wb.stride(0)
+            ops.gemm_bf16(ops.OP_NT, c.Xb, Wb, n, 4 * H, Ep, Ep, Ep, C=c.XP, ldc=4 * H, bias=self.lstm.bias_ih,
+                          a_off=r0 * Ep, c_off=r0 * 4 * H)
+            return
         ops.gemm(ops.OP_NT, c.X, self.lstm.weight_ih, c.XP, n, 4 * H, E, E, E + D, 4 * H, bias=self.lstm.bias_ih,
                  a_off=r0 * E, c_off=r0 * 4 * H)
 
     def _proj_step(self, c, r0, n):
         H, E, D = self.hidden_size, self.embed_size, self.feature_size
+        if c.tc:
+            ops.gemm_bf16(ops.OP_NT, c.CTXb, c.w16["Wctx"], n, 4 * H, D, D, D, C=c.XP, ldc=4 * H, beta=1.0,
+                          a_off=r0 * D, c_off=r0 * 4 * H)
+            return
         ops.gemm(ops.OP_NT, c.CTX, self.lstm.weight_ih, c.XP, n, 4 * H, D, D, E + D, 4 * H, beta=1.0,
                  a_off=r0 * D, b_off=E, c_off=r0 * 4 * H)
 
@@ -547,17 +708,28 @@ class DecoderRNNAtt(_AttBase):
 
     def _proj_step_bwd(self, c, dZ, r0, n):
         H, E, D = self.hidden_size, self.embed_size, self.feature_size
+        if c.tc:
+            ops.gemm_bf16(ops.OP_NN, c.dZb, c.w16["Wctx"], n, D, 4 * H, 4 * H, D, C=c.dCTX, ldc=D, a_off=r0 * 4 * H,
+                          c_off=r0 * D)
+            return
         ops.gemm(ops.OP_NN, dZ, self.lstm.weight_ih, c.dCTX, n, D, 4 * H, 4 * H, E + D, D, a_off=r0 * 4 * H,
                  b_off=E, c_off=r0 * D)
 
     def _proj_weight_grads(self, c, dZ, gbuf):
         H, E, D = self.hidden_size, self.embed_size, self.feature_size
-        N = c.X.shape[0]
+        N = dZ.shape[0]
         gW = self._gview(gbuf, ["lstm.weight_ih"], (4 * H, E + D))
-        ops.gemm(ops.OP_TN, dZ, c.X, gW, 4 * H, E, N, 4 * H, E, E + D)
-        ops.gemm(ops.OP_TN, dZ, c.CTX, gW, 4 * H, D, N, 4 * H, D, E + D, c_off=E)
         ops.colsum(dZ, N, 4 * H, 4 * H, self._gview(gbuf, ["lstm.bias_ih"], (4 * H,)))
         dX = torch.empty(N, E, dtype=torch.float32, device=dZ.device)
+        if c.tc:
+            Wb = c.w16["Wemb"]
+            Ep = Wb.stride(0)
+            ops.gemm_bf16(ops.OP_TN, c.dZb, c.Xb, 4 * H, E, N, 4 * H, Ep, C=gW, ldc=E + D)
+            ops.gemm_bf16(ops.OP_TN, c.dZb, c.CTXb, 4 * H, D, N, 4 * H, D, C=gW, ldc=E + D, c_off=E)
+            ops.gemm_bf16(ops.OP_NN, c.dZb, Wb, N, E, 4 * H, 4 * H, Ep, C=dX, ldc=E)
+            return dX
+        ops.gemm(ops.OP_TN, dZ, c.X, gW, 4 * H, E, N, 4 * H, E, E + D)
+        ops.gemm(ops.OP_TN, dZ, c.CTX, gW, 4 * H, D, N, 4 * H, D, E + D, c_off=E)
         ops.gemm(ops.OP_NN, dZ, self.lstm.weight_ih, dX, N, E, 4 * H, 4 * H, E + D, E)
         return dX
 

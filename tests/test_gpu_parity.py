@@ -303,3 +303,57 @@ def test_graphed_train_step_matches_eager():
     for (n, p), (_, q) in zip(d1.named_parameters(), d2.named_parameters()):
         assert rel_l2(q.detach().cpu(), p.detach().cpu()) < 1e-5, n
     assert t2.optimizer.step_counts()["C.weight"] == 4 and t2.optimizer.step_counts()["S_sad_i.weight"] == 0
+
+
+@pytest.mark.parametrize("which,dims", [
+    ("factored_att", (64, 44, 64, 72, 600, 128, 3, 20, 9)),
+    ("nic_att", (64, 44, 64, 72, 600, 128, 3, 20, 9)),
+    ("factored_att", (512, 300, 512, 512, 2000, 2048, 7, 24, 12)),     # config 3 dimensions, smaller V/B
+])
+def test_bf16_mode_attention_within_2e2(which, dims):
+    """Attention decoders in bf16 mode (tcgen05 GEMMs + tensor-core recurrence steps) vs the float64 oracle.
+    Tolerance 2e-2 (north star) on loss / logits / alphas and, at config-3 dimensions, on the gradients (see the
+    per-parameter note below)."""
+    import icei_b200 as sn
+    from oracle import port
+    A, E, H, F, V, D, S, B, T = dims
+    torch.manual_seed(2)
+    torch.set_default_dtype(torch.float64)
+    try:
+        ref = port.DecoderFactoredLSTMAtt(A, E, H, F, V, 1, feature_size=D, dropout=0.0) if which == "factored_att" \
+            else port.DecoderRNNAtt(A, E, H, V, 1, feature_size=D, dropout=0.0)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    dec = sn.DecoderFactoredLSTMAtt(A, E, H, F, V, 1, feature_size=D, dropout=0.0) if which == "factored_att" \
+        else sn.DecoderRNNAtt(A, E, H, V, 1, feature_size=D, dropout=0.0)
+    kw = {"mode": "angry"} if which == "factored_att" else {}
+    dec.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    dec = dec.cuda().train().set_precision("bf16")
+    assert dec._tc_ok()
+    cap, lens, feats = port.synthetic_batch(B, T, V, feat_shape=(S, S, D), ragged=True, seed=6)
+    l1 = [l - 1 for l in lens]
+    tgt = port.pack_targets(cap[:, 1:], l1)
+    out_ref, al_ref = ref(cap[:, :-1], l1, feats.double(), teacher_forcing_ratio=1.0, **kw)
+    loss_ref = port.caption_loss(out_ref, tgt, al_ref)
+    ref.zero_grad(); loss_ref.backward()
+    out, al = dec(cap[:, :-1].cuda(), l1, feats.cuda(), teacher_forcing_ratio=1.0, **kw)
+    loss = port.caption_loss(out, tgt.cuda(), al)
+    dec.zero_grad(); loss.backward()
+    assert rel_l2(out.detach().cpu(), out_ref.detach()) < 2e-2
+    assert rel_l2(al.detach().cpu(), al_ref.detach()) < 2e-2
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    gref = {n: p.grad for n, p in ref.named_parameters()}
+    errs = {}
+    for n, p in dec.named_parameters():
+        if gref[n] is None:
+            assert p.grad is None, n
+        elif n.endswith("full_att.bias"):
+            assert float(p.grad.abs().max()) < 1e-6
+        else:
+            errs[n] = rel_l2(p.grad.cpu(), gref[n])
+    # 2e-2 everywhere at config-3 dimensions except the attention net's own parameters (3e-2: their gradient
+    # passes through the relu mask of att1+att2, which flips for pre-activations within bf16 rounding of 0);
+    # at the toy hidden size (H=64) every gradient carries more rounding noise (few terms to average): 6e-2.
+    tol = lambda n: 6e-2 if H < 128 else (3e-2 if n.startswith("attention") else 2e-2)
+    bad = {n: e for n, e in errs.items() if e >= tol(n)}
+    assert not bad, bad
