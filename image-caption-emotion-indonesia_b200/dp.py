@@ -33,6 +33,8 @@ class GradSync:
         self.bytes = 0
 
     def launch(self, flat, ranges):
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return                      # single process: nothing to exchange
         for o, n in ranges:
             w = dist.all_reduce(flat[o:o + n], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self.pending.append(w)
@@ -53,7 +55,9 @@ class DataParallelTrainer:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.sync = GradSync(group)
 
-    def step(self, captions, lengths, features, n_global=None, b_global=None, **kw):
+    def forward_backward(self, captions, lengths, features, n_global=None, b_global=None, grad_hook=None, **kw):
+        """zero_grad + forward + loss + backward with gradients scaled by 1/N_global; ``grad_hook(names)`` is
+        called when a bucket of gradients is final."""
         dec = self.decoder
         a = dec.arena()
         N_local = sum(int(l) for l in lengths)
@@ -64,13 +68,17 @@ class DataParallelTrainer:
         extra = {}
         if b_global is not None or hasattr(dec, "attention"):
             extra["b_global"] = b_global if b_global is not None else len(lengths) * self.world
+        return dec.forward_loss(captions, lengths, features, n_global=n_global, grad_hook=grad_hook, **extra, **kw)
+
+    def step(self, captions, lengths, features, n_global=None, b_global=None, **kw):
+        a = self.decoder.arena()
+        hook = None
         if self.world > 1:
             def hook(names):
                 self.sync.launch(a.gflat, merged_ranges(a, names))
-            loss, stats = dec.forward_loss(captions, lengths, features, n_global=n_global, grad_hook=hook,
-                                           **extra, **kw)
+        loss, stats = self.forward_backward(captions, lengths, features, n_global=n_global, b_global=b_global,
+                                            grad_hook=hook, **kw)
+        if self.world > 1:
             self.sync.wait()
-        else:
-            loss, stats = dec.forward_loss(captions, lengths, features, n_global=n_global, **extra, **kw)
         self.optimizer.step()
         return loss, stats

@@ -278,8 +278,10 @@ def test_bf16_mode_within_2e2(which, B, T, V, E, H, F):
             assert rel_l2(p.grad.cpu(), gref[n]) < 2e-2, n
 
 
-def test_graphed_train_step_matches_eager():
-    """A CUDA-graph replay is a real training step: 3 replays == 3 eager steps (same weights afterwards)."""
+@pytest.mark.parametrize("segmented", [False, True])
+def test_graphed_train_step_matches_eager(segmented):
+    """A CUDA-graph replay is a real training step: 3 replays == 3 eager steps (same weights afterwards).
+    ``segmented``: the 3-graph form used under data parallelism (split where gradient buckets become final)."""
     import icei_b200 as sn
     from oracle import port
     V, E, H, F, B, T = 300, 28, 64, 72, 12, 8
@@ -291,7 +293,9 @@ def test_graphed_train_step_matches_eager():
     cap, feats = cap.cuda(), feats.cuda()
     t1 = sn.DataParallelTrainer(d1, sn.FusedClampAdam(d1, lr=1e-3))
     t2 = sn.DataParallelTrainer(d2, sn.FusedClampAdam(d2, lr=1e-3))
-    g = sn.GraphedTrainStep(t2, cap, lens, feats, warmup=1, mode="happy", teacher_forcing_ratio=1.0)
+    g = sn.GraphedTrainStep(t2, cap, lens, feats, warmup=1, force_segmented=segmented, mode="happy",
+                            teacher_forcing_ratio=1.0)
+    assert len(g.segments) == (3 if segmented else 1)
     n_eager = 1            # GraphedTrainStep ran 1 real warm-up step on d2 (the capture pass only records)
     for _ in range(n_eager):
         t1.step(cap, lens, feats, mode="happy", teacher_forcing_ratio=1.0)
