@@ -23,7 +23,7 @@
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;   // 3 x 32 KB: two CTAs per SM -> one CTA's epilogue overlaps the other's MMA main loop
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;       // 16 KB each
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -110,7 +110,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
 gemm_tc_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSet tma_b, TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
