@@ -31,6 +31,7 @@ struct RArgs {
   float* Hall; __nv_bfloat16* Hb; __nv_bfloat16* Hprevb; float* Call; float* gates; float* c_state;
   const float* dHall; float* dZ; __nv_bfloat16* dZb; float* dh_carry; float* dc_carry;
   int* flags; int n_ub, nbb, BB;
+  int nbuf;        // forward: 2 = double-buffered staging across sample groups, 1 = single buffer (large H)
 };
 
 __device__ __forceinline__ void wait_flag(const int* flag, int target) {
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_bf16_kernel(RArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int H = a.H, ldw = H + PADB;
   __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(smem_raw);     // [32][ldw]  row j*8+u = Whh[j*H+u0+u, :]
-  __nv_bfloat16* INs = Ws + 32 * ldw;                                  // [G][ldw]
+  __nv_bfloat16* INs = Ws + 32 * ldw;                                  // [2][G][ldw] (double buffered)
   const int ub = blockIdx.x % a.n_ub, bb = blockIdx.x / a.n_ub;
   const int u0 = ub * 8, sb0 = bb * a.BB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -93,59 +94,84 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_bf16_kernel(RArgs a) {
   }
   __syncthreads();
 
+  __nv_bfloat16* INbuf[2] = {INs, a.nbuf == 2 ? INs + G * ldw : INs};
+  const float bh0 = a.bhh ? __ldg(a.bhh + u) : 0.f, bh1 = a.bhh ? __ldg(a.bhh + H + u) : 0.f;
+  const float bh2 = a.bhh ? __ldg(a.bhh + 2 * H + u) : 0.f, bh3 = a.bhh ? __ldg(a.bhh + 3 * H + u) : 0.f;
+
   for (int t = a.t0; t < a.t1; ++t) {
     const int bt = a.bs[t];
     const int nv = min(max(bt - sb0, 0), a.BB);
     if (nv > 0) {
       const int64_t row0 = (int64_t)a.off[t] + sb0;
-      // prefetch XP (+ recurrent bias) and c_{t-1} of this lane's two samples of the first group
+      const int n0 = warp * 8;
+      // XP (+ recurrent bias) and c_{t-1} of this lane's two samples of a group: loaded one group AHEAD so the
+      // global-memory latency hides under the wait / the previous group's MMAs
       float pz[2][4], pc[2];
+      auto prefetch = [&](int g0) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int sl = warp * 8 + sj + j;
-        pc[j] = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) pz[j][q] = 0.f;
-        if (sl < min(G, nv)) {
-          const float* xp = a.XP + (row0 + sl) * 4 * H + u;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) pz[j][q] = __ldg(xp + q * H) + (a.bhh ? __ldg(a.bhh + q * H + u) : 0.f);
-          pc[j] = a.c_state[(int64_t)(sb0 + sl) * H + u];
+        for (int j = 0; j < 2; ++j) {
+          const int sl = g0 + n0 + sj + j;
+          pc[j] = 0.f;
+          pz[j][0] = pz[j][1] = pz[j][2] = pz[j][3] = 0.f;
+          if (sl < nv) {
+            const float* xp = a.XP + (row0 + sl) * 4 * H + u;
+            pz[j][0] = __ldg(xp) + bh0; pz[j][1] = __ldg(xp + H) + bh1;
+            pz[j][2] = __ldg(xp + 2 * H) + bh2; pz[j][3] = __ldg(xp + 3 * H) + bh3;
+            pc[j] = a.c_state[(int64_t)(sb0 + sl) * H + u];
+          }
         }
-      }
+      };
+      prefetch(0);
       const bool first = (t == a.t0);
       if (!first) wait_flag(a.flags + bb * a.T + (t - 1), a.n_ub);
-      for (int g0 = 0; g0 < nv; g0 += G) {
+      const __nv_bfloat16* hsrc = first ? nullptr : a.Hb + ((int64_t)a.off[t - 1] + sb0) * H;
+      // stage(g): asynchronous copy of group g's h_{t-1} rows into buffer g&1
+      auto stage = [&](int g0, __nv_bfloat16* dst) {
         const int ng = min(G, nv - g0);
         if (!first) {
-          stage_async(INs, ldw, a.Hb + ((int64_t)a.off[t - 1] + sb0 + g0) * H, H, ng, 0, H);
-          cp_async_commit();
-          cp_async_wait<0>();
+          stage_async(dst, ldw, hsrc + (int64_t)g0 * H, H, ng, 0, H);
         } else {
           // state before step t0 comes in fp32 (zeros when NULL): convert while staging
           for (int i = tid; i < ng * (H >> 1); i += NT) {
             int r = i / (H >> 1), c = (i - r * (H >> 1)) << 1;
             float2 v = make_float2(0.f, 0.f);
             if (a.h_init) v = *reinterpret_cast<const float2*>(a.h_init + (int64_t)(sb0 + g0 + r) * H + c);
-            *reinterpret_cast<__nv_bfloat162*>(INs + r * ldw + c) = __floats2bfloat162_rn(v.x, v.y);
+            *reinterpret_cast<__nv_bfloat162*>(dst + r * ldw + c) = __floats2bfloat162_rn(v.x, v.y);
           }
         }
+        cp_async_commit();
+      };
+      stage(0, INbuf[0]);
+      int buf = 0;
+      for (int g0 = 0; g0 < nv; g0 += G, buf ^= 1) {
+        const int ng = min(G, nv - g0);
+        const bool more = g0 + G < nv;
+        if (more && a.nbuf == 2) { stage(g0 + G, INbuf[buf ^ 1]); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncthreads();
+        const __nv_bfloat16* IN = INbuf[buf];
         if (a.Hprevb) {      // h_{t-1} rows (bf16): operand of dW_hh = dZ^T Hprev
           for (int i = tid; i < ng; i += NT)
-            *reinterpret_cast<uint4*>(a.Hprevb + (row0 + g0 + i) * H + u0) = *reinterpret_cast<const uint4*>(INs + i * ldw + u0);
+            *reinterpret_cast<uint4*>(a.Hprevb + (row0 + g0 + i) * H + u0) = *reinterpret_cast<const uint4*>(IN + i * ldw + u0);
         }
+        // this group's operands were prefetched one iteration ago; move them aside and prefetch the next group's
+        float z[2][4], cp_[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          cp_[j] = pc[j];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) z[j][q] = pz[j][q];
+        }
+        if (more) prefetch(g0 + G);
         float acc[2][4];
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[m][q] = 0.f;
-        const int n0 = warp * 8;
         if (n0 < ng) {
           // A (Ws): lanes 0-15 -> rows 0-15 @k0, lanes 16-31 -> rows 0-15 @k0+8
           const __nv_bfloat16* a_ptr = Ws + (lane & 15) * ldw + (lane >> 4) * 8;
-          // B (INs): matrices {k0, k0+8, k0+16, k0+24} x samples n0..n0+7
-          const __nv_bfloat16* b_ptr = INs + (n0 + (lane & 7)) * ldw + (lane >> 3) * 8;
+          // B (IN): matrices {k0, k0+8, k0+16, k0+24} x samples n0..n0+7
+          const __nv_bfloat16* b_ptr = IN + (n0 + (lane & 7)) * ldw + (lane >> 3) * 8;
           for (int k0 = 0; k0 < H; k0 += 32) {
             uint32_t bfr[4], a0[4], a1[4];
             ldmatrix_x4(bfr, b_ptr + k0);
@@ -164,25 +190,15 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_bf16_kernel(RArgs a) {
           const int sl = g0 + n0 + sj + j;
           if (n0 + sj + j < ng) {
             const int64_t row = row0 + sl;
-            float z0, z1, z2, z3, cprev;
-            float* cst = a.c_state + (int64_t)(sb0 + sl) * H + u;
-            if (g0 == 0) {
-              z0 = pz[j][0]; z1 = pz[j][1]; z2 = pz[j][2]; z3 = pz[j][3]; cprev = pc[j];
-            } else {
-              const float* xp = a.XP + row * 4 * H + u;
-              z0 = xp[0]; z1 = xp[H]; z2 = xp[2 * H]; z3 = xp[3 * H];
-              if (a.bhh) { z0 += a.bhh[u]; z1 += a.bhh[H + u]; z2 += a.bhh[2 * H + u]; z3 += a.bhh[3 * H + u]; }
-              cprev = *cst;
-            }
             // accumulator rows: m-tile 0 = gate blocks 0,1 ; m-tile 1 = gate blocks 2,3
-            const float zi = acc[0][j] + z0, zf = acc[0][2 + j] + z1;
-            const float za = acc[1][j] + z2, zb = acc[1][2 + j] + z3;
+            const float zi = acc[0][j] + z[j][0], zf = acc[0][2 + j] + z[j][1];
+            const float za = acc[1][j] + z[j][2], zb = acc[1][2 + j] + z[j][3];
             const float zo = a.cell == SN_CELL_LSTM ? zb : za;
             const float zc = a.cell == SN_CELL_LSTM ? za : zb;
             const float gi = sn::sigmoidf_(zi), gf = sn::sigmoidf_(zf), go = sn::sigmoidf_(zo), gc = tanhf(zc);
-            const float c = gf * cprev + gi * gc;
+            const float c = gf * cp_[j] + gi * gc;
             const float h = a.cell == SN_CELL_LSTM ? go * tanhf(c) : go * c;
-            *cst = c;
+            a.c_state[(int64_t)(sb0 + sl) * H + u] = c;
             a.Hb[row * H + u] = __float2bfloat16(h);
             if (a.Hall) a.Hall[row * H + u] = h;
             if (a.Call) a.Call[row * H + u] = c;
@@ -192,7 +208,8 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_bf16_kernel(RArgs a) {
             }
           }
         }
-        __syncthreads();
+        __syncthreads();     // buffer `buf` may be overwritten by the staging issued in the next iteration
+        if (more && a.nbuf == 1) stage(g0 + G, INbuf[0]);
       }
     }
     signal_flag(a.flags + bb * a.T + t);
@@ -381,7 +398,8 @@ int32_t plan(bool bwd, int64_t H, int64_t B, int* n_ub, int* nbb, int* BB, size_
   *nbb = nb;
   *BB = (int)((B + nb - 1) / nb);
   if (!bwd) {
-    *smem = ((size_t)32 * (H + PADB) + (size_t)G * (H + PADB)) * 2;
+    *smem = ((size_t)32 * (H + PADB) + (size_t)2 * G * (H + PADB)) * 2;   // W slice + double-buffered h staging
+    if (*smem > (size_t)d.smem_optin) *smem = ((size_t)32 * (H + PADB) + (size_t)G * (H + PADB)) * 2;   // single
   } else {
     const int64_t K = 4 * H, KC = K < KCB ? K : KCB;
     *smem = ((size_t)UBB * (K + PADB) + (size_t)2 * GB * (KC + PADB)) * 2 + 2 * 4 * 32 * 4 * sizeof(float);
@@ -420,6 +438,7 @@ int32_t sn_recur_fwd_bf16(int32_t cell, int64_t H, int64_t B, const int32_t* bat
   a.bs = batch_sizes; a.off = offsets; a.XP = XP; a.Wb = (const __nv_bfloat16*)Whh_bf16; a.bhh = bhh;
   a.h_init = h_init; a.Hall = Hall; a.Hb = (__nv_bfloat16*)Hb; a.Hprevb = (__nv_bfloat16*)Hprevb;
   a.Call = Call; a.gates = gates; a.c_state = c_state; a.flags = (int*)ws;
+  a.nbuf = smem >= ((size_t)32 * (H + PADB) + (size_t)2 * G * (H + PADB)) * 2 ? 2 : 1;
   cudaStream_t st = (cudaStream_t)stream;
   SN_CUDA(cudaMemsetAsync(ws, 0, sizeof(int) * (size_t)a.nbb * (size_t)t1, st));
   return launch(recur_fwd_bf16_kernel, a, smem, st, "sn_recur_fwd_bf16");
