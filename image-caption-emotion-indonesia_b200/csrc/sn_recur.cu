@@ -90,10 +90,11 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // a thread in flight at once); rows past nrows are left untouched (their results are never stored)
 __device__ __forceinline__ void stage_rows_async(float* __restrict__ INs, int ldi, const float* __restrict__ src,
                                                  int64_t ld, int nrows, int k0, int KC) {
-  const int vec_per_row = KC >> 2;
-  for (int i = threadIdx.x; i < nrows * vec_per_row; i += NT) {
-    int r = i / vec_per_row, c = (i - r * vec_per_row) << 2;
-    cp_async16(INs + r * ldi + c, src + (int64_t)r * ld + k0 + c);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < nrows; r += NW) {            // division-free: a warp per row, 16-byte chunks per lane
+    const float* s = src + (int64_t)r * ld + k0;
+    float* d = INs + r * ldi;
+    for (int c = lane << 2; c < KC; c += 128) cp_async16(d + c, s + c);
   }
 }
 
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_kernel(RecurArgs a) {
         if (kl + 4 * j < SW && sl < min(G, nv)) {
           const float* xp = a.XP + (row0 + sl) * 4 * H + u0 + rl;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) pz[j][q] = __ldg(xp + q * H) + (a.bhh ? __ldg(a.bhh + q * H + u0 + rl) : 0.f);
+          for (int q = 0; q < 4; ++q) pz[j][q] = __ldg(xp + q * H);     // raw loads: arithmetic here would stall the prefetch
           pc[j] = a.c_state[(int64_t)(sb0 + sl) * H + u0 + rl];
         }
       }
@@ -198,9 +199,9 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_kernel(RecurArgs a) {
             } else {
               const float* xp = a.XP + row * 4 * H + u;
               z0 = xp[0]; z1 = xp[H]; z2 = xp[2 * H]; z3 = xp[3 * H];
-              if (a.bhh) { z0 += a.bhh[u]; z1 += a.bhh[H + u]; z2 += a.bhh[2 * H + u]; z3 += a.bhh[3 * H + u]; }
               cprev = *cst;
             }
+            if (a.bhh) { z0 += a.bhh[u]; z1 += a.bhh[H + u]; z2 += a.bhh[2 * H + u]; z3 += a.bhh[3 * H + u]; }
             const float zi = acc[0][s] + z0, zf = acc[1][s] + z1;
             const float za = acc[2][s] + z2, zb = acc[3][s] + z3;
             const float zo = a.cell == SN_CELL_LSTM ? zb : za;

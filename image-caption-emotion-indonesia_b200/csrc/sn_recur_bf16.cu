@@ -64,10 +64,11 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 // stage rows [0,nrows) x bf16 cols [k0, k0+KC) (KC multiple of 8) into smem rows of pitch ldi (elements)
 __device__ __forceinline__ void stage_async(__nv_bfloat16* INs, int ldi, const __nv_bfloat16* src, int64_t ld,
                                             int nrows, int k0, int KC) {
-  const int vpr = KC >> 3;
-  for (int i = threadIdx.x; i < nrows * vpr; i += NT) {
-    int r = i / vpr, c = (i - r * vpr) << 3;
-    cp_async16(INs + r * ldi + c, src + (int64_t)r * ld + k0 + c);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < nrows; r += NW) {
+    const __nv_bfloat16* s = src + (int64_t)r * ld + k0;
+    __nv_bfloat16* d = INs + r * ldi;
+    for (int c = lane << 3; c < KC; c += 256) cp_async16(d + c, s + c);
   }
 }
 
@@ -115,8 +116,9 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_bf16_kernel(RArgs a) {
           pz[j][0] = pz[j][1] = pz[j][2] = pz[j][3] = 0.f;
           if (sl < nv) {
             const float* xp = a.XP + (row0 + sl) * 4 * H + u;
-            pz[j][0] = __ldg(xp) + bh0; pz[j][1] = __ldg(xp + H) + bh1;
-            pz[j][2] = __ldg(xp + 2 * H) + bh2; pz[j][3] = __ldg(xp + 3 * H) + bh3;
+            // raw loads only: any arithmetic here would stall on the load and defeat the prefetch
+            pz[j][0] = __ldg(xp); pz[j][1] = __ldg(xp + H);
+            pz[j][2] = __ldg(xp + 2 * H); pz[j][3] = __ldg(xp + 3 * H);
             pc[j] = a.c_state[(int64_t)(sb0 + sl) * H + u];
           }
         }
@@ -191,8 +193,8 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_bf16_kernel(RArgs a) {
           if (n0 + sj + j < ng) {
             const int64_t row = row0 + sl;
             // accumulator rows: m-tile 0 = gate blocks 0,1 ; m-tile 1 = gate blocks 2,3
-            const float zi = acc[0][j] + z[j][0], zf = acc[0][2 + j] + z[j][1];
-            const float za = acc[1][j] + z[j][2], zb = acc[1][2 + j] + z[j][3];
+            const float zi = acc[0][j] + z[j][0] + bh0, zf = acc[0][2 + j] + z[j][1] + bh1;
+            const float za = acc[1][j] + z[j][2] + bh2, zb = acc[1][2 + j] + z[j][3] + bh3;
             const float zo = a.cell == SN_CELL_LSTM ? zb : za;
             const float zc = a.cell == SN_CELL_LSTM ? za : zb;
             const float gi = sn::sigmoidf_(zi), gf = sn::sigmoidf_(zf), go = sn::sigmoidf_(zo), gc = tanhf(zc);
