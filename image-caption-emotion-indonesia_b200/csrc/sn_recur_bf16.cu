@@ -164,28 +164,33 @@ __global__ void __launch_bounds__(NT, 1) recur_fwd_bf16_kernel(RArgs a) {
           for (int q = 0; q < 4; ++q) z[j][q] = pz[j][q];
         }
         if (more) prefetch(g0 + G);
-        float acc[2][4];
+        float acc[2][4], acc2[2][4];       // two k-phases per m-tile: 4 independent MMA dependency chains
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc[m][q] = 0.f;
+          for (int q = 0; q < 4; ++q) acc[m][q] = acc2[m][q] = 0.f;
         if (n0 < ng) {
           // A (Ws): lanes 0-15 -> rows 0-15 @k0, lanes 16-31 -> rows 0-15 @k0+8
           const __nv_bfloat16* a_ptr = Ws + (lane & 15) * ldw + (lane >> 4) * 8;
           // B (IN): matrices {k0, k0+8, k0+16, k0+24} x samples n0..n0+7
           const __nv_bfloat16* b_ptr = IN + (n0 + (lane & 7)) * ldw + (lane >> 3) * 8;
+#pragma unroll 2
           for (int k0 = 0; k0 < H; k0 += 32) {
-            uint32_t bfr[4], a0[4], a1[4];
+            uint32_t bfr[4], a0[4], a1[4], a2[4], a3[4];
             ldmatrix_x4(bfr, b_ptr + k0);
             ldmatrix_x4(a0, a_ptr + k0);
             ldmatrix_x4(a1, a_ptr + 16 * ldw + k0);
+            ldmatrix_x4(a2, a_ptr + k0 + 16);
+            ldmatrix_x4(a3, a_ptr + 16 * ldw + k0 + 16);
             mma_bf16(acc[0], a0, bfr[0], bfr[1]);
             mma_bf16(acc[1], a1, bfr[0], bfr[1]);
-            ldmatrix_x4(a0, a_ptr + k0 + 16);
-            ldmatrix_x4(a1, a_ptr + 16 * ldw + k0 + 16);
-            mma_bf16(acc[0], a0, bfr[2], bfr[3]);
-            mma_bf16(acc[1], a1, bfr[2], bfr[3]);
+            mma_bf16(acc2[0], a2, bfr[2], bfr[3]);
+            mma_bf16(acc2[1], a3, bfr[2], bfr[3]);
           }
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[m][q] += acc2[m][q];
         }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -242,9 +247,13 @@ __global__ void __launch_bounds__(NT, 1) recur_bwd_bf16_kernel(RArgs a) {
   // after the cross-warp reduction thread tid finishes pairs p = 2*tid, 2*tid+1:  s = p / 16, u = p % 16
   const int ps = (2 * tid) >> 4, pu = (2 * tid) & 15;
 
-  for (int i = tid; i < K * UBB; i += NT) {
-    int k = i >> 4, uu = i & 15;
-    Ws[uu * ldw + k] = a.Wb[(int64_t)k * H + u0 + uu];
+  // Ws[u][k] = Whh[k, u0+u]: each thread reads 8 consecutive units of one row k (16 B) and scatters them
+  for (int i = tid; i < K * 2; i += NT) {
+    const int k = i >> 1, half = i & 1;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.Wb + (int64_t)k * H + u0 + half * 8));
+    const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) Ws[(half * 8 + q) * ldw + k] = e[q];
   }
   __syncthreads();
 
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(NT, 1) recur_bwd_bf16_kernel(RArgs a) {
         const int ng = min(GB, nv - g0);
         const int ngrec = min(max(nrec - g0, 0), GB);
         if (ngrec > 0) {
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};   // two MMA dependency chains
           const __nv_bfloat16* src = a.dZb + (rown0 + g0) * K;
           const int nchunk = K / KC;
           stage_async(IN0, ldi, src, K, ngrec, 0, KC);
@@ -308,18 +317,20 @@ __global__ void __launch_bounds__(NT, 1) recur_bwd_bf16_kernel(RArgs a) {
               const int kh = KC >> 1;                      // this warp's half of the chunk
               const __nv_bfloat16* a_ptr = Ws + (lane & 15) * ldw + ci * KC + khalf * kh + (lane >> 4) * 8;
               const __nv_bfloat16* b_ptr = cur + (ntile * 8 + (lane & 7)) * ldi + khalf * kh + (lane >> 3) * 8;
+#pragma unroll 2
               for (int k0 = 0; k0 < kh; k0 += 32) {
-                uint32_t bfr[4], a0[4];
+                uint32_t bfr[4], a0[4], a1[4];
                 ldmatrix_x4(bfr, b_ptr + k0);
                 ldmatrix_x4(a0, a_ptr + k0);
+                ldmatrix_x4(a1, a_ptr + k0 + 16);
                 mma_bf16(acc, a0, bfr[0], bfr[1]);
-                ldmatrix_x4(a0, a_ptr + k0 + 16);
-                mma_bf16(acc, a0, bfr[2], bfr[3]);
+                mma_bf16(accb, a1, bfr[2], bfr[3]);
               }
             }
             __syncthreads();
           }
-          *reinterpret_cast<float4*>(part + ((khalf * 4 + ntile) * 32 + lane) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          *reinterpret_cast<float4*>(part + ((khalf * 4 + ntile) * 32 + lane) * 4) =
+              make_float4(acc[0] + accb[0], acc[1] + accb[1], acc[2] + accb[2], acc[3] + accb[3]);
         }
         __syncthreads();
 #pragma unroll
