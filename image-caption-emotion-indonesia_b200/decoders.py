@@ -133,6 +133,26 @@ class _DecoderBase(nn.Module):
     def _publish(self, names, gbuf):
         self.arena().publish_grads(names, gbuf)
 
+    def _side(self):
+        """Second CUDA stream for GEMMs that are independent of the critical chain (weight gradients): each has
+        only 45-320 tiles, so two of them side by side fill the 148 SMs where one cannot.  Works eagerly and
+        under CUDA-graph capture (fork/join become parallel graph branches)."""
+        st = self.__dict__.get("_side_stream")
+        if st is None:
+            st = torch.cuda.Stream()
+            self.__dict__["_side_stream"] = st
+        return st
+
+    def _fork(self):
+        side = self._side()
+        side.wait_stream(torch.cuda.current_stream())
+        return side
+
+    def _join(self):
+        st = self.__dict__.get("_side_stream")
+        if st is not None:
+            torch.cuda.current_stream().wait_stream(st)
+
     def _next_seed(self, dev, p_drop):
         """Dropout randomness = hash(seed + device counter, row, col).  The counter lives in device memory
         and is bumped by a (graph-capturable) device op once per forward, so CUDA-graph replays draw a fresh
@@ -289,10 +309,13 @@ class _DecoderBase(nn.Module):
             c.dZb = torch.empty(N, 4 * H, dtype=torch.bfloat16, device=dev)
             ops.recur_bwd_bf16(self.cell, H, B, d["bs"], d["off"], 0, T, c.w16["Whh"], None, c.Call, c.gates, dHall,
                                dZ, c.dZb, dh, dc)
-            ops.gemm_bf16(ops.OP_TN, c.dZb, c.Hpb, 4 * H, H, N, 4 * H, H, C=gW, ldc=H)
-            ops.colsum(dZ, N, 4 * H, 4 * H, gbW)
+            with torch.cuda.stream(self._fork()):
+                ops.gemm_bf16(ops.OP_TN, c.dZb, c.Hpb, 4 * H, H, N, 4 * H, H, C=gW, ldc=H)
+                ops.colsum(dZ, N, 4 * H, 4 * H, gbW)
             dX = self._input_projection_bwd(c, dZ, gbuf)
-            return self._embedding_bwd(c, dX, gbuf, need_dfeat)
+            out = self._embedding_bwd(c, dX, gbuf, need_dfeat)
+            self._join()
+            return out
         ops.recur_bwd(self.cell, H, B, d["bs"], d["off"], 0, T, Whh, None, c.Call, c.gates, dHall, dZ, dh, dc)
         # dW_hh = dZ^T Hprev ; d b_hh = colsum(dZ)
         if self.bf16:
@@ -358,11 +381,15 @@ class _DecoderBase(nn.Module):
             Wb = self.__dict__.pop("_out_w16", None) if dLb is not None and have_b16 else None
             if Wb is None:
                 Wb = ops.to_bf16_padded(out.weight)
+            if have_b16:
+                # dC / db_C do not feed the recurrence: side stream, joined by the caller (_join)
+                with torch.cuda.stream(self._fork()):
+                    ops.gemm_bf16(ops.OP_TN, dLb, Hb, V, H, N, dLb.stride(0), Hb.stride(0), C=gC, ldc=H)
+                    ops.colsum_bf16(dLb, N, V, dLb.stride(0), gb)
+                ops.gemm_bf16(ops.OP_NN, dLb, Wb, N, H, V, dLb.stride(0), Wb.stride(0), C=dHall, ldc=H)
+                return dHall
             ops.gemm_bf16(ops.OP_NN, dLb, Wb, N, H, V, dLb.stride(0), Wb.stride(0), C=dHall, ldc=H)
             ops.gemm_bf16(ops.OP_TN, dLb, Hb, V, H, N, dLb.stride(0), Hb.stride(0), C=gC, ldc=H)
-            if have_b16:
-                ops.colsum_bf16(dLb, N, V, dLb.stride(0), gb)
-                return dHall
         else:
             ops.gemm(ops.OP_NN, dlogits, out.weight, dHall, N, H, V, dlogits.stride(0), H, H)
             ops.gemm(ops.OP_TN, dlogits, Hall, gC, V, H, N, dlogits.stride(0), H, H)
@@ -426,9 +453,11 @@ class _DecoderBase(nn.Module):
                 gbuf = self._grad_target(c.grad_names + list(self._out_names()))
                 dHall = self._vocab_backward(c.Hall, logits, gbuf, c.Hb, dLb)
                 if grad_hook is not None and gbuf is self.arena().gflat:
+                    self._join()
                     grad_hook(list(self._out_names()))       # bucket 0 is final: overlap its all-reduce
                 need_dfeat = features is not None and features.requires_grad
                 dfeat = self._run_backward(c, dHall, gbuf, need_dfeat)
+                self._join()
                 self._publish(c.grad_names + list(self._out_names()), gbuf)
                 if grad_hook is not None:
                     grad_hook(c.grad_names if gbuf is self.arena().gflat else c.grad_names + list(self._out_names()))
@@ -610,19 +639,28 @@ class DecoderFactoredLSTM(_DecoderBase):
         dZb = c.dZb
         f32 = dict(dtype=torch.float32, device=dev)
         b16 = dict(dtype=torch.bfloat16, device=dev)
-        ops.gemm_bf16(ops.OP_TN, dZb, c.A2, H, F, N, 4 * H, 4 * F, C=gU, ldc=F, batch=4, sA=H, sB=F, sC=H * F)
-        ops.colsum(dZ, N, 4 * H, 4 * H, gbU)
+        main = torch.cuda.current_stream()
+        side = self._side()
+        # critical chain (main stream): dZ -> dA2 -> dA1 -> dX ; weight / bias gradients trail on the side stream
         dA2, dA2b = torch.empty(N, 4 * F, **f32), torch.empty(N, 4 * F, **b16)
+        dA1, dA1b = torch.empty(N, 4 * F, **f32), torch.empty(N, 4 * F, **b16)
+        dX = torch.empty(N, Ein, **f32)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.gemm_bf16(ops.OP_TN, dZb, c.A2, H, F, N, 4 * H, 4 * F, C=gU, ldc=F, batch=4, sA=H, sB=F, sC=H * F)
+            ops.colsum(dZ, N, 4 * H, 4 * H, gbU)
         ops.gemm_bf16(ops.OP_NN, dZb, Ub, N, F, H, 4 * H, Fp, C=dA2, ldc=4 * F, Cb=dA2b, ldcb=4 * F, batch=4, sA=H,
                       sB=H * Fp, sC=F, sCb=F)
-        ops.gemm_bf16(ops.OP_TN, dA2b, c.A1, F, F, N, 4 * F, 4 * F, C=gS, ldc=F, batch=4, sA=F, sB=F, sC=F * F)
-        ops.colsum(dA2, N, 4 * F, 4 * F, gbS)
-        dA1, dA1b = dA2, torch.empty(N, 4 * F, **b16)      # dA2 (fp32) is dead after its colsum: reuse
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.gemm_bf16(ops.OP_TN, dA2b, c.A1, F, F, N, 4 * F, 4 * F, C=gS, ldc=F, batch=4, sA=F, sB=F, sC=F * F)
+            ops.colsum(dA2, N, 4 * F, 4 * F, gbS)
         ops.gemm_bf16(ops.OP_NN, dA2b, Sb, N, F, F, 4 * F, Fp, C=dA1, ldc=4 * F, Cb=dA1b, ldcb=4 * F, batch=4, sA=F,
                       sB=F * Fp, sC=F, sCb=F)
-        ops.gemm_bf16(ops.OP_TN, dA1b, c.Xb, 4 * F, Ein, N, 4 * F, Ep, C=gV, ldc=Ein)
-        ops.colsum(dA1, N, 4 * F, 4 * F, gbV)
-        dX = torch.empty(N, Ein, **f32)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.gemm_bf16(ops.OP_TN, dA1b, c.Xb, 4 * F, Ein, N, 4 * F, Ep, C=gV, ldc=Ein)
+            ops.colsum(dA1, N, 4 * F, 4 * F, gbV)
         ops.gemm_bf16(ops.OP_NN, dA1b, Vb, N, Ein, 4 * F, 4 * F, Ep, C=dX, ldc=Ein)
         return dX
 
