@@ -3,7 +3,11 @@
 // (the reference recomputes it every step, stylenet/model_att.py:59); this kernel consumes it.
 // One CTA per sample; feature/att1 rows are read with coalesced 128-bit loads; HBM-bound
 // (algorithmic bytes per sample-step: P*(A+D)*4 read, (D+P)*4 written).
+#include <cooperative_groups.h>
+
 #include "sn_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -157,6 +161,173 @@ __global__ void __launch_bounds__(NT) att_step_bwd_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Cluster versions: CL = 4 CTAs per sample (a thread-block cluster).  The pixel axis (scores, attention-net
+// backward) and the feature axis D (context, gate, d alpha partials) are each split 4 ways; the P scores /
+// partial d alpha vectors are exchanged through distributed shared memory.  4x the CTAs of the per-sample
+// kernels -> enough memory-level parallelism to stream the feature map near HBM speed.
+// ------------------------------------------------------------------------------------------------------
+constexpr int CL = 4;
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT)
+att_step_fwd_cl_kernel(const float* __restrict__ att1, const float* __restrict__ att2, const float* __restrict__ feat,
+                       const float* __restrict__ wfull, float bfull, const float* __restrict__ gate_pre, int P, int A,
+                       int D, float* __restrict__ alpha, int64_t ld_alpha, float* __restrict__ ctx, int64_t ldc) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ float sm[];
+  float* att2s = sm;          // [A]
+  float* ws = sm + A;         // [A]
+  float* e = ws + A;          // [P]  all scores of the sample (filled by the 4 CTAs through DSMEM)
+  __shared__ float red[NT / 32];
+  const int r = (int)cluster.block_rank();
+  const int b = blockIdx.x / CL, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int a = tid; a < A; a += NT) { att2s[a] = att2[(int64_t)b * A + a]; ws[a] = wfull[a]; }
+  __syncthreads();
+  // scores of this CTA's pixels, broadcast into every CTA's e[]
+  const float* a1b = att1 + (int64_t)b * P * A;
+  for (int p = r + CL * warp; p < P; p += CL * (NT / 32)) {
+    const float* row = a1b + (int64_t)p * A;
+    float s = 0.f;
+    for (int a = lane; a < A; a += 32) s = fmaf(ws[a], fmaxf(__ldg(row + a) + att2s[a], 0.f), s);
+    s = sn::warp_sum(s) + bfull;
+    if (lane < CL) cluster.map_shared_rank(e, lane)[p] = s;
+  }
+  cluster.sync();
+  // softmax over pixels (each CTA redundantly; P is tiny)
+  float mx = -INFINITY;
+  for (int p = tid; p < P; p += NT) mx = fmaxf(mx, e[p]);
+  mx = sn::warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < NT / 32; ++w) mx = fmaxf(mx, red[w]);
+  float se = 0.f;
+  for (int p = tid; p < P; p += NT) { float v = expf(e[p] - mx); e[p] = v; se += v; }
+  se = block_sum(se, red);
+  const float inv = 1.f / se;
+  for (int p = tid; p < P; p += NT) {
+    float al = e[p] * inv;
+    e[p] = al;
+    if (r == 0) alpha[(int64_t)b * ld_alpha + p] = al;
+  }
+  __syncthreads();
+  // gated context for this CTA's D chunk, two features per thread (64-bit loads, coalesced across the warp)
+  const int chunk = D / CL, d0 = r * chunk;
+  const float* fb = feat + (int64_t)b * P * D + d0;
+  for (int dd = 2 * tid; dd < chunk; dd += 2 * NT) {
+    float sx = 0.f, sy = 0.f;
+#pragma unroll 7
+    for (int p = 0; p < P; ++p) {
+      const float2 f = __ldg(reinterpret_cast<const float2*>(fb + (int64_t)p * D + dd));
+      sx = fmaf(e[p], f.x, sx);
+      sy = fmaf(e[p], f.y, sy);
+    }
+    const float2 gp = *reinterpret_cast<const float2*>(gate_pre + (int64_t)b * D + d0 + dd);
+    ctx[(int64_t)b * ldc + d0 + dd] = sn::sigmoidf_(gp.x) * sx;
+    ctx[(int64_t)b * ldc + d0 + dd + 1] = sn::sigmoidf_(gp.y) * sy;
+  }
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT)
+att_step_bwd_cl_kernel(const float* __restrict__ att1, const float* __restrict__ att2, const float* __restrict__ feat,
+                       const float* __restrict__ wfull, const float* __restrict__ gate_pre,
+                       const float* __restrict__ alpha, int64_t ld_alpha, const float* __restrict__ dctx, int64_t ldc,
+                       const float* __restrict__ dalpha_extra, int64_t ld_da, int P, int A, int D,
+                       float* __restrict__ datt2, float* __restrict__ dgate_pre, float* __restrict__ datt1,
+                       float* __restrict__ dwfull, float* __restrict__ dfeat) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ float sm[];
+  float* att2s = sm;              // [A]
+  float* ws = att2s + A;          // [A]
+  float* al = ws + A;             // [P]
+  float* dal = al + P;            // [P]        d alpha (sum over the cluster), then d e
+  float* slots = dal + P;         // [CL][P]    partial d alpha of every CTA of the cluster (DSMEM targets)
+  float* part = slots + CL * P;   // [2][8][A]  cross-warp partials of pass C
+  __shared__ float red[NT / 32];
+  const int r = (int)cluster.block_rank();
+  const int b = blockIdx.x / CL, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int a = tid; a < A; a += NT) { att2s[a] = att2[(int64_t)b * A + a]; ws[a] = wfull[a]; }
+  for (int p = tid; p < P; p += NT) { al[p] = alpha[(int64_t)b * ld_alpha + p]; dal[p] = 0.f; }
+  __syncthreads();
+  // pass A (own D chunk, single pass over the feature map): awe_raw, gate gradient, partial d alpha
+  const int chunk = D / CL, d0 = r * chunk;
+  const float* fb = feat + (int64_t)b * P * D + d0;
+  for (int dd0 = 0; dd0 < chunk; dd0 += 2 * NT) {
+    const int dd = dd0 + 2 * tid;
+    const bool act = dd < chunk;
+    float gx = 0.f, gy = 0.f, dax = 0.f, day = 0.f, sx = 0.f, sy = 0.f;
+    if (act) {
+      const float2 gp = *reinterpret_cast<const float2*>(gate_pre + (int64_t)b * D + d0 + dd);
+      gx = sn::sigmoidf_(gp.x); gy = sn::sigmoidf_(gp.y);
+      dax = dctx[(int64_t)b * ldc + d0 + dd] * gx;          // d awe = dctx * gate
+      day = dctx[(int64_t)b * ldc + d0 + dd + 1] * gy;
+    }
+    for (int p = 0; p < P; ++p) {
+      float2 f = make_float2(0.f, 0.f);
+      if (act) f = __ldg(reinterpret_cast<const float2*>(fb + (int64_t)p * D + dd));
+      sx = fmaf(al[p], f.x, sx);
+      sy = fmaf(al[p], f.y, sy);
+      float t = sn::warp_sum(fmaf(dax, f.x, day * f.y));
+      if (lane == 0) atomicAdd(dal + p, t);
+      if (dfeat && act) {
+        float* df = dfeat + ((int64_t)b * P + p) * D + d0 + dd;
+        df[0] += al[p] * dax; df[1] += al[p] * day;
+      }
+    }
+    if (act) {
+      const float dcx = dctx[(int64_t)b * ldc + d0 + dd], dcy = dctx[(int64_t)b * ldc + d0 + dd + 1];
+      dgate_pre[(int64_t)b * D + d0 + dd] = dcx * sx * gx * (1.f - gx);
+      dgate_pre[(int64_t)b * D + d0 + dd + 1] = dcy * sy * gy * (1.f - gy);
+    }
+  }
+  __syncthreads();
+  // exchange the partial d alpha vectors: slot r of every CTA <- this CTA's partial
+  for (int i = tid; i < CL * P; i += NT) {
+    const int q = i / P, p = i - q * P;
+    cluster.map_shared_rank(slots, q)[r * P + p] = dal[p];
+  }
+  cluster.sync();
+  for (int p = tid; p < P; p += NT) {
+    float s = dalpha_extra ? dalpha_extra[(int64_t)b * ld_da + p] : 0.f;
+#pragma unroll
+    for (int q = 0; q < CL; ++q) s += slots[q * P + p];
+    dal[p] = s;
+  }
+  __syncthreads();
+  // softmax backward: de_p = alpha_p (dalpha_p - sum_q alpha_q dalpha_q)
+  float dot = 0.f;
+  for (int p = tid; p < P; p += NT) dot += al[p] * dal[p];
+  dot = block_sum(dot, red);
+  for (int p = tid; p < P; p += NT) dal[p] = al[p] * (dal[p] - dot);
+  for (int a = tid; a < 2 * (NT / 32) * A; a += NT) part[a] = 0.f;
+  __syncthreads();
+  // pass C (own pixels): through relu / full_att
+  float* p_att2 = part + warp * A;
+  float* p_w = part + (NT / 32) * A + warp * A;
+  const float* a1b = att1 + (int64_t)b * P * A;
+  float* d1b = datt1 + (int64_t)b * P * A;
+  for (int p = r + CL * warp; p < P; p += CL * (NT / 32)) {
+    const float de = dal[p];
+    for (int a = lane; a < A; a += 32) {
+      const float v = a1b[(int64_t)p * A + a] + att2s[a];
+      const float dpre = v > 0.f ? de * ws[a] : 0.f;
+      d1b[(int64_t)p * A + a] += dpre;
+      p_att2[a] += dpre;
+      p_w[a] += de * fmaxf(v, 0.f);
+    }
+  }
+  __syncthreads();
+  for (int a = tid; a < A; a += NT) {
+    float s2 = 0.f, sw = 0.f;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) { s2 += part[w * A + a]; sw += part[(NT / 32) * A + w * A + a]; }
+    atomicAdd(datt2 + (int64_t)b * A + a, s2);      // datt2 rows are zeroed by the host wrapper
+    atomicAdd(dwfull + a, sw);
+  }
+  cluster.sync();     // keep every CTA's shared memory alive until all remote accesses are done
+}
+
 }  // namespace
 
 extern "C" {
@@ -168,6 +339,11 @@ int32_t sn_att_step_fwd(const float* att1, const float* att2, const float* feat,
   if (nb == 0) return 0;
   size_t smem = (size_t)(2 * A + P) * sizeof(float);
   SN_REQUIRE(smem <= 48 * 1024, "sn_att_step_fwd: A=%lld P=%lld exceed shared memory", (long long)A, (long long)P);
+  if (D % (2 * CL) == 0 && (ldc % 2) == 0 && (((uintptr_t)feat | (uintptr_t)gate_pre) & 7) == 0) {
+    att_step_fwd_cl_kernel<<<(unsigned)(nb * CL), NT, smem, (cudaStream_t)stream>>>(
+        att1, att2, feat, wfull, bfull, gate_pre, (int)P, (int)A, (int)D, alpha, ld_alpha, ctx, ldc);
+    return sn::check_launch("sn_att_step_fwd(cluster)");
+  }
   att_step_fwd_kernel<<<(unsigned)nb, NT, smem, (cudaStream_t)stream>>>(att1, att2, feat, wfull, bfull, gate_pre, (int)P,
                                                                        (int)A, (int)D, alpha, ld_alpha, ctx, ldc);
   return sn::check_launch("sn_att_step_fwd");
@@ -179,6 +355,18 @@ int32_t sn_att_step_bwd(const float* att1, const float* att2, const float* feat,
                         float* datt2, float* dgate_pre, float* datt1, float* dwfull, float* dfeat, void* stream) {
   SN_REQUIRE(nb >= 0 && P > 0 && A > 0 && D > 0, "sn_att_step_bwd: bad dims");
   if (nb == 0) return 0;
+  if (D % (2 * CL) == 0 && (((uintptr_t)feat | (uintptr_t)gate_pre) & 7) == 0) {
+    size_t smem_cl = (size_t)(2 * A + 2 * P + CL * P + 2 * (NT / 32) * A) * sizeof(float);
+    if (smem_cl <= 200 * 1024) {
+      if (smem_cl > 48 * 1024)
+        SN_CUDA(cudaFuncSetAttribute(att_step_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      SN_CUDA(cudaMemsetAsync(datt2, 0, sizeof(float) * (size_t)nb * (size_t)A, (cudaStream_t)stream));
+      att_step_bwd_cl_kernel<<<(unsigned)(nb * CL), NT, smem_cl, (cudaStream_t)stream>>>(
+          att1, att2, feat, wfull, gate_pre, alpha, ld_alpha, dctx, ldc, dalpha_extra, ld_da, (int)P, (int)A, (int)D,
+          datt2, dgate_pre, datt1, dwfull, dfeat);
+      return sn::check_launch("sn_att_step_bwd(cluster)");
+    }
+  }
   size_t smem = (size_t)(2 * A + 2 * P + D + 2 * (NT / 32) * A) * sizeof(float);
   SN_REQUIRE(smem <= 200 * 1024, "sn_att_step_bwd: dims exceed shared memory");
   if (smem > 48 * 1024) {
