@@ -234,7 +234,7 @@ def run_gpu(args):
     if not args.no_graph:
         # the whole step (fwd + loss + bwd [+ all-reduce] + clamp/Adam) captured once, replayed per step
         ops.LAUNCHES[0] = 0
-        graphed = sn.GraphedTrainStep(trainer, cap_d, lens, feat_d, warmup=3, **step_kw)
+        graphed = sn.GraphedTrainStep(trainer, cap_d, lens, feat_d, warmup=3, force_segmented=args.segmented, **step_kw)
         launches_per_step = ops.LAUNCHES[0] // 4          # 3 warm-up runs + 1 capture run
 
     def step_resident():
@@ -442,6 +442,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--workload", default="factored", choices=["factored", "att", "nic"])
+    ap.add_argument("--segmented", action="store_true", help="force the 3-graph (data-parallel) replay form on one GPU")
     args = ap.parse_args()
     global WORKLOAD
     WORKLOAD = args.workload

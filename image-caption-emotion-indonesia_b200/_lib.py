@@ -37,6 +37,8 @@ SIGNATURES = {
     "sn_reduce_sum": (_I32, [_P, _I64, _F, _P, _I32, _P]),
     "sn_adam_clamp": (_I32, [_P, _P, _P, _P, _I32, _P, _P, _P, _F, _F, _F, _F, _P]),
     "sn_adam_clamp_dev": (_I32, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P]),
+    "sn_enable_peer_access": (_I32, [_I32]),
+    "sn_dp_adam_fused": (_I32, [_I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P]),
     "sn_att_step_fwd": (_I32, [_P, _P, _P, _P, _F, _P, _I64, _I64, _I64, _I64, _P, _I64, _P, _I64, _P]),
     "sn_att_step_bwd": (_I32, [_P, _P, _P, _P, _F, _P, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "sn_mean_pixels": (_I32, [_P, _I64, _I64, _I64, _P, _P]),

@@ -256,6 +256,107 @@ __global__ void __launch_bounds__(256) adam_clamp_kernel(float* __restrict__ p, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Data-parallel exchange fused with the optimizer (K9+K7): reduce-scatter of the gradients over NVLink peer
+// memory -> clamp + Adam on this rank's shard -> all-gather of the updated parameters by peer stores, in ONE
+// kernel and with no NCCL call.  Every rank runs the same kernel on its own GPU; chunk c (4096 elements of the
+// concatenated active ranges) belongs to rank c % world.  Cross-GPU ordering uses two epoch flags per peer in
+// a small "pad" that lives in every rank's memory (arrive: my gradients are final; done: I have read every
+// gradient I need and my parameter stores have landed).
+// ------------------------------------------------------------------------------------------------------
+struct DpPeers {
+  float* grad[8];
+  float* param[8];
+  int* pad[8];
+  int world, rank;
+};
+constexpr int PAD_ARRIVE = 0, PAD_DONE = 8, PAD_COUNTER = 16, PAD_EPOCH = 17;
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) dp_adam_fused_kernel(DpPeers P, AdamRanges R, const float* __restrict__ coef,
+                                                            float* __restrict__ m, float* __restrict__ v, float beta1,
+                                                            float beta2, float eps, float clip) {
+  __shared__ int s_epoch, s_last;
+  int* mypad = P.pad[P.rank];
+  if (threadIdx.x == 0) s_epoch = mypad[PAD_EPOCH] + 1;
+  __syncthreads();
+  const int e = s_epoch;
+  // 1. my gradients are final (stream order): tell every peer; 2. wait until every peer said the same
+  if (blockIdx.x == 0 && threadIdx.x < P.world) st_release_sys(P.pad[threadIdx.x] + PAD_ARRIVE + P.rank, e);
+  if (threadIdx.x < P.world) { while (ld_acquire_sys(mypad + PAD_ARRIVE + threadIdx.x) < e) { } }
+  __syncthreads();
+  // 3. my chunks: reduce over the peers (fixed rank order), clamp, Adam, store the new parameters everywhere
+  const int64_t total_chunks = R.chunk_start[R.n];
+  for (int64_t ch = P.rank + (int64_t)P.world * blockIdx.x; ch < total_chunks; ch += (int64_t)P.world * gridDim.x) {
+    int r = 0;
+    while (ch >= R.chunk_start[r + 1]) ++r;
+    const int64_t base = R.off[r] + (ch - R.chunk_start[r]) * ADAM_CHUNK;
+    const int64_t end = R.off[r] + R.len[r];
+    const int64_t lim = base + ADAM_CHUNK < end ? base + ADAM_CHUNK : end;
+    const float ss = coef[2 * r], bc = coef[2 * r + 1];
+    if ((base & 3) == 0 && lim - base == ADAM_CHUNK) {
+#pragma unroll
+      for (int it = 0; it < ADAM_CHUNK / (256 * 4); ++it) {
+        const int64_t i = base + (int64_t)(it * 256 + threadIdx.x) * 4;
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < P.world; ++q) {
+          const float4 t = __ldcg(reinterpret_cast<const float4*>(P.grad[q] + i));
+          g4.x += t.x; g4.y += t.y; g4.z += t.z; g4.w += t.w;
+        }
+        float4 m4 = *reinterpret_cast<const float4*>(m + i);
+        float4 v4 = *reinterpret_cast<const float4*>(v + i);
+        float4 p4 = *reinterpret_cast<const float4*>(P.param[P.rank] + i);
+        float* gp = &g4.x; float* mp = &m4.x; float* vp = &v4.x; float* pp = &p4.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float gi = gp[k];
+          if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+          const float mi = mp[k] + (1.f - beta1) * (gi - mp[k]);
+          const float vi = vp[k] * beta2 + (1.f - beta2) * gi * gi;
+          pp[k] = pp[k] - ss * (mi / (sqrtf(vi) / bc + eps));
+          mp[k] = mi; vp[k] = vi;
+        }
+        *reinterpret_cast<float4*>(m + i) = m4;
+        *reinterpret_cast<float4*>(v + i) = v4;
+        for (int q = 0; q < P.world; ++q) *reinterpret_cast<float4*>(P.param[q] + i) = p4;
+      }
+      continue;
+    }
+    for (int64_t i = base + threadIdx.x; i < lim; i += 256) {
+      float gi = 0.f;
+      for (int q = 0; q < P.world; ++q) gi += __ldcg(P.grad[q] + i);
+      if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+      const float mi = m[i] + (1.f - beta1) * (gi - m[i]);
+      const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;
+      const float pn = P.param[P.rank][i] - ss * (mi / (sqrtf(vi) / bc + eps));
+      m[i] = mi; v[i] = vi;
+      for (int q = 0; q < P.world; ++q) P.param[q][i] = pn;
+    }
+  }
+  // 4. all my reads are done and my stores are on their way: fence, count blocks, last block runs the exit barrier
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(mypad + PAD_COUNTER, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    if (threadIdx.x < P.world) {
+      st_release_sys(P.pad[threadIdx.x] + PAD_DONE + P.rank, e);
+      while (ld_acquire_sys(mypad + PAD_DONE + threadIdx.x) < e) { }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { mypad[PAD_COUNTER] = 0; mypad[PAD_EPOCH] = e; }
+  }
+}
+
 __global__ void mean_pixels_kernel(const float* __restrict__ feat, int64_t P, int64_t D, float* __restrict__ out) {
   int64_t b = blockIdx.y;
   int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -384,6 +485,53 @@ int32_t sn_adam_clamp_dev(float* p, float* g, float* m, float* v, int32_t n_rang
   unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
   adam_clamp_kernel<<<grid, 256, 0, st>>>(p, g, m, v, R, coef_ws, beta1, beta2, eps, clip);
   return sn::check_launch("sn_adam_clamp_dev");
+}
+
+int32_t sn_enable_peer_access(int32_t peer_device) {
+  int cur = 0;
+  SN_CUDA(cudaGetDevice(&cur));
+  if (peer_device == cur) return 0;
+  int can = 0;
+  SN_CUDA(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+  SN_REQUIRE(can, "sn_enable_peer_access: device %d cannot access peer %d", cur, peer_device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) return sn::fail((int32_t)e, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+  return 0;
+}
+
+int32_t sn_dp_adam_fused(int32_t world, int32_t rank, void* const* grad_ptrs, void* const* param_ptrs,
+                         void* const* pad_ptrs, float* m, float* v, int32_t n_ranges, const int64_t* ranges,
+                         const int32_t* step_idx, int32_t* steps_dev, const float* lr_dev, float* coef_ws, float beta1,
+                         float beta2, float eps, float clip, void* stream) {
+  SN_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "sn_dp_adam_fused: bad world/rank %d/%d", world, rank);
+  SN_REQUIRE(n_ranges >= 0 && n_ranges <= AdamRanges::MAX, "sn_dp_adam_fused: at most %d ranges per call", AdamRanges::MAX);
+  SN_REQUIRE(grad_ptrs && param_ptrs && pad_ptrs && steps_dev && lr_dev && coef_ws && m && v, "sn_dp_adam_fused: null argument");
+  DpPeers P;
+  P.world = world; P.rank = rank;
+  for (int q = 0; q < 8; ++q) {
+    P.grad[q] = q < world ? (float*)grad_ptrs[q] : nullptr;
+    P.param[q] = q < world ? (float*)param_ptrs[q] : nullptr;
+    P.pad[q] = q < world ? (int*)pad_ptrs[q] : nullptr;
+    SN_REQUIRE(q >= world || (P.grad[q] && P.param[q] && P.pad[q]), "sn_dp_adam_fused: null peer pointer %d", q);
+  }
+  AdamRanges R;
+  R.n = n_ranges;
+  R.chunk_start[0] = 0;
+  for (int i = 0; i < n_ranges; ++i) {
+    R.off[i] = ranges[2 * i]; R.len[i] = ranges[2 * i + 1]; R.step_idx[i] = step_idx[i];
+    R.step_size[i] = 0.f; R.bc2_sqrt[i] = 1.f;
+    SN_REQUIRE(R.off[i] >= 0 && R.len[i] >= 0, "sn_dp_adam_fused: bad range %d", i);
+    R.chunk_start[i + 1] = R.chunk_start[i] + (R.len[i] + ADAM_CHUNK - 1) / ADAM_CHUNK;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_ranges > 0) adam_prepare_kernel<<<1, 64, 0, st>>>(R, steps_dev, lr_dev, coef_ws, beta1, beta2);
+  // every rank launches the same grid even when it owns no chunk: the kernel is also the cross-GPU barrier
+  int64_t mine = (R.chunk_start[R.n] + world - 1) / world;
+  int64_t cap = (int64_t)sn::dev_info().sm_count * 2;
+  unsigned grid = (unsigned)(mine < 1 ? 1 : (mine < cap ? mine : cap));
+  dp_adam_fused_kernel<<<grid, 256, 0, st>>>(P, R, coef_ws, m, v, beta1, beta2, eps, clip);
+  return sn::check_launch("sn_dp_adam_fused");
 }
 
 int32_t sn_mean_pixels(const float* feat, int64_t B, int64_t P, int64_t D, float* out, void* stream) {

@@ -46,14 +46,60 @@ class GradSync:
         self.pending = []
 
 
-class DataParallelTrainer:
-    """forward -> loss -> backward -> bucketed gradient all-reduce -> fused clamp+Adam, one rank per GPU."""
+class PeerExchange:
+    """NVLink peer-memory view of every rank's parameter arena, gradient arena and signal pad (CUDA IPC handles
+    exchanged once through torch.distributed; torch.multiprocessing's CUDA tensor sharing does the mapping).
+    Feeds sn_dp_adam_fused: ONE kernel per step does reduce-scatter + clamp/Adam + all-gather over NVLink."""
 
-    def __init__(self, decoder, optimizer, group=None):
+    def __init__(self, arena, group=None):
+        from torch.multiprocessing.reductions import reduce_tensor
+        from . import ops
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("peer exchange supports one NVSwitch box (<= 8 ranks)")
+        dev = arena.flat.device
+        self.pad = torch.zeros(32, dtype=torch.int32, device=dev)
+        mine = [reduce_tensor(t) for t in (arena.flat, arena.gflat, self.pad)]
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (self.rank, dev.index, mine), group=group)
+        self.keep = []                      # peer tensors must stay alive as long as their pointers are used
+        self.param_ptrs, self.grad_ptrs, self.pad_ptrs = [0] * self.world, [0] * self.world, [0] * self.world
+        for r, dev_index, objs in gathered:
+            if r == self.rank:
+                ts = (arena.flat, arena.gflat, self.pad)
+            else:
+                ops.enable_peer_access(dev_index)
+                ts = tuple(fn(*args) for fn, args in objs)
+                self.keep.append(ts)
+            self.param_ptrs[r], self.grad_ptrs[r], self.pad_ptrs[r] = (t.data_ptr() for t in ts)
+        self.arena_version = arena.version
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+
+class DataParallelTrainer:
+    """forward -> loss -> backward -> gradient exchange -> fused clamp+Adam, one rank per GPU.
+
+    comm="peer" (default when world > 1 on CUDA): the exchange and the optimizer are ONE kernel over NVLink peer
+    memory (sn_dp_adam_fused: reduce-scatter by peer loads, Adam on the owned shard, all-gather by peer stores).
+    comm="nccl": bucketed NCCL SUM all-reduce (bucket 0 overlapped with the recurrence backward) + local Adam."""
+
+    def __init__(self, decoder, optimizer, group=None, comm=None):
         self.decoder, self.optimizer = decoder, optimizer
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.sync = GradSync(group)
+        if comm is None:
+            comm = "peer" if (self.world > 1 and dist.get_backend(group) == "nccl") else "nccl"
+        self.comm = comm
+        self.peers = None
+
+    def _peers(self):
+        a = self.decoder.arena()
+        if self.peers is None or self.peers.arena_version != a.version:
+            self.peers = PeerExchange(a, self.group)
+        return self.peers
 
     def forward_backward(self, captions, lengths, features, n_global=None, b_global=None, grad_hook=None, **kw):
         """zero_grad + forward + loss + backward with gradients scaled by 1/N_global; ``grad_hook(names)`` is
@@ -72,6 +118,11 @@ class DataParallelTrainer:
 
     def step(self, captions, lengths, features, n_global=None, b_global=None, **kw):
         a = self.decoder.arena()
+        if self.world > 1 and self.comm == "peer":
+            peers = self._peers()
+            loss, stats = self.forward_backward(captions, lengths, features, n_global=n_global, b_global=b_global, **kw)
+            self.optimizer.step_peer(peers)
+            return loss, stats
         hook = None
         if self.world > 1:
             def hook(names):

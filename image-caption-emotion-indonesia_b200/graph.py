@@ -37,7 +37,7 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.segments = []          # [(graph, ranges to all-reduce after it | None)]
-        if trainer.world == 1 and not force_segmented:
+        if (trainer.world == 1 or getattr(trainer, 'comm', 'nccl') == 'peer') and not force_segmented:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self.loss, self.stats = self.trainer.step(self.captions, self.lengths, self.features, **self.kw)

@@ -243,3 +243,27 @@ def adam_clamp_dev(p, g, m, v, ranges, step_idx, steps_dev, lr_dev, coef_ws, bet
                                       _ptr(steps_dev), _ptr(lr_dev),
                                       ctypes.c_void_p(coef_ws.data_ptr() + 4 * 2 * i0), beta1, beta2, eps, clip,
                                       _stream()), "sn_adam_clamp_dev")
+
+
+def enable_peer_access(peer_device):
+    _check(lib().sn_enable_peer_access(int(peer_device)), "sn_enable_peer_access")
+
+
+def dp_adam_fused(world, rank, grad_ptrs, param_ptrs, pad_ptrs, m, v, ranges, step_idx, steps_dev, lr_dev, coef_ws,
+                  beta1, beta2, eps, clip):
+    """Fused reduce-scatter + clamp/Adam + all-gather over peer memory (sn_dp_adam_fused)."""
+    n = len(ranges)
+    if n > 48:
+        raise _lib.SnError("dp_adam_fused: more than 48 ranges")
+    G = (ctypes.c_void_p * world)(*grad_ptrs)
+    Pp = (ctypes.c_void_p * world)(*param_ptrs)
+    D = (ctypes.c_void_p * world)(*pad_ptrs)
+    R = (ctypes.c_int64 * (2 * max(n, 1)))()
+    S = (ctypes.c_int32 * max(n, 1))()
+    for i in range(n):
+        R[2 * i], R[2 * i + 1] = ranges[i]
+        S[i] = step_idx[i]
+    check(lib().sn_dp_adam_fused(world, rank, ctypes.cast(G, ctypes.c_void_p), ctypes.cast(Pp, ctypes.c_void_p),
+                                 ctypes.cast(D, ctypes.c_void_p), _ptr(_req(m)), _ptr(_req(v)), n,
+                                 ctypes.cast(R, ctypes.c_void_p), ctypes.cast(S, ctypes.c_void_p), _ptr(steps_dev),
+                                 _ptr(lr_dev), _ptr(coef_ws), beta1, beta2, eps, clip, _stream()), "sn_dp_adam_fused")

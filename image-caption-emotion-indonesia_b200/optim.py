@@ -72,6 +72,21 @@ class FusedClampAdam:
             if p.grad is not None:
                 self._step_tensor(p, ("extra", i))
 
+    @torch.no_grad()
+    def step_peer(self, peers):
+        """Data-parallel step: gradient reduce-scatter + clamp/Adam on the owned shard + parameter all-gather in
+        one kernel over NVLink peer memory.  Every rank must call it with the same set of gradients."""
+        a = self._state()
+        self._sync_lr()
+        items, foreign = a.grad_ranges()
+        if foreign or any(p.grad is not None for p in self.extra):
+            raise RuntimeError("peer-fused step needs every gradient in the arena")
+        ranges = [(off, n) for off, n, _ in items]
+        idx = [self.index[name] for _, _, name in items]
+        ops.dp_adam_fused(peers.world, peers.rank, peers.grad_ptrs, peers.param_ptrs, peers.pad_ptrs, self.m, self.v,
+                          ranges, idx, self.steps_dev, self.lr_dev, self.coef_ws, self.betas[0], self.betas[1],
+                          self.eps, self.grad_clip)
+
     def _step_tensor(self, p, key):
         st = self.extra_state.get(key)
         if st is None:

@@ -187,6 +187,23 @@ int32_t sn_adam_clamp_dev(float* p, float* g, float* m, float* v, int32_t n_rang
                           const float* lr_dev, float* coef_ws, float beta1, float beta2, float eps,
                           float clip, void* stream);
 
+/* ---- K9: data-parallel exchange fused with the optimizer, over NVLink peer memory (no NCCL) ------------
+ * The reference has no distributed code; this replaces what `ncclAllReduce` + K7 would do.  Every rank (one
+ * process per GPU) calls it with the SAME ranges after its backward: reduce-scatter of the gradient ranges by
+ * peer loads (chunk c of 4096 elements is owned by rank c % world, summed in rank order 0..world-1), clamp +
+ * Adam on the owned chunks (moments only for owned chunks), all-gather of the new parameters by peer stores.
+ *   grad_ptrs/param_ptrs/pad_ptrs  HOST arrays of `world` DEVICE pointers: every rank's flat gradient arena,
+ *                flat parameter arena and 32-int signal pad (zero-initialised once), mapped into this process
+ *                (CUDA IPC) with peer access enabled (sn_enable_peer_access)
+ * The kernel is also the cross-GPU barrier (arrive / done epoch flags in the pads, epoch kept in device memory),
+ * so it is CUDA-graph replayable and must be called by all ranks the same number of times. */
+int32_t sn_enable_peer_access(int32_t peer_device);
+int32_t sn_dp_adam_fused(int32_t world, int32_t rank, void* const* grad_ptrs, void* const* param_ptrs,
+                         void* const* pad_ptrs, float* m, float* v, int32_t n_ranges,
+                         const int64_t* ranges, const int32_t* step_idx, int32_t* steps_dev,
+                         const float* lr_dev, float* coef_ws, float beta1, float beta2, float eps,
+                         float clip, void* stream);
+
 /* ---- K4: soft attention step (scores -> softmax over pixels -> context -> f_beta gate) ----------
  * replaces Attention.forward after the hoisted encoder_att GEMM (model_att.py:61-70) and the gate
  * multiply (model_att.py:283-284) for one time step over nb samples.

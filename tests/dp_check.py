@@ -32,8 +32,17 @@ def main():
     # data parallel
     idx, my_lens = sn.shard_lengths(lens, world, rank)
     opt = sn.FusedClampAdam(dec, lr=5e-4)
-    tr = sn.DataParallelTrainer(dec, opt)
+    comm = os.environ.get("SN_DP_COMM", "peer")
+    tr = sn.DataParallelTrainer(dec, opt, comm=comm)
+    g_local = None
     loss, _ = tr.step(cap[idx].to(dev), my_lens, feats[idx].to(dev), n_global=n_global, mode="sad")
+    if comm == "peer":
+        # the fused kernel leaves the LOCAL gradients in .grad: reduce them here only to compare
+        for n, p in dec.named_parameters():
+            if p.grad is not None:
+                g = p.grad.clone()
+                dist.all_reduce(g)
+                p.grad = g
     tot = loss.clone()
     dist.all_reduce(tot)
     torch.cuda.synchronize()
@@ -51,7 +60,7 @@ def main():
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("DP_CHECK_OK" if flag.item() == 1.0 else "DP_CHECK_FAIL", "worst grad rel err %.2e" % worst,
+        print("DP_CHECK_OK" if flag.item() == 1.0 else "DP_CHECK_FAIL", comm, "worst grad rel err %.2e" % worst,
               "loss %.6f vs %.6f" % (tot.item(), loss_ref.item()), flush=True)
     dist.destroy_process_group()
 

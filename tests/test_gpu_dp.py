@@ -10,10 +10,13 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def test_dp2_equals_single_gpu():
+@pytest.mark.parametrize("comm", ["peer", "nccl"])
+def test_dp2_equals_single_gpu(comm):
+    """2-GPU data-parallel step (NVLink peer-fused exchange+Adam, or NCCL all-reduce + local Adam) == the
+    single-GPU step on the same global batch: loss, reduced gradients and updated parameters <= 1e-5."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29611", os.path.join(HERE, "dp_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "127.0.0.1", "--master-port", "29611" if comm == "peer" else "29612", os.path.join(HERE, "dp_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, SN_DP_COMM=comm))
     assert "DP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
