@@ -47,12 +47,14 @@ class GradSync:
 
 
 class PeerExchange:
-    """NVLink peer-memory view of every rank's parameter arena, gradient arena and signal pad (CUDA IPC handles
-    exchanged once through torch.distributed; torch.multiprocessing's CUDA tensor sharing does the mapping).
-    Feeds sn_dp_adam_fused: ONE kernel per step does reduce-scatter + clamp/Adam + all-gather over NVLink."""
+    """NVLink peer-memory view of every rank's parameter arena, gradient arena and signal pad: each rank exports
+    CUDA IPC handles of the three buffers (exchanged once through torch.distributed), and opens its peers' with
+    its own device current, which yields peer mappings its kernels can load from / store to over NVLink.
+    Feeds sn_dp_adam_fused: ONE kernel per step does reduce-scatter + clamp/Adam + all-gather, no NCCL."""
+
+    _opened = {}        # handle bytes -> mapped base address (an allocation can be opened once per process)
 
     def __init__(self, arena, group=None):
-        from torch.multiprocessing.reductions import reduce_tensor
         from . import ops
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -60,20 +62,26 @@ class PeerExchange:
             raise RuntimeError("peer exchange supports one NVSwitch box (<= 8 ranks)")
         dev = arena.flat.device
         self.pad = torch.zeros(32, dtype=torch.int32, device=dev)
-        mine = [reduce_tensor(t) for t in (arena.flat, arena.gflat, self.pad)]
+        torch.cuda.synchronize()
+        mine = [ops.ipc_export(t) for t in (arena.flat, arena.gflat, self.pad)]
         gathered = [None] * self.world
         dist.all_gather_object(gathered, (self.rank, dev.index, mine), group=group)
-        self.keep = []                      # peer tensors must stay alive as long as their pointers are used
         self.param_ptrs, self.grad_ptrs, self.pad_ptrs = [0] * self.world, [0] * self.world, [0] * self.world
-        for r, dev_index, objs in gathered:
+        for r, dev_index, exports in gathered:
             if r == self.rank:
-                ts = (arena.flat, arena.gflat, self.pad)
+                ptrs = [t.data_ptr() for t in (arena.flat, arena.gflat, self.pad)]
             else:
                 ops.enable_peer_access(dev_index)
-                ts = tuple(fn(*args) for fn, args in objs)
-                self.keep.append(ts)
-            self.param_ptrs[r], self.grad_ptrs[r], self.pad_ptrs[r] = (t.data_ptr() for t in ts)
+                ptrs = []
+                for handle, offset in exports:
+                    base = PeerExchange._opened.get(handle)
+                    if base is None:
+                        base = ops.ipc_open(handle)
+                        PeerExchange._opened[handle] = base
+                    ptrs.append(base + offset)
+            self.param_ptrs[r], self.grad_ptrs[r], self.pad_ptrs[r] = ptrs
         self.arena_version = arena.version
+        self.keep = (arena.flat, arena.gflat, self.pad)      # exported memory must stay allocated
         torch.cuda.synchronize()
         dist.barrier(group=group)
 

@@ -252,9 +252,12 @@ def enable_peer_access(peer_device):
 def dp_adam_fused(world, rank, grad_ptrs, param_ptrs, pad_ptrs, m, v, ranges, step_idx, steps_dev, lr_dev, coef_ws,
                   beta1, beta2, eps, clip):
     """Fused reduce-scatter + clamp/Adam + all-gather over peer memory (sn_dp_adam_fused)."""
+    if len(ranges) > 48:            # each call is also a cross-GPU barrier; batches of <= 48 ranges
+        for i0 in range(0, len(ranges), 48):
+            dp_adam_fused(world, rank, grad_ptrs, param_ptrs, pad_ptrs, m, v, ranges[i0:i0 + 48],
+                          step_idx[i0:i0 + 48], steps_dev, lr_dev, coef_ws, beta1, beta2, eps, clip)
+        return
     n = len(ranges)
-    if n > 48:
-        raise _lib.SnError("dp_adam_fused: more than 48 ranges")
     G = (ctypes.c_void_p * world)(*grad_ptrs)
     Pp = (ctypes.c_void_p * world)(*param_ptrs)
     D = (ctypes.c_void_p * world)(*pad_ptrs)
@@ -267,3 +270,20 @@ def dp_adam_fused(world, rank, grad_ptrs, param_ptrs, pad_ptrs, m, v, ranges, st
                                  ctypes.cast(D, ctypes.c_void_p), _ptr(_req(m)), _ptr(_req(v)), n,
                                  ctypes.cast(R, ctypes.c_void_p), ctypes.cast(S, ctypes.c_void_p), _ptr(steps_dev),
                                  _ptr(lr_dev), _ptr(coef_ws), beta1, beta2, eps, clip, _stream()), "sn_dp_adam_fused")
+
+
+def ipc_export(t):
+    """(handle bytes, byte offset) describing tensor ``t``'s device memory for another process."""
+    h = (ctypes.c_uint8 * 64)()
+    off = ctypes.c_int64(0)
+    _check(lib().sn_ipc_export(ctypes.c_void_p(t.data_ptr()), ctypes.cast(h, ctypes.c_void_p), ctypes.byref(off)),
+           "sn_ipc_export")
+    return bytes(h), off.value
+
+
+def ipc_open(handle):
+    """Map an exported allocation into this process (peer mapping of the current device); returns its base."""
+    h = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
+    base = ctypes.c_void_p(0)
+    _check(lib().sn_ipc_open(ctypes.cast(h, ctypes.c_void_p), ctypes.byref(base)), "sn_ipc_open")
+    return base.value

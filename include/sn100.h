@@ -198,6 +198,11 @@ int32_t sn_adam_clamp_dev(float* p, float* g, float* m, float* v, int32_t n_rang
  * The kernel is also the cross-GPU barrier (arrive / done epoch flags in the pads, epoch kept in device memory),
  * so it is CUDA-graph replayable and must be called by all ranks the same number of times. */
 int32_t sn_enable_peer_access(int32_t peer_device);
+/* CUDA IPC plumbing for the above: export = (64-byte handle of the cudaMalloc allocation containing ptr, byte
+ * offset of ptr in it); open maps that allocation into this process as a PEER mapping of the current device. */
+int32_t sn_ipc_export(const void* ptr, uint8_t* handle64, int64_t* offset);
+int32_t sn_ipc_open(const uint8_t* handle64, void** base_out);
+int32_t sn_ipc_close(void* base);
 int32_t sn_dp_adam_fused(int32_t world, int32_t rank, void* const* grad_ptrs, void* const* param_ptrs,
                          void* const* pad_ptrs, float* m, float* v, int32_t n_ranges,
                          const int64_t* ranges, const int32_t* step_idx, int32_t* steps_dev,

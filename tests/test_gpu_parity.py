@@ -361,3 +361,35 @@ def test_bf16_mode_attention_within_2e2(which, dims):
     tol = lambda n: 6e-2 if H < 128 else (3e-2 if n.startswith("attention") else 2e-2)
     bad = {n: e for n, e in errs.items() if e >= tol(n)}
     assert not bad, bad
+
+
+def test_peer_fused_adam_degenerate_world1():
+    """sn_dp_adam_fused with world = 1 (its own arenas as the only 'peer') == the local fused clamp+Adam."""
+    import icei_b200 as sn
+    from oracle import port
+    V, E, H, F, B, T = 300, 28, 64, 72, 12, 8
+    torch.manual_seed(0)
+    make = lambda: sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0).cuda().train()
+    d1, d2 = make(), make()
+    d2.load_state_dict(d1.state_dict())
+    cap, lens, feats = port.synthetic_batch(B, T, V, E=E, ragged=True, seed=9)
+    cap, feats = cap.cuda(), feats.cuda()
+    o1, o2 = sn.FusedClampAdam(d1, lr=1e-3), sn.FusedClampAdam(d2, lr=1e-3)
+
+    class Fake:
+        pass
+    a2 = d2.arena()
+    pe = Fake()
+    pe.world, pe.rank = 1, 0
+    pe.pad = torch.zeros(32, dtype=torch.int32, device="cuda")
+    pe.param_ptrs, pe.grad_ptrs, pe.pad_ptrs = [a2.flat.data_ptr()], [a2.gflat.data_ptr()], [pe.pad.data_ptr()]
+    for _ in range(3):
+        for d in (d1, d2):
+            d.zero_grad()
+            d.forward_loss(cap, lens, feats, mode="happy")
+        o1.step()
+        o2.step_peer(pe)
+    torch.cuda.synchronize()
+    assert int(pe.pad[17]) == 3                      # epoch advanced once per call
+    for (n, p), (_, q) in zip(d1.named_parameters(), d2.named_parameters()):
+        assert rel_l2(q.detach().cpu(), p.detach().cpu()) < 1e-6, n
