@@ -281,6 +281,7 @@ __device__ __forceinline__ void st_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+template <int W>      // world size as a template parameter: the W peer loads / stores of an element are all in flight
 __global__ void __launch_bounds__(256) dp_adam_fused_kernel(DpPeers P, AdamRanges R, const float* __restrict__ coef,
                                                             float* __restrict__ m, float* __restrict__ v, float beta1,
                                                             float beta2, float eps, float clip) {
@@ -306,11 +307,12 @@ __global__ void __launch_bounds__(256) dp_adam_fused_kernel(DpPeers P, AdamRange
 #pragma unroll
       for (int it = 0; it < ADAM_CHUNK / (256 * 4); ++it) {
         const int64_t i = base + (int64_t)(it * 256 + threadIdx.x) * 4;
-        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < P.world; ++q) {
-          const float4 t = __ldcg(reinterpret_cast<const float4*>(P.grad[q] + i));
-          g4.x += t.x; g4.y += t.y; g4.z += t.z; g4.w += t.w;
-        }
+        float4 t[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) t[q] = __ldcg(reinterpret_cast<const float4*>(P.grad[q] + i));
+        float4 g4 = t[0];
+#pragma unroll
+        for (int q = 1; q < W; ++q) { g4.x += t[q].x; g4.y += t[q].y; g4.z += t[q].z; g4.w += t[q].w; }
         float4 m4 = *reinterpret_cast<const float4*>(m + i);
         float4 v4 = *reinterpret_cast<const float4*>(v + i);
         float4 p4 = *reinterpret_cast<const float4*>(P.param[P.rank] + i);
@@ -326,19 +328,22 @@ __global__ void __launch_bounds__(256) dp_adam_fused_kernel(DpPeers P, AdamRange
         }
         *reinterpret_cast<float4*>(m + i) = m4;
         *reinterpret_cast<float4*>(v + i) = v4;
-        for (int q = 0; q < P.world; ++q) *reinterpret_cast<float4*>(P.param[q] + i) = p4;
+#pragma unroll
+        for (int q = 0; q < W; ++q) *reinterpret_cast<float4*>(P.param[q] + i) = p4;
       }
       continue;
     }
     for (int64_t i = base + threadIdx.x; i < lim; i += 256) {
-      float gi = 0.f;
-      for (int q = 0; q < P.world; ++q) gi += __ldcg(P.grad[q] + i);
+      float gi = __ldcg(P.grad[0] + i);
+#pragma unroll
+      for (int q = 1; q < W; ++q) gi += __ldcg(P.grad[q] + i);
       if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
       const float mi = m[i] + (1.f - beta1) * (gi - m[i]);
       const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;
       const float pn = P.param[P.rank][i] - ss * (mi / (sqrtf(vi) / bc + eps));
       m[i] = mi; v[i] = vi;
-      for (int q = 0; q < P.world; ++q) P.param[q][i] = pn;
+#pragma unroll
+      for (int q = 0; q < W; ++q) P.param[q][i] = pn;
     }
   }
   // 4. all my reads are done and my stores are on their way: fence, count blocks, last block runs the exit barrier
@@ -528,9 +533,20 @@ int32_t sn_dp_adam_fused(int32_t world, int32_t rank, void* const* grad_ptrs, vo
   if (n_ranges > 0) adam_prepare_kernel<<<1, 64, 0, st>>>(R, steps_dev, lr_dev, coef_ws, beta1, beta2);
   // every rank launches the same grid even when it owns no chunk: the kernel is also the cross-GPU barrier
   int64_t mine = (R.chunk_start[R.n] + world - 1) / world;
-  int64_t cap = (int64_t)sn::dev_info().sm_count * 2;
+  int64_t cap = (int64_t)sn::dev_info().sm_count * 8;      // one owned chunk per CTA whenever they all fit
   unsigned grid = (unsigned)(mine < 1 ? 1 : (mine < cap ? mine : cap));
-  dp_adam_fused_kernel<<<grid, 256, 0, st>>>(P, R, coef_ws, m, v, beta1, beta2, eps, clip);
+#define SN_DP_LAUNCH(WW) dp_adam_fused_kernel<WW><<<grid, 256, 0, st>>>(P, R, coef_ws, m, v, beta1, beta2, eps, clip)
+  switch (world) {
+    case 1: SN_DP_LAUNCH(1); break;
+    case 2: SN_DP_LAUNCH(2); break;
+    case 3: SN_DP_LAUNCH(3); break;
+    case 4: SN_DP_LAUNCH(4); break;
+    case 5: SN_DP_LAUNCH(5); break;
+    case 6: SN_DP_LAUNCH(6); break;
+    case 7: SN_DP_LAUNCH(7); break;
+    default: SN_DP_LAUNCH(8); break;
+  }
+#undef SN_DP_LAUNCH
   return sn::check_launch("sn_dp_adam_fused");
 }
 
