@@ -47,7 +47,8 @@ def main():
     out_rows = []
 
     def timed(fn, reps):
-        fn()
+        for _ in range(3):          # warm-up: the 2nd call of a decode session captures its CUDA graph
+            fn()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(reps):

@@ -6,7 +6,7 @@
 
 namespace {
 
-constexpr int NT = 256;
+constexpr int NT = 512;
 constexpr int KMAX = 8;
 
 struct BeamArgs {
@@ -18,6 +18,7 @@ struct BeamArgs {
   int* done_len; float* done_score; int* n_done;
   int* out_seq; int* out_len; int* n_unfinished;
   int n_img;
+  const int* step_dev;   // optional: step number in device memory (CUDA-graph replay), overrides `step`
 };
 
 __global__ void __launch_bounds__(NT) beam_step_kernel(BeamArgs a) {
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(NT) beam_step_kernel(BeamArgs a) {
   __shared__ float w_val[KMAX];
   __shared__ int w_idx[KMAX];
   const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (a.step_dev) a.step = *a.step_dev;
   const int k = a.k_live[img];
   const int row0 = img * a.kmax;
   if (k == 0) {
@@ -174,7 +176,8 @@ extern "C" int32_t sn_beam_step(const float* logits, int64_t ld, int64_t V, int3
                                 int32_t max_len, int32_t end_token, int32_t* k_live, float* run_score,
                                 int32_t* prev_word, int32_t* src_row, int32_t* cur_buf, int32_t* seqs,
                                 int32_t* done_seq, int32_t* done_len, float* done_score, int32_t* n_done,
-                                int32_t* out_seq, int32_t* out_len, int32_t* n_unfinished, void* stream) {
+                                int32_t* out_seq, int32_t* out_len, int32_t* n_unfinished, const int32_t* step_dev,
+                                void* stream) {
   SN_REQUIRE(kmax >= 1 && kmax <= KMAX, "sn_beam_step: beam width %d not in [1,%d]", kmax, KMAX);
   SN_REQUIRE(n_img >= 0 && V > 0 && step >= 1, "sn_beam_step: bad dims");
   SN_REQUIRE((int64_t)kmax * V < 0x7fffffff, "sn_beam_step: k*V overflows int32");
@@ -185,6 +188,7 @@ extern "C" int32_t sn_beam_step(const float* logits, int64_t ld, int64_t V, int3
   a.k_live = k_live; a.run_score = run_score; a.prev_word = prev_word; a.src_row = src_row; a.cur_buf = cur_buf;
   a.seqs = seqs; a.done_seq = done_seq; a.done_len = done_len; a.done_score = done_score; a.n_done = n_done;
   a.out_seq = out_seq; a.out_len = out_len; a.n_unfinished = n_unfinished; a.n_img = n_img;
+  a.step_dev = step_dev;
   beam_step_kernel<<<(unsigned)n_img, NT, 0, (cudaStream_t)stream>>>(a);
   return sn::check_launch("sn_beam_step");
 }

@@ -116,6 +116,61 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
   }
 }
 
+// Skinny NT GEMM for decode steps (M <= 16 rows: live beams / a single image): weight-bandwidth bound, so one
+// warp streams one weight row (coalesced, 128-bit) and dots it with all M input rows held in shared memory.
+constexpr int SK_MAXM = 16;
+
+__global__ void __launch_bounds__(256) gemm_skinny_nt_kernel(GemmArgs g) {
+  extern __shared__ __align__(16) float xs[];      // [M][Kp]
+  const int m0 = blockIdx.z * SK_MAXM;             // rows are processed 16 at a time (grid.z chunks)
+  const int M = min(SK_MAXM, (int)g.M - m0), K = (int)g.K;
+  const int Kp = (K + 3) & ~3;
+  const float* A = g.A + blockIdx.y * g.strideA + (int64_t)m0 * g.sam;
+  const float* B = g.B + blockIdx.y * g.strideB;
+  float* C = g.C + blockIdx.y * g.strideC + (int64_t)m0 * g.ldc;
+  const float* bias = g.bias ? g.bias + blockIdx.y * g.strideBias : nullptr;
+  for (int i = threadIdx.x; i < M * Kp; i += 256) {
+    int m = i / Kp, k = i - m * Kp;
+    xs[i] = k < K ? A[(int64_t)m * g.sam + k] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n = (int64_t)blockIdx.x * 8 + warp;
+  if (n >= g.N) return;
+  const float* w = B + n * g.sbn;                  // row n of B[N,K] (k contiguous)
+  float acc[SK_MAXM];
+#pragma unroll
+  for (int m = 0; m < SK_MAXM; ++m) acc[m] = 0.f;
+  const bool vec = ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
+  if (vec) {
+    for (int k = lane * 4; k < K; k += 128) {
+      float4 wv;
+      if (k + 3 < K) wv = __ldg(reinterpret_cast<const float4*>(w + k));
+      else { wv.x = w[k]; wv.y = k + 1 < K ? w[k + 1] : 0.f; wv.z = k + 2 < K ? w[k + 2] : 0.f; wv.w = 0.f; }
+#pragma unroll
+      for (int m = 0; m < SK_MAXM; ++m) {
+        if (m < M) {
+          const float4 xv = *reinterpret_cast<const float4*>(xs + m * Kp + k);
+          acc[m] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[m]))));
+        }
+      }
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(w + k);
+#pragma unroll
+      for (int m = 0; m < SK_MAXM; ++m) if (m < M) acc[m] = fmaf(wv, xs[m * Kp + k], acc[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < SK_MAXM; ++m) {
+    if (m < M) {
+      float v = sn::warp_sum(acc[m]);
+      if (lane == 0) C[(int64_t)m * g.ldc + n] = v + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+
 constexpr int CS_ROWS = 128;   // rows per CTA: enough CTAs to fill the machine even for narrow matrices
 
 __global__ void colsum_scale_kernel(float* __restrict__ out, int64_t N, float beta) {
@@ -165,6 +220,22 @@ extern "C" int32_t sn_gemm(int32_t op, int64_t M, int64_t N, int64_t K, const fl
   if (op == SN_OP_NT) { g.sam = lda; g.sak = 1; g.sbk = 1; g.sbn = ldb; }
   else if (op == SN_OP_NN) { g.sam = lda; g.sak = 1; g.sbk = ldb; g.sbn = 1; }
   else { g.sam = 1; g.sak = lda; g.sbk = ldb; g.sbn = 1; }
+  if (op == SN_OP_NT && M <= 8 * SK_MAXM && beta == 0.f) {
+    // few rows (decode steps, per-time-step Linears): weight-bandwidth bound -> skinny kernel, 16 rows per CTA.z
+    size_t smem = (size_t)(M < SK_MAXM ? M : SK_MAXM) * ((K + 3) & ~(int64_t)3) * sizeof(float);
+    if (smem <= 96 * 1024) {
+      if (smem > 48 * 1024) {
+        static thread_local bool configured = false;
+        if (!configured) {
+          SN_CUDA(cudaFuncSetAttribute(gemm_skinny_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+          configured = true;
+        }
+      }
+      dim3 sgrid((unsigned)((N + 7) / 8), (unsigned)batch, (unsigned)((M + SK_MAXM - 1) / SK_MAXM));
+      gemm_skinny_nt_kernel<<<sgrid, 256, smem, (cudaStream_t)stream>>>(g);
+      return sn::check_launch("sn_gemm(skinny)");
+    }
+  }
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch);
   gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g);
   return sn::check_launch("sn_gemm");

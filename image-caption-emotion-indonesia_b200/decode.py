@@ -78,14 +78,31 @@ class BeamState:
         self.out_seq = torch.zeros(n_img, L, **i32)
         self.out_len = torch.zeros(n_img, **i32)
         self.n_unfinished = torch.full((1,), n_img, **i32)
+        self.step_dev = torch.ones(1, **i32)
+        self.start_token = start_token
+        self._arange = torch.arange(R, **i32)
 
-    def step(self, logits, step, end_token):
+    def reset(self):
+        """Back to the state before step 1 (in place: the buffers may be baked into a CUDA graph)."""
+        self.k_live.fill_(self.kmax)
+        self.run_score.zero_()
+        self.prev_word.fill_(self.start_token)
+        self.src_row.copy_(self._arange)
+        self.cur_buf.zero_()
+        self.seqs[:, :, 0] = self.start_token
+        self.n_done.zero_()
+        self.out_len.zero_()
+        self.n_unfinished.fill_(self.n_img)
+        self.step_dev.fill_(1)
+
+    def step(self, logits, step, end_token, device_step=False):
         p = ops._ptr
         check(ops.lib().sn_beam_step(
             p(logits), logits.stride(0), logits.shape[1], self.n_img, self.kmax, step, self.max_len, end_token,
             p(self.k_live), p(self.run_score), p(self.prev_word), p(self.src_row), p(self.cur_buf), p(self.seqs),
             p(self.done_seq), p(self.done_len), p(self.done_score), p(self.n_done), p(self.out_seq),
-            p(self.out_len), p(self.n_unfinished), ops._stream()), "sn_beam_step")
+            p(self.out_len), p(self.n_unfinished), p(self.step_dev) if device_step else None, ops._stream()),
+            "sn_beam_step")
 
     def results(self):
         out = self.out_seq.cpu()
@@ -93,48 +110,117 @@ class BeamState:
         return [out[i, :int(n[i])].long().unsqueeze(0) for i in range(self.n_img)]
 
 
+class _DecodeSession:
+    """Static buffers + (lazily captured) CUDA graphs of one decode step for a fixed (decoder, n_img, k, mode,
+    start/end token).  ``sample()`` is called once per image by the reference's evaluation loops
+    (stylenet/evaluator.py:74-81): replaying the captured step removes the ~12 Python-issued launches per step
+    that otherwise make a single-image beam search launch-bound."""
+
+    def __init__(self, dec, n_img, k, mode, start_token, end_token):
+        emb = dec._emb()
+        dev = emb.weight.device
+        E, H = emb.weight.shape[1], dec.hidden_size
+        out = dec._out()
+        V = out.weight.shape[0]
+        self.dec, self.mode, self.end_token = dec, mode, end_token
+        self.st = BeamState(n_img, k, dec.max_seq_length, start_token, dev)
+        R = self.st.R
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.h, self.c = torch.zeros(R, H, **f32), torch.zeros(R, H, **f32)
+        self.h_new = torch.empty(R, H, **f32)
+        self.logits = torch.empty(R, V, **f32)
+        self.X = torch.empty(R, E, **f32)
+        self.ctx = _StepCtx()
+        self.ctx.XP = torch.empty(R, 4 * H, **f32)
+        self.ctx.w16 = {}
+        self.row_img = (torch.arange(R, device=dev, dtype=torch.int32) // k).contiguous()
+        self.row_zero = torch.zeros(R, dtype=torch.int32, device=dev)
+        self.dummy_cap = torch.zeros(1, 1, dtype=torch.int64, device=dev)
+        self.feats = torch.zeros(n_img, E, **f32)
+        self.bs1, self.off1 = _i32(dev, [R]), _i32(dev, [0])
+        self.cache = {}
+        self.graph = None          # generic step (steps >= 2)
+        self.calls = 0
+        self.arena_version = dec.arena().version
+
+    def step(self, step, feed_image, device_step):
+        dec, st = self.dec, self.st
+        emb, out = dec._emb(), dec._out()
+        R, H = st.R, dec.hidden_size
+        if feed_image and step == 1:
+            ops.gather_pack_fwd(self.dummy_cap, emb.weight, self.feats, True, self.row_img, self.row_zero, None, R,
+                                self.X, 0.0, 0)
+        else:
+            ops.gather_pack_fwd(self.dummy_cap, emb.weight, None, False, self.row_img, self.row_zero, st.prev_word, R,
+                                self.X, 0.0, 0)
+        dec._input_projection(self.ctx, self.X, self.mode, 0, R)
+        Whh, bhh = dec._recurrent_weights()
+        ops.recur_fwd(dec.cell, H, R, self.bs1, self.off1, 0, 1, self.ctx.XP, Whh, bhh, self.h, self.h_new, None, None,
+                      None, self.c)
+        _vocab_step(dec, self.h_new, self.logits, self.cache)
+        st.step(self.logits, step, self.end_token, device_step=device_step)
+        idx = st.src_row.long()
+        torch.index_select(self.h_new, 0, idx, out=self.h)
+        c_new = self.c.index_select(0, idx)
+        self.c.copy_(c_new)
+        st.step_dev.add_(1)
+
+    def capture(self):
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.step(2, False, True)            # warm-up on the capture side stream (allocator, lazy state)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            self.step(2, False, True)
+        self.graph = g
+
+
+def _session(dec, n_img, k, mode, start_token, end_token):
+    cache = dec.__dict__.setdefault("_decode_sessions", {})
+    key = (n_img, k, mode, start_token, end_token, dec.precision)
+    sess = cache.get(key)
+    if sess is None or sess.arena_version != dec.arena().version:
+        if len(cache) > 8:
+            cache.clear()
+        sess = _DecodeSession(dec, n_img, k, mode, start_token, end_token)
+        cache[key] = sess
+    return sess
+
+
 @torch.no_grad()
-def beam_sample(dec, features, start_token, end_token, k, mode, feed_image, sync_every=4):
+def beam_sample(dec, features, start_token, end_token, k, mode, feed_image, sync_every=4, use_graph=None):
     """Returns a list of LongTensor [1, L_i] (one per image; the reference handles one image per call).
-    ``features``: [n_img, E] (or [n_img, 1, E]); rows are independent images."""
+    ``features``: [n_img, E] (or [n_img, 1, E]); rows are independent images.
+    ``use_graph`` (default: fp32 mode): steps >= 2 replay one captured CUDA graph of the decode step."""
     emb = dec._emb()
     E = emb.weight.shape[1]
     dev = emb.weight.device
     ops.lib()
     dec.arena()
-    feats = features.detach().to(dev).float().reshape(-1, E).contiguous()
+    feats = features.detach().to(dev).float().reshape(-1, E)
     n_img = feats.shape[0]
-    H = dec.hidden_size
-    st = BeamState(n_img, k, dec.max_seq_length, start_token, dev)
-    R = st.R
-    h = torch.zeros(R, H, dtype=torch.float32, device=dev)
-    c = torch.zeros(R, H, dtype=torch.float32, device=dev)
-    h_new = torch.empty_like(h)
-    out = dec._out()
-    V = out.weight.shape[0]
-    logits = torch.empty(R, V, dtype=torch.float32, device=dev)
-    X = torch.empty(R, E, dtype=torch.float32, device=dev)
-    ctx = _StepCtx()
-    ctx.XP = torch.empty(R, 4 * H, dtype=torch.float32, device=dev)
-    row_img = (torch.arange(R, device=dev, dtype=torch.int32) // k).contiguous()
-    row_zero = torch.zeros(R, dtype=torch.int32, device=dev)
-    dummy_cap = torch.zeros(1, 1, dtype=torch.int64, device=dev)
-    bs1, off1 = _i32(dev, [R]), _i32(dev, [0])
-    Whh, bhh = dec._recurrent_weights()
-    cache = {}
-    ctx.w16 = {}
+    if use_graph is None:
+        use_graph = not dec.bf16           # bf16 mode refreshes weight shadows per call: stays eager
+    sess = _session(dec, n_img, k, mode, start_token, end_token)
+    st = sess.st
+    sess.calls += 1
+    if use_graph and sess.graph is None and sess.calls >= 2:
+        sess.capture()                      # first call runs eagerly (and warms everything up)
+    st.reset()
+    sess.h.zero_()
+    sess.c.zero_()
+    sess.feats.copy_(feats)
+    sess.cache.clear()
+    sess.ctx.w16 = {}
+    graph = sess.graph if use_graph else None
     for step in range(1, dec.max_seq_length + 2):
-        if feed_image and step == 1:
-            ops.gather_pack_fwd(dummy_cap, emb.weight, feats, True, row_img, row_zero, None, R, X, 0.0, 0)
+        if graph is not None and step >= 2:
+            graph.replay()
         else:
-            ops.gather_pack_fwd(dummy_cap, emb.weight, None, False, row_img, row_zero, st.prev_word, R, X, 0.0, 0)
-        dec._input_projection(ctx, X, mode, 0, R)
-        ops.recur_fwd(dec.cell, H, R, bs1, off1, 0, 1, ctx.XP, Whh, bhh, h, h_new, None, None, None, c)
-        _vocab_step(dec, h_new, logits, cache)
-        st.step(logits, step, end_token)
-        idx = st.src_row.long()
-        h = h_new.index_select(0, idx)
-        c = c.index_select(0, idx)
+            sess.step(step, feed_image, device_step=True)
         if sync_every and step % sync_every == 0 and int(st.n_unfinished.item()) == 0:
             break
     return st.results()

@@ -245,13 +245,15 @@ int32_t sn_mean_pixels(const float* feat, int64_t B, int64_t P, int64_t D, float
  *   out_seq [n_img][L], out_len [n_img]         final result when the image finishes: first arg-max of
  *                             the un-normalised scores of finished beams, or [end] if none finished
  *   n_unfinished [1]          decremented once per image when it finishes (poll to stop early)
- * step counts from 1; an image finishes when k reaches 0 or after step > max_len (model.py:273,283). */
+ * step counts from 1; an image finishes when k reaches 0 or after step > max_len (model.py:273,283).
+ * step_dev (optional, device int): the step number read at run time instead of `step`, so that one captured
+ * decode step can be replayed from a CUDA graph (the caller increments it on the device). */
 int32_t sn_beam_step(const float* logits, int64_t ld, int64_t V, int32_t n_img, int32_t kmax,
                      int32_t step, int32_t max_len, int32_t end_token, int32_t* k_live,
                      float* run_score, int32_t* prev_word, int32_t* src_row, int32_t* cur_buf,
                      int32_t* seqs, int32_t* done_seq, int32_t* done_len, float* done_score,
                      int32_t* n_done, int32_t* out_seq, int32_t* out_len, int32_t* n_unfinished,
-                     void* stream);
+                     const int32_t* step_dev, void* stream);
 
 #ifdef __cplusplus
 }
