@@ -18,43 +18,54 @@ struct GemmArgs {
 
 constexpr int BM = 128, BN = 128, BK = 8;
 
-// load a [ROWS(major) x BK] operand tile into smem as S[k][major]
-__device__ __forceinline__ void load_tile(float (*S)[BM + 4], const float* __restrict__ P, int64_t s_major,
-                                          int64_t s_k, int64_t major0, int64_t k0, int64_t major_lim,
-                                          int64_t k_lim, int tid) {
+// one thread's share (4 elements) of a [major x BK] operand tile: fetched into registers first so that the
+// global loads of tile i+1 are in flight while tile i is being multiplied (software pipelining)
+struct Frag { float v[4]; };
+
+__device__ __forceinline__ Frag fetch_tile(const float* __restrict__ P, int64_t s_major, int64_t s_k, int64_t major0,
+                                           int64_t k0, int64_t major_lim, int64_t k_lim, int tid) {
+  Frag f;
+  f.v[0] = f.v[1] = f.v[2] = f.v[3] = 0.f;
   if (s_k == 1) {
     // k contiguous: thread -> (major = tid/2, 4 consecutive k)
     int mj = tid >> 1, kk = (tid & 1) * 4;
     int64_t gm = major0 + mj, gk = k0 + kk;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (gm < major_lim) {
       const float* src = P + gm * s_major + gk;
       if (gk + 3 < k_lim && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-        float4 t = *reinterpret_cast<const float4*>(src);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        float4 t = __ldg(reinterpret_cast<const float4*>(src));
+        f.v[0] = t.x; f.v[1] = t.y; f.v[2] = t.z; f.v[3] = t.w;
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (gk + j < k_lim) v[j] = src[j];
+        for (int j = 0; j < 4; ++j) if (gk + j < k_lim) f.v[j] = __ldg(src + j);
       }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) S[kk + j][mj] = v[j];
   } else {
     // major contiguous (s_major == 1): thread -> (k = tid/32, 4 consecutive major)
     int kk = tid >> 5, mj = (tid & 31) * 4;
     int64_t gm = major0 + mj, gk = k0 + kk;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (gk < k_lim) {
       const float* src = P + gk * s_k + gm * s_major;
       if (s_major == 1 && gm + 3 < major_lim && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-        float4 t = *reinterpret_cast<const float4*>(src);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        float4 t = __ldg(reinterpret_cast<const float4*>(src));
+        f.v[0] = t.x; f.v[1] = t.y; f.v[2] = t.z; f.v[3] = t.w;
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (gm + j < major_lim) v[j] = src[j * s_major];
+        for (int j = 0; j < 4; ++j) if (gm + j < major_lim) f.v[j] = __ldg(src + j * s_major);
       }
     }
-    *reinterpret_cast<float4*>(&S[kk][mj]) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  return f;
+}
+
+__device__ __forceinline__ void store_tile(float (*S)[BM + 4], const Frag& f, int64_t s_k, int tid) {
+  if (s_k == 1) {
+    int mj = tid >> 1, kk = (tid & 1) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S[kk + j][mj] = f.v[j];
+  } else {
+    int kk = tid >> 5, mj = (tid & 31) * 4;
+    *reinterpret_cast<float4*>(&S[kk][mj]) = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
   }
 }
 
@@ -75,10 +86,16 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
+  Frag fa = fetch_tile(A, g.sam, g.sak, m0, 0, g.M, g.K, tid);
+  Frag fb = fetch_tile(B, g.sbn, g.sbk, n0, 0, g.N, g.K, tid);
   for (int64_t k0 = 0; k0 < g.K; k0 += BK) {
-    load_tile(As, A, g.sam, g.sak, m0, k0, g.M, g.K, tid);
-    load_tile(Bs, B, g.sbn, g.sbk, n0, k0, g.N, g.K, tid);
+    store_tile(As, fa, g.sak, tid);
+    store_tile(Bs, fb, g.sbk, tid);
     __syncthreads();
+    if (k0 + BK < g.K) {      // next tile's global loads fly while this tile is multiplied
+      fa = fetch_tile(A, g.sam, g.sak, m0, k0 + BK, g.M, g.K, tid);
+      fb = fetch_tile(B, g.sbn, g.sbk, n0, k0 + BK, g.N, g.K, tid);
+    }
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
