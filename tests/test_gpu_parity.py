@@ -391,5 +391,7 @@ def test_peer_fused_adam_degenerate_world1():
         o2.step_peer(pe)
     torch.cuda.synchronize()
     assert int(pe.pad[17]) == 3                      # epoch advanced once per call
+    # the two decoders ran their own backward passes: atomics-ordered reductions (embedding scatter, bias column
+    # sums) differ in the last bits between runs, and 3 Adam steps carry that into the weights
     for (n, p), (_, q) in zip(d1.named_parameters(), d2.named_parameters()):
-        assert rel_l2(q.detach().cpu(), p.detach().cpu()) < 1e-6, n
+        assert rel_l2(q.detach().cpu(), p.detach().cpu()) < 1e-5, n
