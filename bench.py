@@ -329,6 +329,12 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same kernels at
+# B=96, T=20, H=512 (profiles/r1_f_ncu_full_k3_bf16_B96_raw.csv); below the algorithmic bytes because the
+# per-step exchange and most of the outputs stay in the 126 MB L2 for the life of the launch
+NCU_TRAFFIC = {"recur_fwd_bf16_kernel": 18.07e6 + 0.12e6, "recur_bwd_bf16_kernel": 26.11e6 + 0.12e6}
+
+
 def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src):
     """Per-kernel device time (CUDA events, L2 flushed) of the HBM-bound kernels of one step, the roofline
     object for the dominant one, and a large-batch point of the same kernel (B=4096/GPU) where the serial
@@ -422,7 +428,8 @@ def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src):
     dom = max((k for k in kernels if k.startswith("recur")), key=lambda k: kernels[k]["ms"])
     ach = kernels[dom]["gbs"]
     roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-            "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC.get(dom) if len(lens) == 96 else None,
+            "traffic_source": "ncu --set full, profiles/r1_f_ncu_full_k3_bf16_B96_raw.csv", "peak_source": peak_src,
             "note": "latency-bound at B=96: T serial steps, each with an inter-SM exchange through L2 (DESIGN.md 4). "
                     "Same kernel at B=4096/GPU (bandwidth regime): %.0f GB/s = %.2f of peak"
                     % (big[dom]["gbs"], big[dom]["gbs"] / hbm_peak),
