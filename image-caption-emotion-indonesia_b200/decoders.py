@@ -376,8 +376,9 @@ class _DecoderBase(nn.Module):
             have_b16 = dLb is not None
             if not have_b16:
                 dLb = ops.to_bf16_padded(dlogits)
+            hb_stash = self.__dict__.pop("_out_h16", None)
             if Hb is None:
-                Hb = ops.to_bf16_padded(Hall.contiguous())
+                Hb = hb_stash if (have_b16 and hb_stash is not None) else ops.to_bf16_padded(Hall.contiguous())
             Wb = self.__dict__.pop("_out_w16", None) if dLb is not None and have_b16 else None
             if Wb is None:
                 Wb = ops.to_bf16_padded(out.weight)
@@ -395,6 +396,39 @@ class _DecoderBase(nn.Module):
             ops.gemm(ops.OP_TN, dlogits, Hall, gC, V, H, N, dlogits.stride(0), H, H)
         ops.colsum(dlogits, N, V, dlogits.stride(0), gb)
         return dHall
+
+    def _vocab_nll(self, Hall, Hb, targets, denom, backward):
+        """Vocabulary projection + log-softmax + NLL (+ gradient w.r.t. the logits) + arg-max + top-5
+        (stylenet/model.py:193-194, train_multitask.py:377-383, utils.py:127-140).
+        bf16 mode: K5 fused with the projection -- logits live only in TMEM, never in HBM.  Pass 1 -> log-sum-exp,
+        target logit, loss, arg-max; pass 2 recomputes the tiles and emits the gradient directly as the bf16
+        operand of the dH / dC GEMMs (or only ranks the target when not training).
+        fp32 mode: fp32 FFMA logits + the one-pass softmax kernel (gradient in place).
+        Returns (row_loss, argmax, top5hit, dlogits_fp32 | None, dlogits_bf16 | None)."""
+        out = self._out()
+        V, H = out.weight.shape
+        N, dev = Hall.shape[0], Hall.device
+        row_loss = torch.empty(N, dtype=torch.float32, device=dev)
+        argmax = torch.empty(N, dtype=torch.int64, device=dev)
+        top5 = torch.empty(N, dtype=torch.int32, device=dev)
+        if self.bf16:
+            if Hb is None:
+                Hb = ops.to_bf16_padded(Hall.contiguous())
+            Wb = ops.to_bf16_padded(out.weight)
+            self.__dict__["_out_w16"] = Wb              # reused by the matching _vocab_backward
+            self.__dict__["_out_h16"] = Hb
+            tl = torch.empty(N, dtype=torch.float32, device=dev)
+            lse = torch.empty(N, dtype=torch.float32, device=dev)
+            above = torch.empty(N, dtype=torch.int32, device=dev)
+            ops.vocab_nll_fwd(Hb, Wb, out.bias, targets, N, V, H, tl, lse, row_loss=row_loss, argmax=argmax, above=above)
+            dLb = torch.empty(N, _pad8(V), dtype=torch.bfloat16, device=dev) if backward else None
+            ops.vocab_nll_bwd(Hb, Wb, out.bias, targets, N, V, H, tl, lse, 1.0 / denom, dLb=dLb, above=above,
+                              top5hit=top5)
+            return row_loss, argmax, top5, None, dLb
+        logits = self._vocab_logits(Hall, Hb)
+        ops.softmax_nll(logits, N, V, targets=targets, row_loss=row_loss, dlogits=logits if backward else None,
+                        grad_scale=1.0 / denom, argmax=argmax, top5hit=top5)
+        return row_loss, argmax, top5, logits, None
 
     # ---- public API --------------------------------------------------------------------------------
     def _forward_hidden(self, captions, lengths, features, teacher_forcing_ratio, mode):
@@ -435,18 +469,8 @@ class _DecoderBase(nn.Module):
                     raise ValueError("forward_loss: pass `targets` when features is None (language-only "
                                      "pass: inputs captions[:, :-1], targets packed captions[:, 1:])")
                 targets = self._default_targets(captions, plan, True)
-            logits = self._vocab_logits(c.Hall, c.Hb)
-            row_loss = torch.empty(N, dtype=torch.float32, device=dev)
-            argmax = torch.empty(N, dtype=torch.int64, device=dev)
-            top5 = torch.empty(N, dtype=torch.int32, device=dev)
             denom = float(n_global if n_global is not None else N)
-            dLb = None
-            if backward and self.bf16:
-                # the gradient leaves the softmax kernel directly as the bf16 GEMM operand (no fp32 copy)
-                dLb = torch.empty(N, _pad8(V), dtype=torch.bfloat16, device=dev)
-            ops.softmax_nll(logits, N, V, targets=targets, row_loss=row_loss,
-                            dlogits=logits if (backward and dLb is None) else None, grad_scale=1.0 / denom,
-                            argmax=argmax, top5hit=top5, dlogits_bf16=dLb)
+            row_loss, argmax, top5, logits, dLb = self._vocab_nll(c.Hall, c.Hb, targets, denom, backward)
             loss = torch.empty(1, dtype=torch.float32, device=dev)
             ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
             if backward:

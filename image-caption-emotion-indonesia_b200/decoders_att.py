@@ -354,13 +354,8 @@ class _AttBase(_DecoderBase):
                 targets = full_captions[d["row_b"].long(), d["row_t"].long() + 1].contiguous()
             out = self._out()
             V = out.weight.shape[0]
-            logits = self._vocab_logits(c.Hall)
-            row_loss = torch.empty(N, dtype=torch.float32, device=dev)
-            argmax = torch.empty(N, dtype=torch.int64, device=dev)
-            top5 = torch.empty(N, dtype=torch.int32, device=dev)
             denom = float(n_global if n_global is not None else N)
-            ops.softmax_nll(logits, N, V, targets=targets, row_loss=row_loss, dlogits=logits if backward else None,
-                            grad_scale=1.0 / denom, argmax=argmax, top5hit=top5)
+            row_loss, argmax, top5, logits, dLb = self._vocab_nll(c.Hall, None, targets, denom, backward)
             loss = torch.empty(1, dtype=torch.float32, device=dev)
             ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
             # doubly stochastic regulariser: tiny [B,P] reduction (plumbing-size torch ops)
@@ -372,7 +367,8 @@ class _AttBase(_DecoderBase):
                 dAl = dAl.unsqueeze(1).expand(B, c.alphas.shape[1], P).contiguous()
                 names = c.grad_names + list(self._out_names())
                 gbuf = self._grad_target(names)
-                dHall = self._vocab_backward(c.Hall, logits, gbuf)
+                dHall = self._vocab_backward(c.Hall, logits, gbuf, None, dLb)
+                self._join()
                 if grad_hook is not None and gbuf is self.arena().gflat:
                     grad_hook(list(self._out_names()))
                 dfeat = self._run_backward_att(c, dHall, dAl, gbuf, features.requires_grad)

@@ -187,15 +187,81 @@ def _bptr(t, off_elems, elem_size):
     return ctypes.c_void_p(t.data_ptr() + elem_size * off_elems) if t is not None else None
 
 
+# GEMM kernel selection for gemm_bf16: "auto" = CTA-pair kernel (sn_gemm2.cu) when the problem has at least one
+# full 256-row tile, else the single-CTA 128x128 kernel (sn_gemm_tc.cu); "tc" / "pair" force one of them.
+GEMM_IMPL = ["auto"]
+_SM_PAIRS = 74
+
+
+def _pick_splits(M, N, K, batch):
+    """Split-K factor for the pair kernel: fill the 74 SM pairs when the tile count alone cannot."""
+    tiles = ((M + 255) // 256) * ((N + 255) // 256) * batch
+    kb = (K + 63) // 64
+    if tiles * 2 > _SM_PAIRS or kb < 16:
+        return 1
+    return max(1, min(_SM_PAIRS // tiles, kb // 8, 16))
+
+
+_g2_ws = {}
+
+
+def _gemm2_ws(device, nbytes):
+    """Split-K work space, one per (device, stream): sized up on demand, reused across calls."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _g2_ws.get(key)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = torch.empty(nbytes // 4 + 4, dtype=torch.float32, device=device)
+        _g2_ws[key] = ws
+    return ws
+
+
 def gemm_bf16(op, A, B, M, N, K, lda, ldb, C=None, ldc=0, Cb=None, ldcb=0, bias=None, beta=0.0, batch=1,
-              sA=0, sB=0, sC=0, sCb=0, sBias=0, a_off=0, b_off=0, c_off=0, cb_off=0, bias_off=0, splits=1):
+              sA=0, sB=0, sC=0, sCb=0, sBias=0, a_off=0, b_off=0, c_off=0, cb_off=0, bias_off=0, splits=1,
+              impl=None):
     """tcgen05 GEMM: A, B bf16; C fp32 and/or Cb bf16.  Offsets in elements of the respective tensor.
-    splits: 1 = off (default: the atomic reduction epilogue costs more than it gains at these sizes, see
-    profiles/README.md r1_d), 0 = automatic, n = forced."""
+    Pair kernel: splits=1 -> automatic split-K (deterministic work-space reduction) for few-tile / long-K shapes.
+    Single-CTA kernel: splits: 1 = off, 0 = automatic, n = forced (fp32 atomics)."""
     _req(A, torch.bfloat16); _req(B, torch.bfloat16)
+    impl = impl or GEMM_IMPL[0]
+    if impl == "pair" or (impl == "auto" and M >= 256):
+        sp = _pick_splits(M, N, K, batch) if splits in (0, 1) else splits
+        if sp > 1 and N % 4 != 0:
+            sp = 1
+        ws, wsb = None, 0
+        if sp > 1:
+            wsb = lib().sn_gemm2_ws_bytes(M, N, batch, sp)
+            ws = _gemm2_ws(A.device, wsb)
+            LAUNCHES[0] += batch
+        check(lib().sn_gemm2_bf16(op, M, N, K, _bptr(A, a_off, 2), lda, _bptr(B, b_off, 2), ldb,
+                                  _bptr(C, c_off, 4), ldc, _bptr(Cb, cb_off, 2), ldcb, _bptr(bias, bias_off, 4),
+                                  float(beta), batch, sA, sB, sC, sCb, sBias, sp, _ptr(ws), wsb, _stream()),
+              "sn_gemm2_bf16")
+        return
     check(lib().sn_gemm_bf16_splitk(op, M, N, K, _bptr(A, a_off, 2), lda, _bptr(B, b_off, 2), ldb,
                                     _bptr(C, c_off, 4), ldc, _bptr(Cb, cb_off, 2), ldcb, _bptr(bias, bias_off, 4),
                                     float(beta), batch, sA, sB, sC, sCb, sBias, splits, _stream()), "sn_gemm_bf16")
+
+
+def vocab_nll_fwd(Hb, Wb, bias, targets, N, V, H, tlogit, lse, row_loss=None, argmax=None, above=None):
+    """Vocabulary projection fused with log-softmax / NLL statistics (no logits in HBM)."""
+    _req(Hb, torch.bfloat16); _req(Wb, torch.bfloat16); _req(targets, torch.int64)
+    nbytes = lib().sn_vocab_ws_bytes(N, V)
+    ws = _gemm2_ws(Hb.device, nbytes)
+    check(lib().sn_vocab_nll_fwd(N, V, H, _ptr(Hb), Hb.stride(0), _ptr(Wb), Wb.stride(0), _ptr(_req(bias)),
+                                 _ptr(targets), _ptr(ws), nbytes, _ptr(tlogit), _ptr(lse), _ptr(row_loss),
+                                 _ptr(argmax), _ptr(above), _stream()), "sn_vocab_nll_fwd")
+    LAUNCHES[0] += 1
+
+
+def vocab_nll_bwd(Hb, Wb, bias, targets, N, V, H, tlogit, lse, grad_scale, dLb=None, above=None, top5hit=None):
+    """Recompute the logits tiles; write (softmax - onehot) * grad_scale as bf16 [N, ld]; rank of the target."""
+    _req(Hb, torch.bfloat16); _req(Wb, torch.bfloat16); _req(targets, torch.int64)
+    check(lib().sn_vocab_nll_bwd(N, V, H, _ptr(Hb), Hb.stride(0), _ptr(Wb), Wb.stride(0), _ptr(_req(bias)),
+                                 _ptr(targets), _ptr(tlogit), _ptr(lse), float(grad_scale), _ptr(dLb),
+                                 dLb.stride(0) if dLb is not None else 0, _ptr(above), _ptr(top5hit), _stream()),
+          "sn_vocab_nll_bwd")
+    if top5hit is not None:
+        LAUNCHES[0] += 1
 
 
 def cast_bf16(src, R, C, lds, dst, Cp, ldd, src_off=0, dst_off=0):

@@ -98,6 +98,17 @@ int32_t sn_gemm_bf16_splitk(int32_t op, int64_t M, int64_t N, int64_t K, const v
                             const float* bias, float beta, int32_t batch, int64_t strideA,
                             int64_t strideB, int64_t strideC, int64_t strideCb, int64_t strideBias,
                             int32_t splits, void* stream);
+/* K2b: the same GEMM as sn_gemm_bf16 on CTA PAIRS (tcgen05.mma.cta_group::2, 256x256 tiles, persistent tile loop,
+ * double-buffered TMEM accumulator; sn_gemm2.cu).  Twice the arithmetic intensity per byte fetched from L2 --
+ * the kernel for the time-batched projection / vocabulary / weight-gradient GEMMs (M >= 256).
+ * splits > 1: split-K through the caller-provided work space `ws` (sn_gemm2_ws_bytes), reduced by a second
+ * kernel (deterministic, no atomics); any epilogue (bias, beta, bf16 copy) is applied by the reduction. */
+int64_t sn_gemm2_ws_bytes(int64_t M, int64_t N, int32_t batch, int32_t splits);
+int32_t sn_gemm2_bf16(int32_t op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                      const void* B, int64_t ldb, float* C, int64_t ldc, void* Cb, int64_t ldcb,
+                      const float* bias, float beta, int32_t batch, int64_t strideA, int64_t strideB,
+                      int64_t strideC, int64_t strideCb, int64_t strideBias, int32_t splits, void* ws,
+                      int64_t ws_bytes, void* stream);
 /* fp32 [R,C] (row pitch lds) -> bf16 [R,Cp] (row pitch ldd), columns C..Cp zero-filled (weight shadows and
  * activation operands of sn_gemm_bf16; Cp pads K to the TMA 16-byte rule, e.g. E=300 -> 304) */
 int32_t sn_cast_bf16(const float* src, int64_t R, int64_t C, int64_t lds, void* dst, int64_t Cp,
@@ -166,6 +177,25 @@ int32_t sn_recur_bwd_bf16(int32_t cell, int64_t H, int64_t B, const int32_t* bat
 int32_t sn_softmax_nll(const float* logits, int64_t N, int64_t V, int64_t ld, const int64_t* targets,
                        float* row_loss, float* dlogits, int64_t ldd, float grad_scale,
                        int64_t* argmax, int32_t* top5hit, void* dlogits_bf16, int64_t lddb, void* stream);
+/* K5 fused with the vocabulary projection (bf16 mode): logits = Hb Wb^T + bias are produced tile by tile in
+ * TMEM and consumed by the epilogue -- the [N,V] logits are NEVER written to HBM.
+ * replaces self.C(hiddens) + nn.CrossEntropyLoss + output.max(1) + utils.accuracy
+ *   stylenet/model.py:189-194, train_multitask.py:134,377-383, utils.py:127-140
+ * sn_vocab_nll_fwd: per-row log-sum-exp `lse`, target logit `tlogit`, row_loss = lse - tlogit, argmax (lowest index
+ *   on ties); `above` (optional) is zeroed for the ranking pass.  ws: sn_vocab_ws_bytes(N, V) bytes.
+ * sn_vocab_nll_bwd: recomputes the logits tiles and writes dL = (softmax - onehot) * grad_scale as the bf16
+ *   [N, lddl] operand of the two backward GEMMs (columns V..lddl zero; dL may be NULL = ranking only);
+ *   above[row] += #{v : logit_v > logit_target}; top5hit[row] = above[row] < 5 (optional).
+ * Hb [N,ldh], Wb [V,ldw]: bf16, K = H padded per the TMA rules of sn_gemm_bf16. */
+int64_t sn_vocab_ws_bytes(int64_t N, int64_t V);
+int32_t sn_vocab_nll_fwd(int64_t N, int64_t V, int64_t H, const void* Hb, int64_t ldh, const void* Wb,
+                         int64_t ldw, const float* bias, const int64_t* targets, void* ws, int64_t ws_bytes,
+                         float* tlogit, float* lse, float* row_loss, int64_t* argmax, int32_t* above,
+                         void* stream);
+int32_t sn_vocab_nll_bwd(int64_t N, int64_t V, int64_t H, const void* Hb, int64_t ldh, const void* Wb,
+                         int64_t ldw, const float* bias, const int64_t* targets, const float* tlogit,
+                         const float* lse, float grad_scale, void* dL, int64_t lddl, int32_t* above,
+                         int32_t* top5hit, void* stream);
 /* loss = scale * sum(row_loss[0..N)) (+ loss if accumulate), deterministic order, double sum */
 int32_t sn_reduce_sum(const float* x, int64_t N, float scale, float* out, int32_t accumulate,
                       void* stream);

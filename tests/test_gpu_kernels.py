@@ -193,7 +193,8 @@ def test_gemm_tcgen05_bf16(ops, op, M, N, K):
     C0 = torch.randn(M, N, device="cuda", generator=g)
     C = C0.clone()
     Cb = torch.zeros(M, pad(N), device="cuda", dtype=torch.bfloat16)
-    ops.gemm_bf16(op, A, B, M, N, K, A.stride(0), B.stride(0), C=C, ldc=N, Cb=Cb, ldcb=Cb.stride(0), bias=bias, beta=0.5)
+    ops.gemm_bf16(op, A, B, M, N, K, A.stride(0), B.stride(0), C=C, ldc=N, Cb=Cb, ldcb=Cb.stride(0), bias=bias, beta=0.5,
+                  impl="tc")
     a = A.double()[:, :K] if op != 2 else A.double()[:, :M].t()
     b = B.double()[:, :K].t() if op == 0 else B.double()[:, :N]
     want = a @ b + bias.double() + 0.5 * C0.double()
@@ -208,7 +209,7 @@ def test_gemm_tcgen05_grouped(ops):
     B = (torch.randn(4, H, F, device="cuda", generator=g) / 16).bfloat16()
     bias = torch.randn(4 * H, device="cuda", generator=g)
     C = torch.zeros(n, 4 * H, device="cuda")
-    ops.gemm_bf16(0, A, B, n, H, F, 4 * F, F, C=C, ldc=4 * H, bias=bias, batch=4, sA=F, sB=H * F, sC=H, sBias=H)
+    ops.gemm_bf16(0, A, B, n, H, F, 4 * F, F, C=C, ldc=4 * H, bias=bias, batch=4, sA=F, sB=H * F, sC=H, sBias=H, impl="tc")
     want = torch.cat([A[:, i * F:(i + 1) * F].double() @ B[i].double().t() + bias[i * H:(i + 1) * H].double()
                       for i in range(4)], 1)
     assert _rel(C, want) < 1e-5
