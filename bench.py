@@ -35,6 +35,9 @@ WORKLOAD_TEXT = {
     "att": "configs[2]: StyleNet DecoderFactoredLSTMAtt(attention 512, embed 300, hidden 512, factored 512, vocab 10000) "
            "over a 7x7x2048 feature map, mode=happy, teacher_forcing=1.0, dropout 0.5 on, "
            "CE + doubly-stochastic regulariser, fwd+bwd+clip(0.5)+Adam, T=20 (19 decoded steps)",
+    "stack3": "configs[3]: 3-layer FactoredLSTM stack (embed 300, hidden 512, factored 1024, vocab 10000; 73.4 M parameters), "
+              "multitask alternation: factual pass (optimizer A, lr 2e-4) / emotion pass mode=happy (optimizer B, lr 5e-4) "
+              "on alternate steps, teacher_forcing=1.0, dropout 0.5 on, fwd+bwd+clip(0.5)+Adam, T=20",
     "nic": "configs[0] on the GPU: NIC DecoderRNN(embed 300, hidden 512, vocab 10000), B=64, teacher_forcing=1.0, "
            "dropout 0.5 on, fwd+bwd+clip(0.5)+Adam, T=20",
 }
@@ -62,17 +65,41 @@ def cpu_reference_run(steps, warmup, max_seconds=None):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    dec = port.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5)
-    dec.train()
-    opt = torch.optim.Adam(dec.parameters(), lr=5e-4)
     cap, lens, feats = port.synthetic_batch(B_PER_GPU, T, V, E=E, ragged=False, seed=0)
+    if WORKLOAD == "stack3":
+        from oracle.stack import stack_forward, stack_parameters
+        layers = [port.DecoderFactoredLSTM(E if l == 0 else H, H, 1024, V, 1, dropout=0.5) for l in range(3)]
+        for layer in layers:
+            layer.train()
+        params = stack_parameters(layers)
+        opts = [torch.optim.Adam(params, lr=2e-4), torch.optim.Adam(params, lr=5e-4)]
+        tgt = port.pack_targets(cap, lens)
+        count = [0]
+
+        def one_step():
+            i = count[0] % 2
+            count[0] += 1
+            out = stack_forward(layers, cap, lens, feats, teacher_forcing_ratio=1.0, mode=("factual", MODE)[i])
+            loss = torch.nn.functional.cross_entropy(out, tgt)
+            for layer in layers:
+                layer.zero_grad()
+            loss.backward()
+            port.clip_gradient(opts[i], 0.5)
+            opts[i].step()
+    else:
+        dec = port.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5)
+        dec.train()
+        opt = torch.optim.Adam(dec.parameters(), lr=5e-4)
+
+        def one_step():
+            port.train_step(dec, opt, cap, lens, feats, mode=MODE, teacher_forcing_ratio=1.0)
     random.seed(0)
     for _ in range(warmup):
-        port.train_step(dec, opt, cap, lens, feats, mode=MODE, teacher_forcing_ratio=1.0)
+        one_step()
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
-        port.train_step(dec, opt, cap, lens, feats, mode=MODE, teacher_forcing_ratio=1.0)
+        one_step()
         done += 1
         if max_seconds is not None and time.perf_counter() - t0 > max_seconds:
             break
@@ -202,6 +229,8 @@ def run_gpu(args):
         dec = sn.DecoderFactoredLSTMAtt(512, E, H, F, V, 1, dropout=0.5).to(dev)
     elif WORKLOAD == "nic":
         dec = sn.DecoderRNN(E, H, V, 1, dropout=0.5).to(dev)
+    elif WORKLOAD == "stack3":
+        dec = sn.DecoderFactoredLSTMStack(E, H, 1024, V, 3, dropout=0.5).to(dev)
     else:
         dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5).to(dev)
     dec.train()
@@ -210,6 +239,9 @@ def run_gpu(args):
         else "f32 FFMA"
     opt = sn.FusedClampAdam(dec, lr=5e-4, grad_clip=0.5)
     trainer = sn.DataParallelTrainer(dec, opt)
+    trainer_fac = None
+    if WORKLOAD == "stack3":      # multitask: a second optimizer object (own Adam moments) for the factual pass
+        trainer_fac = sn.DataParallelTrainer(dec, sn.FusedClampAdam(dec, lr=2e-4, grad_clip=0.5))
     bsz = 64 if WORKLOAD == "nic" else B_PER_GPU
     cap_h, lens, feat_h = synthetic_batch(bsz, T, V, E, seed=rank)
     step_kw = {"teacher_forcing_ratio": 1.0}
@@ -236,19 +268,32 @@ def run_gpu(args):
         ops.LAUNCHES[0] = 0
         graphed = sn.GraphedTrainStep(trainer, cap_d, lens, feat_d, warmup=3, force_segmented=args.segmented, **step_kw)
         launches_per_step = ops.LAUNCHES[0] // 4          # 3 warm-up runs + 1 capture run
+    graphed_fac = None
+    kw_fac = dict(step_kw, mode="factual")
+    if trainer_fac is not None and graphed is not None:
+        graphed_fac = sn.GraphedTrainStep(trainer_fac, cap_d, lens, feat_d, warmup=3, force_segmented=args.segmented, **kw_fac)
+    parity = [0]                                          # stack3: factual / emotion passes on alternate steps
+
+    def pick():
+        if trainer_fac is None:
+            return graphed, trainer, step_kw
+        parity[0] ^= 1
+        return (graphed_fac, trainer_fac, kw_fac) if parity[0] else (graphed, trainer, step_kw)
 
     def step_resident():
-        if graphed is not None:
-            return graphed()
-        return trainer.step(cap_d, lens, feat_d, **step_kw)
+        g, tr, kw = pick()
+        if g is not None:
+            return g()
+        return tr.step(cap_d, lens, feat_d, **kw)
 
     def step_e2e():
-        if graphed is not None:
-            loss, _ = graphed(cap_pin, feat_pin)          # pinned host -> static device buffers, then replay
+        g, tr, kw = pick()
+        if g is not None:
+            loss, _ = g(cap_pin, feat_pin)                # pinned host -> static device buffers, then replay
         else:
             c = cap_pin.to(dev, non_blocking=True)
             f = feat_pin.to(dev, non_blocking=True)
-            loss, _ = trainer.step(c, lens, f, **step_kw)
+            loss, _ = tr.step(c, lens, f, **kw)
         loss_pin.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_pin[0])
@@ -448,7 +493,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--workload", default="factored", choices=["factored", "att", "nic"])
+    ap.add_argument("--workload", default="factored", choices=["factored", "att", "nic", "stack3"])
     ap.add_argument("--segmented", action="store_true", help="force the 3-graph (data-parallel) replay form on one GPU")
     args = ap.parse_args()
     global WORKLOAD

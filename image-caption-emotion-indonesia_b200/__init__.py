@@ -11,6 +11,7 @@ from .packing import PackPlan, batch_sizes_from_lengths, get_plan, shard_lengths
 from . import ops  # noqa: F401
 from .dp import DataParallelTrainer, GradSync, merged_ranges  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
+from .stack import DecoderFactoredLSTMStack, MultitaskSchedule  # noqa: F401
 
 try:  # attention variants
     from .decoders_att import DecoderFactoredLSTMAtt, DecoderRNNAtt  # noqa: F401

@@ -30,6 +30,7 @@
 //               GEMMs, plus the count of logits above the target's (top-k accuracy).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <math.h>
 #include <math_constants.h>
 
 #include "sn_common.cuh"
@@ -71,7 +72,7 @@ struct G2Args {
   float* pmax; float* psum; int32_t* pidx; int nchunks;   // [M, nchunks]
   float* tlogit;                   // [M] logit of the target column
   const float* lse;                // [M]
-  float scale;
+  float scale, scale_log2;
   __nv_bfloat16* dL; int64_t lddl; // [M, lddl] gradient w.r.t. the logits
   int32_t* above;                  // [M] number of logits strictly above the target's
 };
@@ -207,14 +208,59 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// bf16 output of a 32x32 block held one ROW per thread: pack to bf16x2, transpose through 2 KB of shared memory
+// (16-byte units, unit u of row r at r*64 + (u ^ ((r>>1)&3))*16: conflict-free both ways), then 4 x STG.128 where
+// every instruction covers 8 rows x 64 contiguous bytes.  Requires ld % 8 == 0 and a 16-byte aligned base for the
+// vector path; ragged right edges fall back to scalar stores.
+__device__ __forceinline__ void store_block_bf16(float* xbuf, int lane, const float (&v)[32], __nv_bfloat16* base,
+                                                 int64_t ld, int row0, int M, int nb, int ncols, bool vec_ok) {
+  uint8_t* buf = reinterpret_cast<uint8_t*>(xbuf);
+  __syncwarp();
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * u], v[8 * u + 1]), p1 = __floats2bfloat162_rn(v[8 * u + 2], v[8 * u + 3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * u + 4], v[8 * u + 5]), p3 = __floats2bfloat162_rn(v[8 * u + 6], v[8 * u + 7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(buf + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4)) = pk;
+  }
+  __syncwarp();
+  const int u = lane & 3;
+  const int n8 = nb + 8 * u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    const uint4 pk = *reinterpret_cast<const uint4*>(buf + r * 64 + ((u ^ ((r >> 1) & 3)) << 4));
+    const int rr = row0 + r;
+    if (rr >= M || n8 >= ncols) continue;
+    __nv_bfloat16* dst = base + (int64_t)rr * ld + n8;
+    if (vec_ok && n8 + 8 <= ncols) {
+      *reinterpret_cast<uint4*>(dst) = pk;
+    } else {
+      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&pk);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (n8 + k < ncols) dst[k] = e[k];
+    }
+  }
+}
+
 struct Tile { int m0, n0, grp, split, kb0, nkb; };
 
 __device__ __forceinline__ Tile decode_tile(const G2Args& g, int tile, int tiles_m, int tiles_n, int total_kb) {
+  // Tile order: the fastest-varying index walks the SMALLER operand, so the ~74 tiles in flight share a few tiles of
+  // the larger operand (read from HBM once) while the smaller one stays L2-resident (M >> N: all n-tiles of an
+  // m-tile run side by side; measured before: A re-fetched from HBM behind the streaming output writes).
   Tile t;
-  const int mt = tile % tiles_m;
-  int rest = tile / tiles_m;
-  const int nt = rest % tiles_n;
-  rest /= tiles_n;
+  int mt, nt, rest;
+  if (g.M > g.N) {
+    nt = tile % tiles_n; rest = tile / tiles_n;
+    mt = rest % tiles_m; rest /= tiles_m;
+  } else {
+    mt = tile % tiles_m; rest = tile / tiles_m;
+    nt = rest % tiles_n; rest /= tiles_n;
+  }
   t.split = rest % g.splits;
   t.grp = rest / g.splits;
   t.m0 = mt * BM;
@@ -275,20 +321,19 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
         const Tile t = decode_tile(g, tile, tiles_m, tiles_n, total_kb);
         const CUtensorMap* map_a = &tma_a.m[t.grp];
         const CUtensorMap* map_b = &tma_b.m[t.grp];
         const int m0 = t.m0 + (int)rank * BMC, n0 = t.n0 + (int)rank * BNC;
-        for (int kb = 0; kb < t.nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+        int k0 = t.kb0 * BK;
+        for (int kb = 0; kb < t.nkb; ++kb, k0 += BK) {
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
           const uint32_t lbar = mapa(full0 + 8 * s, 0);
           if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * STAGE_BYTES);
-          const int k0 = (t.kb0 + kb) * BK;
           if (!g.a_mn_major) {
             tma_load_2d_2sm(sa, map_a, lbar, k0, m0);                    // box {64 k, 128 rows}
           } else {
@@ -301,44 +346,48 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
             tma_load_2d_2sm(sb, map_b, lbar, n0, k0);
             tma_load_2d_2sm(sb + B_BYTES / 2, map_b, lbar, n0 + 64, k0);
           }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA) =====================
-    if (rank == 0) {
+    // ===================== MMA issuer (leader CTA, ONE thread) =====================
+    // The whole issue loop runs in a single thread and is kept to a handful of instructions per MMA (descriptors are
+    // a 64-bit add on a per-stage base): at 135 tensor-pipe cycles per 256x256x16 MMA a ~100-instruction issue path
+    // per k-block was itself the bottleneck (ncu: the issuing warp never waited on a barrier, profiles/r1_i).
+    if (rank == 0 && lane == 0) {
       // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major bit15, b_major bit16,
       // N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)g.a_mn_major << 15) |
                              ((uint32_t)g.b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int it = 0, acc_it = 0;
-      for (int tile = pair; tile < total_tiles; tile += npairs, ++acc_it) {
+      // K-major: advance 32 B inside the 128 B swizzle row; SBO = 1024 B between 8-row groups.
+      // MN-major: advance two 8-k-row groups (2 KB); LBO = 8 KB between the two 64-wide MN chunks.
+      const uint64_t adesc0 = g.a_mn_major ? make_desc(smem_base, A_BYTES / 2, 1024) : make_desc(smem_base, 16, 1024);
+      const uint64_t bdesc0 = g.b_mn_major ? make_desc(smem_base + A_BYTES, B_BYTES / 2, 1024)
+                                           : make_desc(smem_base + A_BYTES, 16, 1024);
+      const uint64_t astep = (g.a_mn_major ? 2048 : 32) >> 4, bstep = (g.b_mn_major ? 2048 : 32) >> 4;
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
         const Tile t = decode_tile(g, tile, tiles_m, tiles_n, total_kb);
-        const int as = acc_it & 1;
-        const uint32_t aph = (acc_it >> 1) & 1;
         mbar_wait_cluster(tempty0 + 8 * as, aph ^ 1);      // epilogues of both CTAs drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < t.nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+        for (int kb = 0; kb < t.nkb; ++kb) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+          const uint64_t ad = adesc0 + (uint64_t)(s * (STAGE_BYTES >> 4)), bd = bdesc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
+          umma2_bf16(tmem_d, ad, bd, idesc, kb ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t ad = g.a_mn_major ? make_desc(sa + k * 2048, A_BYTES / 2, 1024) : make_desc(sa + k * 32, 16, 1024);
-              const uint64_t bd = g.b_mn_major ? make_desc(sb + k * 2048, B_BYTES / 2, 1024) : make_desc(sb + k * 32, 16, 1024);
-              umma2_bf16(tmem_d, ad, bd, idesc, (kb | k) ? 1u : 0u);
-            }
-            umma2_commit_mc(empty0 + 8 * s);
-            if (kb == t.nkb - 1) umma2_commit_mc(tfull0 + 8 * as);
-          }
-          __syncwarp();
+          for (int k = 1; k < BK / UMMA_K; ++k) umma2_bf16(tmem_d, ad + k * astep, bd + k * bstep, idesc, 1u);
+          umma2_commit_mc(empty0 + 8 * s);
+          if (kb == t.nkb - 1) umma2_commit_mc(tfull0 + 8 * as);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        if (++as == ACC_STAGES) { as = 0; aph ^= 1; }
       }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..17, both CTAs) =====================
     const int q = warp & 3;                      // TMEM lane quadrant of this warp
@@ -356,7 +405,7 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
       const int row = row0 + lane;                          // the row this thread holds after tcgen05.ld
       const int ncol0 = t.n0 + slice * EPI_COLS;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + slice * EPI_COLS);
-      const bool row_ok = row < g.M && t.nkb > 0;
+      const bool row_ok = row < g.M;
 
       if (EPI == EPI_STORE || EPI == EPI_PARTIAL) {
         float* Cg = nullptr;
@@ -375,11 +424,33 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
         }
         const bool vec_c = Cg && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cg) & 15) == 0);
         const bool vec_cb = Cbg && ((g.ldcb & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cbg) & 7) == 0);
+        const bool bf16_only = (EPI == EPI_STORE) && !Cg && Cbg && ((g.ldcb & 7) == 0) &&
+                               ((reinterpret_cast<uintptr_t>(Cbg) & 15) == 0);
 #pragma unroll 1
         for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
           uint32_t r[32];
           tmem_ld32_issue(taddr + c0, r);
           const int nb = ncol0 + c0;
+          if (bf16_only) {
+            // bf16-only output (activations of the forward chain): bias in the row layout, packed transpose
+            float v[32];
+            if (bias && nb + 32 <= g.N && ((reinterpret_cast<uintptr_t>(bias + nb) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
+                v[j] = b.x; v[j + 1] = b.y; v[j + 2] = b.z; v[j + 3] = b.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (bias && nb + j < g.N) ? __ldg(bias + nb + j) : 0.f;
+            }
+            tmem_ld_wait(r);
+            if (nb >= g.N || row0 >= g.M) continue;                   // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+            store_block_bf16(xbuf, lane, v, Cbg, g.ldcb, row0, g.M, nb, g.N, true);
+            continue;
+          }
           const int n4 = nb + 4 * (lane & 7);              // this lane's 4 columns in the store phase
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (bias && nb < g.N) {
@@ -393,7 +464,7 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
             }
           }
           tmem_ld_wait(r);
-          if (nb >= g.N || row0 >= g.M || t.nkb <= 0) continue;        // warp-uniform
+          if (nb >= g.N || row0 >= g.M) continue;                     // warp-uniform
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -498,7 +569,7 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
         }
       } else {  // EPI_GRAD
         const int64_t tgt = row_ok ? g.targets[row] : -1;
-        const float lse2 = row_ok ? g.lse[row] * LOG2E : 0.f;
+        const float escale = row_ok ? g.scale_log2 - g.lse[row] * LOG2E : 0.f;   // exp2 argument offset: -lse + log(scale)
         const float tl = row_ok ? g.tlogit[row] : 0.f;
         int cnt = 0;
 #pragma unroll 1
@@ -518,40 +589,36 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
             for (int j = 0; j < 32; ++j) v[j] = (nb + j < g.N) ? __ldg(g.bias + nb + j) : 0.f;
           }
           tmem_ld_wait(r);
-          if (nb >= g.lddl || row0 >= g.M || t.nkb <= 0) continue;     // warp-uniform
+          if (nb >= g.lddl || row0 >= g.M) continue;                  // warp-uniform
+          if (nb + 32 <= g.N) {
+            // (softmax - onehot) * scale with the scale folded into the exponent: 5 instructions per logit
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j;
-            const float x = v[j] + __uint_as_float(r[j]);
-            const bool in = row_ok && n < g.N;
-            cnt += (in && x > tl);
-            const float p = ex2(fmaf(x, LOG2E, -lse2));
-            v[j] = in ? (p - (n == (int)tgt ? 1.f : 0.f)) * g.scale : 0.f;   // zeros = K padding of the next GEMMs
-          }
-          if (g.dL) {
-            __syncwarp();
-            xpose_write(xbuf, lane, v);
-            __syncwarp();
-            const int n4 = nb + 4 * (lane & 7);
+            for (int j = 0; j < 32; ++j) {
+              const float x = v[j] + __uint_as_float(r[j]);
+              cnt += (x > tl);
+              v[j] = ex2(fmaf(x, LOG2E, escale));
+            }
+            if (tgt >= nb && tgt < nb + 32) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = row0 + 4 * i + (lane >> 3);
-              const float4 x = xpose_read(xbuf, lane, i);
-              if (rr >= g.M || n4 >= g.lddl) continue;
-              __nv_bfloat16* dst = g.dL + (int64_t)rr * g.lddl + n4;
-              if (n4 + 4 <= g.lddl) {                       // lddl % 8 == 0 and base 16-byte aligned (host check)
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(x.x, x.y), p1 = __floats2bfloat162_rn(x.z, x.w);
-                uint2 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                *reinterpret_cast<uint2*>(dst) = pk;
-              } else {
-                const float e[4] = {x.x, x.y, x.z, x.w};
+              for (int j = 0; j < 32; ++j) if (nb + j == (int)tgt) v[j] -= g.scale;
+            }
+            if (!row_ok) {
+              cnt = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (n4 + k < g.lddl) dst[k] = __float2bfloat16(e[k]);
-              }
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = nb + j;
+              const float x = v[j] + __uint_as_float(r[j]);
+              const bool in = row_ok && n < g.N;
+              cnt += (in && x > tl);
+              const float p = ex2(fmaf(x, LOG2E, escale));
+              v[j] = in ? p - (n == (int)tgt ? g.scale : 0.f) : 0.f;    // zeros = K padding of the next GEMMs
             }
           }
+          if (g.dL) store_block_bf16(xbuf, lane, v, g.dL, g.lddl, row0, g.M, nb, (int)g.lddl, true);
         }
         if (g.above && cnt) atomicAdd(g.above + row, cnt);
       }
@@ -812,7 +879,7 @@ extern "C" int32_t sn_vocab_nll_bwd(int64_t N, int64_t V, int64_t H, const void*
   g.M = (int)N; g.N = (int)V; g.K = (int)H; g.groups = 1; g.splits = 1;
   rc = make_maps(SN_OP_NT, N, V, H, Hb, ldh, Wb, ldw, 1, 0, 0, ta, tb, g);
   if (rc) return rc;
-  g.bias = bias; g.targets = targets; g.tlogit = (float*)tlogit; g.lse = lse; g.scale = grad_scale;
+  g.bias = bias; g.targets = targets; g.tlogit = (float*)tlogit; g.lse = lse; g.scale = grad_scale; g.scale_log2 = log2f(grad_scale);
   g.dL = (__nv_bfloat16*)dL; g.lddl = dL ? lddl : V; g.above = above;
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch<EPI_GRAD>(ta, tb, g, st, "sn_vocab_nll_bwd");

@@ -53,7 +53,7 @@ class _HiddenFn(torch.autograd.Function):
         c = dec._run_forward(plan, captions, features, coins, mode, save=save)
         ctx.dec, ctx.c = dec, c
         ctx.need_dfeat = features is not None and features.requires_grad
-        return c.Hall
+        return c.top.Hall
 
     @staticmethod
     def backward(ctx, dHall):
@@ -242,6 +242,8 @@ class _DecoderBase(nn.Module):
             c.Hb = torch.empty(N, H, dtype=torch.bfloat16, device=dev)
             c.Hpb = torch.empty(N, H, dtype=torch.bfloat16, device=dev) if save else None
             c.Hprev = None
+        c.upper = self._upper_layers_init(c, save)     # layers above the first (stack.py); [] for the reference models
+        c.top = c.upper[-1] if c.upper else c
 
         def run(t0, t1):
             h_init = None
@@ -253,6 +255,8 @@ class _DecoderBase(nn.Module):
             else:
                 ops.recur_fwd(self.cell, H, B, d["bs"], d["off"], t0, t1, c.XP, Whh, bhh, h_init, c.Hall,
                               c.Call, c.Hprev, c.gates, c_state)
+            if c.upper:
+                self._upper_layers_fwd(c, t0, t1)
 
         if all_tf:
             run(0, T)
@@ -275,7 +279,7 @@ class _DecoderBase(nn.Module):
                         # predicted = argmax C(h_{t-1})  (model.py:189-191), lowest index on ties
                         bp, rp = plan.bs[t - 1], plan.off[t - 1]
                         lg = torch.empty(bp, V, dtype=torch.float32, device=dev)
-                        ops.gemm(ops.OP_NT, c.Hall, out.weight, lg, bp, V, H, H, H, V, bias=out.bias,
+                        ops.gemm(ops.OP_NT, c.top.Hall, out.weight, lg, bp, V, H, H, H, V, bias=out.bias,
                                  a_off=rp * H)
                         ops.softmax_nll(lg, bp, V, argmax=am)
                         pred = am[:bp].to(torch.int32)
@@ -292,41 +296,52 @@ class _DecoderBase(nn.Module):
             c.X = c.XP = None
         return c
 
-    def _run_backward(self, c, dHall, gbuf, need_dfeat):
-        a = self.arena()
+    def _upper_layers_init(self, c, save):
+        return []
+
+    def _upper_layers_fwd(self, c, t0, t1):
+        pass
+
+    def _layer_bwd(self, c, cl, dHall, gbuf):
+        """Reverse-time recurrence of ONE layer (K3 backward), its recurrent weight / bias gradients and the
+        backward of its input projection.  ``cl`` holds the layer's saved activations (``c`` itself for the first
+        layer).  Returns the gradient w.r.t. the layer's input rows [N, Ein]."""
         plan = c.plan
         dev = dHall.device
         d = plan.dev(dev)
         H, N, B, T = self.hidden_size, plan.N, plan.B, plan.T
-        emb = self._emb()
-        E = emb.weight.shape[1]
-        Whh, _ = self._recurrent_weights()
+        L = getattr(cl, "layer", 0)
+        Whh, _ = self._recurrent_weights(L)
         dZ = torch.empty(N, 4 * H, dtype=torch.float32, device=dev)
         dh = torch.zeros(B, H, dtype=torch.float32, device=dev)
         dc = torch.zeros(B, H, dtype=torch.float32, device=dev)
-        gW, gbW = self._recurrent_grads(gbuf)
-        if c.Hpb is not None:
-            c.dZb = torch.empty(N, 4 * H, dtype=torch.bfloat16, device=dev)
-            ops.recur_bwd_bf16(self.cell, H, B, d["bs"], d["off"], 0, T, c.w16["Whh"], None, c.Call, c.gates, dHall,
-                               dZ, c.dZb, dh, dc)
+        gW, gbW = self._recurrent_grads(gbuf, L)
+        if cl.Hpb is not None:
+            cl.dZb = torch.empty(N, 4 * H, dtype=torch.bfloat16, device=dev)
+            ops.recur_bwd_bf16(self.cell, H, B, d["bs"], d["off"], 0, T, cl.w16["Whh"], None, cl.Call, cl.gates, dHall,
+                               dZ, cl.dZb, dh, dc)
             with torch.cuda.stream(self._fork()):
-                ops.gemm_bf16(ops.OP_TN, c.dZb, c.Hpb, 4 * H, H, N, 4 * H, H, C=gW, ldc=H)
+                ops.gemm_bf16(ops.OP_TN, cl.dZb, cl.Hpb, 4 * H, H, N, 4 * H, H, C=gW, ldc=H)
                 ops.colsum(dZ, N, 4 * H, 4 * H, gbW)
-            dX = self._input_projection_bwd(c, dZ, gbuf)
-            out = self._embedding_bwd(c, dX, gbuf, need_dfeat)
-            self._join()
-            return out
-        ops.recur_bwd(self.cell, H, B, d["bs"], d["off"], 0, T, Whh, None, c.Call, c.gates, dHall, dZ, dh, dc)
+            return self._input_projection_bwd(cl, dZ, gbuf)
+        ops.recur_bwd(self.cell, H, B, d["bs"], d["off"], 0, T, Whh, None, cl.Call, cl.gates, dHall, dZ, dh, dc)
         # dW_hh = dZ^T Hprev ; d b_hh = colsum(dZ)
         if self.bf16:
-            c.dZb = ops.to_bf16_padded(dZ)
-            Hpb = ops.to_bf16_padded(c.Hprev)
-            ops.gemm_bf16(ops.OP_TN, c.dZb, Hpb, 4 * H, H, N, 4 * H, H, C=gW, ldc=H)
+            cl.dZb = ops.to_bf16_padded(dZ)
+            Hpb = ops.to_bf16_padded(cl.Hprev)
+            ops.gemm_bf16(ops.OP_TN, cl.dZb, Hpb, 4 * H, H, N, 4 * H, H, C=gW, ldc=H)
         else:
-            ops.gemm(ops.OP_TN, dZ, c.Hprev, gW, 4 * H, H, N, 4 * H, H, H)
+            ops.gemm(ops.OP_TN, dZ, cl.Hprev, gW, 4 * H, H, N, 4 * H, H, H)
         ops.colsum(dZ, N, 4 * H, 4 * H, gbW)
-        dX = self._input_projection_bwd(c, dZ, gbuf)
-        return self._embedding_bwd(c, dX, gbuf, need_dfeat)
+        return self._input_projection_bwd(cl, dZ, gbuf)
+
+    def _run_backward(self, c, dHall, gbuf, need_dfeat):
+        for cl in reversed(c.upper):
+            dHall = self._layer_bwd(c, cl, dHall, gbuf)      # d(input of layer l) = d(hidden states of layer l-1)
+        dX = self._layer_bwd(c, c, dHall, gbuf)
+        out = self._embedding_bwd(c, dX, gbuf, need_dfeat)
+        self._join()
+        return out
 
     def _embedding_bwd(self, c, dX, gbuf, need_dfeat):
         plan = c.plan
@@ -470,12 +485,12 @@ class _DecoderBase(nn.Module):
                                      "pass: inputs captions[:, :-1], targets packed captions[:, 1:])")
                 targets = self._default_targets(captions, plan, True)
             denom = float(n_global if n_global is not None else N)
-            row_loss, argmax, top5, logits, dLb = self._vocab_nll(c.Hall, c.Hb, targets, denom, backward)
+            row_loss, argmax, top5, logits, dLb = self._vocab_nll(c.top.Hall, c.top.Hb, targets, denom, backward)
             loss = torch.empty(1, dtype=torch.float32, device=dev)
             ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
             if backward:
                 gbuf = self._grad_target(c.grad_names + list(self._out_names()))
-                dHall = self._vocab_backward(c.Hall, logits, gbuf, c.Hb, dLb)
+                dHall = self._vocab_backward(c.top.Hall, logits, gbuf, c.top.Hb, dLb)
                 if grad_hook is not None and gbuf is self.arena().gflat:
                     self._join()
                     grad_hook(list(self._out_names()))       # bucket 0 is final: overlap its all-reduce
@@ -552,25 +567,31 @@ class DecoderFactoredLSTM(_DecoderBase):
     def _out_names(self):
         return ("C.weight", "C.bias")
 
-    def _stack(self, pre, shape, grad=False, gbuf=None, bias=False):
-        names = [pre + g + (".bias" if bias else ".weight") for g in GATES]
+    @staticmethod
+    def _lp(layer):
+        """Parameter-name prefix of stack layer ``layer`` (the first layer keeps the reference names)."""
+        return "" if layer == 0 else "l%d_" % layer
+
+    def _stack(self, pre, shape, grad=False, gbuf=None, bias=False, layer=0):
+        names = [self._lp(layer) + pre + g + (".bias" if bias else ".weight") for g in GATES]
         if gbuf is not None:
             return self._gview(gbuf, names, shape)
         return self.arena().block(names, shape, grad=grad)
 
-    def _style_stack(self, mode, shape, gbuf=None, bias=False):
-        names = [style_attr(mode, g) + (".bias" if bias else ".weight") for g in GATES]
+    def _style_stack(self, mode, shape, gbuf=None, bias=False, layer=0):
+        names = [self._lp(layer) + style_attr(mode, g) + (".bias" if bias else ".weight") for g in GATES]
         if gbuf is not None:
             return self._gview(gbuf, names, shape)
         return self.arena().block(names, shape)
 
-    def _recurrent_weights(self):
+    def _recurrent_weights(self, layer=0):
         H = self.hidden_size
-        return self._stack("W_", (4 * H, H)), self._stack("W_", (4 * H,), bias=True)
+        return self._stack("W_", (4 * H, H), layer=layer), self._stack("W_", (4 * H,), bias=True, layer=layer)
 
-    def _recurrent_grads(self, gbuf):
+    def _recurrent_grads(self, gbuf, layer=0):
         H = self.hidden_size
-        return self._stack("W_", (4 * H, H), gbuf=gbuf), self._stack("W_", (4 * H,), gbuf=gbuf, bias=True)
+        return (self._stack("W_", (4 * H, H), gbuf=gbuf, layer=layer),
+                self._stack("W_", (4 * H,), gbuf=gbuf, bias=True, layer=layer))
 
     def _seq_grad_names(self, mode):
         names = ["B.weight"]
@@ -593,9 +614,10 @@ class DecoderFactoredLSTM(_DecoderBase):
             c.A1 = torch.empty(n, 4 * F, dtype=torch.float32, device=dev)
             c.A2 = torch.empty(n, 4 * F, dtype=torch.float32, device=dev)
         A1, A2 = c.__dict__.get("A1"), c.__dict__.get("A2")
-        Vc, bV = self._stack("V_", (4 * F, Ein)), self._stack("V_", (4 * F,), bias=True)
-        Sc, bS = self._style_stack(mode, (4 * F, F)), self._style_stack(mode, (4 * F,), bias=True)
-        Uc, bU = self._stack("U_", (4 * H, F)), self._stack("U_", (4 * H,), bias=True)
+        L = getattr(c, "layer", 0)
+        Vc, bV = self._stack("V_", (4 * F, Ein), layer=L), self._stack("V_", (4 * F,), bias=True, layer=L)
+        Sc, bS = self._style_stack(mode, (4 * F, F), layer=L), self._style_stack(mode, (4 * F,), bias=True, layer=L)
+        Uc, bU = self._stack("U_", (4 * H, F), layer=L), self._stack("U_", (4 * H,), bias=True, layer=L)
         if self.bf16:
             w16 = c.__dict__.setdefault("w16", {})
             if "V" not in w16:
@@ -628,12 +650,16 @@ class DecoderFactoredLSTM(_DecoderBase):
         N, Ein = dZ.shape[0], c.Ein
         dev = dZ.device
         mode = c.mode
-        Vc = self._stack("V_", (4 * F, Ein))
-        Sc = self._style_stack(mode, (4 * F, F))
-        Uc = self._stack("U_", (4 * H, F))
-        gV, gbV = self._stack("V_", (4 * F, Ein), gbuf=gbuf), self._stack("V_", (4 * F,), gbuf=gbuf, bias=True)
-        gS, gbS = self._style_stack(mode, (4 * F, F), gbuf=gbuf), self._style_stack(mode, (4 * F,), gbuf=gbuf, bias=True)
-        gU, gbU = self._stack("U_", (4 * H, F), gbuf=gbuf), self._stack("U_", (4 * H,), gbuf=gbuf, bias=True)
+        L = getattr(c, "layer", 0)
+        Vc = self._stack("V_", (4 * F, Ein), layer=L)
+        Sc = self._style_stack(mode, (4 * F, F), layer=L)
+        Uc = self._stack("U_", (4 * H, F), layer=L)
+        gV, gbV = (self._stack("V_", (4 * F, Ein), gbuf=gbuf, layer=L),
+                   self._stack("V_", (4 * F,), gbuf=gbuf, bias=True, layer=L))
+        gS, gbS = (self._style_stack(mode, (4 * F, F), gbuf=gbuf, layer=L),
+                   self._style_stack(mode, (4 * F,), gbuf=gbuf, bias=True, layer=L))
+        gU, gbU = (self._stack("U_", (4 * H, F), gbuf=gbuf, layer=L),
+                   self._stack("U_", (4 * H,), gbuf=gbuf, bias=True, layer=L))
         if self.bf16:
             return self._input_projection_bwd_bf16(c, dZ, gV, gbV, gS, gbS, gU, gbU)
         # U stage: dU_g = dZ_g^T A2_g ; dbU = colsum(dZ) ; dA2_g = dZ_g U_g
@@ -742,11 +768,11 @@ class DecoderRNN(_DecoderBase):
     def _out_names(self):
         return ("linear.weight", "linear.bias")
 
-    def _recurrent_weights(self):
+    def _recurrent_weights(self, layer=0):
         self.arena()
         return self.lstm.weight_hh, self.lstm.bias_hh
 
-    def _recurrent_grads(self, gbuf):
+    def _recurrent_grads(self, gbuf, layer=0):
         H = self.hidden_size
         return self._gview(gbuf, ["lstm.weight_hh"], (4 * H, H)), self._gview(gbuf, ["lstm.bias_hh"], (4 * H,))
 

@@ -414,6 +414,7 @@ class DecoderFactoredLSTMAtt(_AttBase):
 
     # reuse the non-attention factored helpers
     from .decoders import DecoderFactoredLSTM as _F
+    _lp = staticmethod(_F._lp)
     _stack = _F._stack
     _style_stack = _F._style_stack
     _recurrent_weights = _F._recurrent_weights

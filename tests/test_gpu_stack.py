@@ -1,0 +1,153 @@
+"""GPU parity of the multi-layer FactoredLSTM stack (BASELINE.json configs[3]) against
+ (a) tests/golden/stack3.npz -- UNMODIFIED reference DecoderFactoredLSTM objects composed by oracle/stack.py
+     (oracle/make_golden_stack.py), fp32 mode <= 1e-5, greedy arg-max ids bit-exact, and
+ (b) the oracle port at configs[3] dimensions (F = 1024, 3 layers) in bf16 mode <= 2e-2."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _layer_sds(rec, L, prefix="sd.", dtype=torch.float32):
+    out = []
+    for l in range(L):
+        pre = "%s%d." % (prefix, l)
+        out.append({k[len(pre):]: torch.from_numpy(v).to(dtype) if v.dtype.kind == "f" else torch.from_numpy(v)
+                    for k, v in rec.items() if k.startswith(pre)})
+    return out
+
+
+def _build(rec, dropout=0.0):
+    import icei_b200 as sn
+    V, E, H, F, L = (int(rec["meta." + k]) for k in ("V", "E", "H", "F", "L"))
+    m = sn.DecoderFactoredLSTMStack(E, H, F, V, L, dropout=dropout, max_seq_length=12)
+    m.load_layer_state_dicts(_layer_sds(rec, L))
+    return m.cuda(), L
+
+
+def _inputs(rec):
+    cap = torch.from_numpy(rec["in.captions"]).cuda()
+    lens = [int(x) for x in rec["in.lengths"]]
+    feats = torch.from_numpy(rec["in.features"]).float().cuda()
+    return cap, lens, feats
+
+
+def _golden_name(n):
+    """stack parameter name -> (layer, reference name)"""
+    if n.startswith("l") and n[1].isdigit() and n[2] == "_":
+        return int(n[1]), n[3:]
+    return 0, n
+
+
+def _check_grads(dec, rec, pre):
+    want = {k[len(pre):] for k in rec if k.startswith(pre)}
+    got = set()
+    for n, p in dec.named_parameters():
+        if p.grad is None:
+            continue
+        l, rn = _golden_name(n)
+        key = "%d.%s" % (l, rn)
+        got.add(key)
+        assert rel_l2(p.grad.cpu(), rec[pre + key]) < TOL, n
+    assert got == want, "set of parameters with a gradient"
+
+
+def test_stack_golden_forward_backward():
+    from oracle import port
+    rec = load_golden("stack3")
+    dec, L = _build(rec)
+    dec.train()
+    cap, lens, feats0 = _inputs(rec)
+    tgt = port.pack_targets(cap.cpu(), lens).cuda()
+    for mode in ("factual", "sad"):
+        dec.zero_grad()
+        feats = feats0.clone().requires_grad_(True)
+        random.seed(1234)
+        out = dec(cap, lens, feats, teacher_forcing_ratio=1.0, mode=mode)
+        loss = torch.nn.functional.cross_entropy(out, tgt)
+        loss.backward()
+        assert rel_l2(out.detach().cpu(), rec["tf1.logits." + mode]) < TOL
+        assert abs(loss.item() - float(rec["tf1.loss." + mode])) < TOL * abs(float(rec["tf1.loss." + mode]))
+        assert rel_l2(feats.grad.cpu(), rec["tf1.dfeatures." + mode]) < TOL
+        _check_grads(dec, rec, "tf1.grad.%s." % mode)
+        with torch.no_grad():
+            random.seed(1234)
+            out0 = dec(cap, lens, feats0, teacher_forcing_ratio=0.0, mode=mode)
+        assert rel_l2(out0.cpu(), rec["tf0.logits." + mode]) < TOL
+        assert np.array_equal(out0.argmax(1).cpu().numpy(), rec["tf0.argmax." + mode])
+        dec.zero_grad()
+        random.seed(1234)
+        out5 = dec(cap, lens, feats0, teacher_forcing_ratio=0.5, mode=mode)
+        torch.nn.functional.cross_entropy(out5, tgt).backward()
+        assert rel_l2(out5.detach().cpu(), rec["tf05.logits." + mode]) < TOL
+        _check_grads(dec, rec, "tf05.grad.%s." % mode)
+
+
+def test_stack_multitask_adam_schedule():
+    """forward_loss + two FusedClampAdam objects alternating factual / emotion passes over the same stack
+    (train_multitask.py:192-235) == reference clip_gradient + torch.optim.Adam after 4 steps."""
+    import icei_b200 as sn
+    rec = load_golden("stack3")
+    dec, L = _build(rec)
+    dec.train()
+    cap, lens, feats = _inputs(rec)
+    opt_a = sn.FusedClampAdam(dec, lr=2e-4, grad_clip=0.5)
+    opt_b = sn.FusedClampAdam(dec, lr=5e-4, grad_clip=0.5)
+    loss = None
+    for opt, mode in [(opt_a, "factual"), (opt_b, "sad"), (opt_a, "factual"), (opt_b, "happy")]:
+        dec.zero_grad()
+        random.seed(1234)
+        loss, _ = dec.forward_loss(cap, lens, feats, teacher_forcing_ratio=1.0, mode=mode)
+        opt.step()
+    assert abs(loss.item() - float(rec["adam4.loss_last"])) < TOL * abs(float(rec["adam4.loss_last"]))
+    for n, p in dec.named_parameters():
+        l, rn = _golden_name(n)
+        assert rel_l2(p.detach().cpu(), rec["adam4.sd.%d.%s" % (l, rn)]) < TOL, n
+
+
+def _oracle_stack(E, H, F, V, L, seed):
+    from oracle import port
+    torch.manual_seed(seed)
+    return [port.DecoderFactoredLSTM(E if l == 0 else H, H, F, V, 1, dropout=0.0) for l in range(L)]
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_stack_config4_dimensions_vs_oracle(precision, tol):
+    """3 layers, factored 1024, hidden 512, embed 300 (configs[3]) on a reduced batch / vocabulary the CPU oracle
+    finishes in seconds; loss and every gradient within the north-star tolerance of the mode."""
+    import icei_b200 as sn
+    from oracle import port
+    from oracle.stack import stack_forward
+    E, H, F, V, L, B, T = 300, 512, 1024, 1000, 3, 24, 9
+    layers = _oracle_stack(E, H, F, V, L, 3)
+    dec = sn.DecoderFactoredLSTMStack(E, H, F, V, L, dropout=0.0)
+    dec.load_layer_state_dicts([l.state_dict() for l in layers])
+    dec = dec.cuda().set_precision(precision)
+    dec.train()
+    cap, lens, feats = port.synthetic_batch(B, T, V, E=E, ragged=True, seed=9)
+    tgt = port.pack_targets(cap, lens)
+    random.seed(1234)
+    out = stack_forward(layers, cap, lens, feats, teacher_forcing_ratio=1.0, mode="happy")
+    loss = torch.nn.functional.cross_entropy(out, tgt)
+    loss.backward()
+    random.seed(1234)
+    loss_g, stats = dec.forward_loss(cap.cuda(), lens, feats.cuda(), teacher_forcing_ratio=1.0, mode="happy")
+    assert abs(loss_g.item() - loss.item()) < tol * abs(loss.item())
+    if precision == "fp32":
+        assert torch.equal(stats["argmax"].cpu(), out.argmax(1))
+    ref = {}
+    for l, layer in enumerate(layers):
+        for n, p in layer.named_parameters():
+            if p.grad is not None:
+                ref[("" if l == 0 else "l%d_" % l) + n] = p.grad
+    got = {n for n, p in dec.named_parameters() if p.grad is not None}
+    assert got == set(ref)
+    for n, p in dec.named_parameters():
+        if p.grad is not None:
+            assert rel_l2(p.grad.cpu(), ref[n]) < tol, n

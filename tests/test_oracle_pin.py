@@ -164,3 +164,44 @@ def test_port_matches_live_reference_fp32(name, mod, cls):
                 outs.append((m(cap, lens, feats, teacher_forcing_ratio=tf, **mkw),))
         for x, y in zip(*outs):
             assert torch.equal(x, y) or rel_l2(x.detach(), y.detach()) < 1e-6
+
+
+def test_stack_oracle_matches_reference_composition():
+    """oracle/stack.py over ORACLE-PORT layers == the same composition over unmodified reference layers
+    (tests/golden/stack3.npz, oracle/make_golden_stack.py): logits, loss, gradients (fp64, 1e-10), greedy ids."""
+    import random
+    from oracle import port
+    from oracle.stack import stack_forward
+    rec = load_golden("stack3")
+    V, E, H, F, L = (int(rec["meta." + k]) for k in ("V", "E", "H", "F", "L"))
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        layers = [port.DecoderFactoredLSTM(E if l == 0 else H, H, F, V, 1, dropout=0.0, max_seq_length=12) for l in range(L)]
+        for l, layer in enumerate(layers):
+            pre = "sd.%d." % l
+            layer.load_state_dict({k[len(pre):]: torch.from_numpy(v) for k, v in rec.items() if k.startswith(pre)})
+        cap = torch.from_numpy(rec["in.captions"])
+        lens = [int(x) for x in rec["in.lengths"]]
+        feats = torch.from_numpy(rec["in.features"])
+        tgt = port.pack_targets(cap, lens)
+        for mode in ("factual", "sad"):
+            for layer in layers:
+                layer.zero_grad()
+            random.seed(1234)
+            out = stack_forward(layers, cap, lens, feats, teacher_forcing_ratio=1.0, mode=mode)
+            loss = torch.nn.functional.cross_entropy(out, tgt)
+            loss.backward()
+            assert rel_l2(out.detach(), rec["tf1.logits." + mode]) < 1e-10
+            assert abs(loss.item() - float(rec["tf1.loss." + mode])) < 1e-10
+            for l, layer in enumerate(layers):
+                for n, p in layer.named_parameters():
+                    key = "tf1.grad.%s.%d.%s" % (mode, l, n)
+                    if p.grad is not None and key in rec:
+                        assert rel_l2(p.grad, rec[key]) < 1e-10, key
+            with torch.no_grad():
+                random.seed(1234)
+                out0 = stack_forward(layers, cap, lens, feats, teacher_forcing_ratio=0.0, mode=mode)
+            assert np.array_equal(out0.argmax(1).numpy(), rec["tf0.argmax." + mode])
+    finally:
+        torch.set_default_dtype(old)
