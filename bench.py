@@ -202,8 +202,9 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as fh:
             d = json.load(fh)
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+        burst = d.get("bf16_tflops", 1590.0)
+        return d.get("hbm_gbs", 6650.0), (burst, d.get("bf16_tflops_sustained", burst)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, (1590.0, 1590.0), "fallback (B200_PROFILING.md)"
 
 
 def run_gpu(args):
@@ -352,7 +353,7 @@ def run_gpu(args):
         if WORKLOAD == "att":
             roof, kernels = None, None
         else:
-            roof, kernels = kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src)
+            roof, kernels = kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src, tf_peak)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -380,7 +381,7 @@ def run_gpu(args):
 NCU_TRAFFIC = {"recur_fwd_bf16_kernel": 18.07e6 + 0.12e6, "recur_bwd_bf16_kernel": 26.11e6 + 0.12e6}
 
 
-def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src):
+def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src, tf_peak=(1638.2, 1368.6)):
     """Per-kernel device time (CUDA events, L2 flushed) of the HBM-bound kernels of one step, the roofline
     object for the dominant one, and a large-batch point of the same kernel (B=4096/GPU) where the serial
     chain no longer hides the memory system.  ALGORITHMIC bytes per launch as defined in DESIGN.md."""
@@ -415,7 +416,30 @@ def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src):
         gates = torch.empty(N, 4 * H, **f32)
         dH = torch.randn(N, H, **f32)
         dZ = torch.empty(N, 4 * H, **f32)
-        if bf16:
+        if bf16 and B >= ops.RECUR_GEMM_MIN_BATCH[0]:
+            # what the decoder runs at this batch size: one tcgen05 GEMM per step, cell fused into the epilogue
+            Hb, dZb = torch.empty(N, H, **b16), torch.empty(N, 4 * H, **b16)
+            Wil = ops.cast_gate_interleave(Whh)
+            dcar = torch.empty(B, H, **f32)
+
+            def fwd():
+                ops.recur_fwd_gemm(dec.cell, H, B, plan, XP, Wil, bhh, Hall, Hb, Call, gates)
+
+            def bwd():
+                ops.recur_bwd_gemm(dec.cell, H, B, plan, Wb, Call, gates, dH, dZ, dZb, dcar)
+            fwd(); bwd()
+            torch.cuda.synchronize()
+            graphs = []
+            for fn in (fwd, bwd):          # replayed from a CUDA graph, like the training step
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph):
+                    fn()
+                graphs.append(gph)
+            fwd, bwd = graphs[0].replay, graphs[1].replay
+            by_f = N * H * (16 + 8 + 16 + 4 + 4) + 4 * H * H * 2
+            by_b = N * H * (16 + 16 + 8 + 4 + 8 + 8) + 4 * H * H * 2
+            names = ("recur_fwd_gemm(cell epilogue) x%d steps" % TT, "recur_bwd_gemm(cell epilogue) x%d steps" % TT)
+        elif bf16:
             Hb, Hpb, dZb = torch.empty(N, H, **b16), torch.empty(N, H, **b16), torch.empty(N, 4 * H, **b16)
 
             def fwd():
@@ -470,17 +494,72 @@ def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src):
     kernels["adam_clamp_kernel"] = {"ms": t_a, "alg_bytes": npar * 28, "gbs": npar * 28 / t_a / 1e6}
     del logits, m_, v_, pcopy, gcopy
     big = recur_pair([T] * 4096)
+    huge = recur_pair([T] * 16384) if bf16 else None
     dom = max((k for k in kernels if k.startswith("recur")), key=lambda k: kernels[k]["ms"])
     ach = kernels[dom]["gbs"]
+    bigdom = max(big, key=lambda k: big[k]["ms"])
     roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
             "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC.get(dom) if len(lens) == 96 else None,
             "traffic_source": "ncu --set full, profiles/r1_f_ncu_full_k3_bf16_B96_raw.csv", "peak_source": peak_src,
             "note": "latency-bound at B=96: T serial steps, each with an inter-SM exchange through L2 (DESIGN.md 4). "
-                    "Same kernel at B=4096/GPU (bandwidth regime): %.0f GB/s = %.2f of peak"
-                    % (big[dom]["gbs"], big[dom]["gbs"] / hbm_peak),
-            "large_batch": {"B": 4096, "achieved": big[dom]["gbs"], "frac": big[dom]["gbs"] / hbm_peak}}
+                    "At B=4096/GPU the recurrence runs as per-step tcgen05 GEMMs with the cell in the epilogue "
+                    "(throughput regime): %.0f GB/s = %.2f of peak" % (big[bigdom]["gbs"], big[bigdom]["gbs"] / hbm_peak),
+            "large_batch": {"B": 4096, "kernel": bigdom, "achieved": big[bigdom]["gbs"],
+                            "frac": big[bigdom]["gbs"] / hbm_peak}}
     kernels["large_batch_B4096"] = big
+    if huge:
+        kernels["large_batch_B16384"] = huge
+        for k in huge:
+            huge[k]["frac_of_hbm_peak"] = huge[k]["gbs"] / hbm_peak
+    for k in big:
+        big[k]["frac_of_hbm_peak"] = big[k]["gbs"] / hbm_peak
+    if bf16:
+        kernels["tensor"] = gemm_tensor_points(timeit, dev, tf_peak)
     return roof, kernels
+
+
+def gemm_tensor_points(timeit, dev, tf_peak):
+    """Tensor-pipe side of the path: the CTA-pair tcgen05 GEMM (sn_gemm2.cu) on the projection / vocabulary shapes of
+    configs[1] at B=96 (N=1920 tokens: latency regime) and at B=4096 (N=81920: throughput regime).  TFLOP/s on
+    2*M*N*K and the fraction of the MEASURED cuBLAS bf16 peaks (burst: a kernel timed alone; sustained: back to back for
+    seconds, power-limited); ncu sm__pipe_tensor_cycles_active of the same kernels:
+    profiles/r1_i_ncu_full_gemm_pair_N40960_raw.csv."""
+    import torch
+    from icei_b200 import ops
+    out = {"peak_tflops_burst": tf_peak[0], "peak_tflops_sustained": tf_peak[1]}
+    b16 = dict(dtype=torch.bfloat16, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+
+    def point(t, fl):
+        tf = fl / t / 1e9
+        return {"ms": t, "tflops": tf, "frac_of_burst_peak": tf / tf_peak[0], "frac_of_sustained_peak": tf / tf_peak[1]}
+
+    for ntok in (T * B_PER_GPU, T * 4096):
+        tag = "N%d" % ntok
+        X = torch.randn(ntok, 304, **b16)
+        Vw = torch.randn(4 * F, 304, **b16)
+        A1 = torch.empty(ntok, 4 * F, **b16)
+        t = timeit(lambda: ops.gemm_bf16(ops.OP_NT, X, Vw, ntok, 4 * F, 304, 304, 304, Cb=A1, ldcb=4 * F, impl="pair"))
+        fl = 2.0 * ntok * 4 * F * 304
+        out["V_stage_" + tag] = point(t, fl)
+        Hb = torch.randn(ntok, H, **b16)
+        Cw = (torch.randn(V, H, **f32) / 8).bfloat16()
+        bias = torch.zeros(V, **f32)
+        tgt = torch.randint(0, V, (ntok,), device=dev)
+        tl, lse, rl = torch.empty(ntok, **f32), torch.empty(ntok, **f32), torch.empty(ntok, **f32)
+        am = torch.empty(ntok, dtype=torch.int64, device=dev)
+        ab = torch.zeros(ntok, dtype=torch.int32, device=dev)
+        dLb = torch.empty(ntok, V, **b16)
+        fl = 2.0 * ntok * V * H
+        t = timeit(lambda: ops.vocab_nll_fwd(Hb, Cw, bias, tgt, ntok, V, H, tl, lse, rl, am, ab))
+        out["vocab_nll_fwd_" + tag] = dict(point(t, fl), hbm_bytes_logits=0)
+        t = timeit(lambda: ops.vocab_nll_bwd(Hb, Cw, bias, tgt, ntok, V, H, tl, lse, 1.0 / ntok, dLb, ab, None))
+        out["vocab_nll_bwd_" + tag] = point(t, fl)
+        dH = torch.empty(ntok, H, **f32)
+        t = timeit(lambda: ops.gemm_bf16(ops.OP_NN, dLb, Cw, ntok, H, V, V, H, C=dH, ldc=H, impl="pair"))
+        out["vocab_dH_" + tag] = point(t, fl)
+        del X, A1, Hb, dLb, dH
+    return out
 
 
 def main():

@@ -37,6 +37,10 @@ SIGNATURES = {
     "sn_recur_bwd": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sn_recur_fwd_bf16": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _I32] + [_P] * 12),
     "sn_recur_bwd_bf16": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _I32] + [_P] * 11),
+    "sn_cast_bf16_gate_interleave": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _P]),
+    "sn_recur_fwd_gemm": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "sn_recur_hprev": (_I32, [_P, _P, _P, _P, _I64, _I64, _P, _P]),
+    "sn_recur_bwd_gemm": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sn_softmax_nll": (_I32, [_P, _I64, _I64, _I64, _P, _P, _P, _I64, _F, _P, _P, _P, _I64, _P]),
     "sn_colsum_bf16": (_I32, [_P, _I64, _I64, _I64, _P, _F, _P]),
     "sn_reduce_sum": (_I32, [_P, _I64, _F, _P, _I32, _P]),

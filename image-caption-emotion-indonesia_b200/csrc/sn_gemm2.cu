@@ -26,6 +26,9 @@
 //   EPI_PARTIAL split-K: raw fp32 partial tile into ws[split][M][N]; sn_gemm2_bf16 reduces them afterwards
 //   EPI_STATS   vocabulary projection fused with log-softmax statistics: per (row, 64-column chunk) max, sum of
 //               exp, arg-max; the target's logit.  Logits never leave the SM.
+//   EPI_CELL_FWD / EPI_CELL_BWD  one time step of the recurrence for LARGE batches (K3 in the throughput regime): the
+//               step's h_{t-1} W_hh^T (resp. dZ_{t+1} W_hh) GEMM with the LSTM / FactoredLSTM cell (resp. its
+//               backward) fused into the epilogue -- see sn_recur_*_gemm below.
 //   EPI_GRAD    recomputed logits -> (softmax - onehot) * scale written as the bf16 operand of the two backward
 //               GEMMs, plus the count of logits above the target's (top-k accuracy).
 #include <cuda.h>
@@ -39,22 +42,28 @@ namespace {
 
 constexpr int BMC = 128;            // rows of A per CTA
 constexpr int BM = 2 * BMC;         // tile rows per CTA pair
-constexpr int BNC = 128;            // rows of B staged per CTA
-constexpr int BN = 2 * BNC;         // tile columns per CTA pair
+constexpr int BN = 256;             // default tile columns per CTA pair (each CTA stages half of them)
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 5;
-constexpr int A_BYTES = BMC * BK * 2, B_BYTES = BNC * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;                   // 32 KB per CTA per stage
+constexpr int A_BYTES = BMC * BK * 2;
 constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * BN;                       // 512: the whole TMEM of the SM
 constexpr int EPI_WARPS = 16;
 constexpr int NTHREADS = 64 + 32 * EPI_WARPS;                    // 576
-constexpr int EPI_COLS = BN / (EPI_WARPS / 4);                   // 64 accumulator columns per epilogue warp
 constexpr int XPOSE_BYTES = 32 * 32 * 4;                         // per-warp transpose buffer (32x32 fp32, swizzled)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * XPOSE_BYTES + 1024 + 256;
+// Tile geometry as a function of the pair tile width BN_ (256: the GEMMs; 128: the recurrence backward step, whose
+// N = H = 512 would otherwise give too few tiles to occupy the SM pairs)
+template <int BN_>
+struct Geo {
+  static constexpr int BNC = BN_ / 2;                            // rows of B staged per CTA
+  static constexpr int B_BYTES = BNC * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;          // 32 KB (BN 256) / 24 KB (BN 128) per CTA per stage
+  static constexpr int STAGES = BN_ == 256 ? 5 : 6;
+  static constexpr int TMEM_COLS = ACC_STAGES * BN_;             // 512 (the whole TMEM of the SM) / 256
+  static constexpr int EPI_COLS = BN_ / (EPI_WARPS / 4);         // accumulator columns per epilogue warp: 64 / 32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * XPOSE_BYTES + 1024 + 256;
+};
 
-enum { EPI_STORE = 0, EPI_PARTIAL = 1, EPI_STATS = 2, EPI_GRAD = 3 };
+enum { EPI_STORE = 0, EPI_PARTIAL = 1, EPI_STATS = 2, EPI_GRAD = 3, EPI_CELL_FWD = 4, EPI_CELL_BWD = 5 };
 
 struct TmaSet { CUtensorMap m[4]; };
 
@@ -75,6 +84,13 @@ struct G2Args {
   float scale, scale_log2;
   __nv_bfloat16* dL; int64_t lddl; // [M, lddl] gradient w.r.t. the logits
   int32_t* above;                  // [M] number of logits strictly above the target's
+  // EPI_CELL_FWD / EPI_CELL_BWD (one recurrence step; rows = samples of the step, all row-indexed pointers are
+  // already offset to the step's first packed row)
+  int cell, Hdim;
+  const float* xp; const float* bhh; const float* c_prev;      // [M,4H], [4H], [M,H] (NULL = zeros)
+  float* h_out; __nv_bfloat16* hb_out; float* c_out; float* gates_out;
+  const float* gates_in; const float* c_cur; const float* dh_in; float* dc_carry;   // bwd: [M,4H], [M,H], [M,H], [M,H]
+  float* dz_out; __nv_bfloat16* dzb_out;                        // bwd: [M,4H] fp32 (optional) and bf16
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -180,6 +196,25 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 constexpr float LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2(-LOG2E * x)));
+  return r;
+}
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {      // 32-byte aligned row piece
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
 
 // ---- per-warp 32x32 fp32 transpose through shared memory -------------------------------------------------------
 // write side: thread = row, 8 x STS.128; element (row, c) lives at row*32 + ((c/4) ^ (row & 7))*4 + c%4 -> the 8 rows of
@@ -248,7 +283,7 @@ __device__ __forceinline__ void store_block_bf16(float* xbuf, int lane, const fl
 
 struct Tile { int m0, n0, grp, split, kb0, nkb; };
 
-__device__ __forceinline__ Tile decode_tile(const G2Args& g, int tile, int tiles_m, int tiles_n, int total_kb) {
+__device__ __forceinline__ Tile decode_tile(const G2Args& g, int tile, int tiles_m, int tiles_n, int total_kb, int bn) {
   // Tile order: the fastest-varying index walks the SMALLER operand, so the ~74 tiles in flight share a few tiles of
   // the larger operand (read from HBM once) while the smaller one stays L2-resident (M >> N: all n-tiles of an
   // m-tile run side by side; measured before: A re-fetched from HBM behind the streaming output writes).
@@ -264,7 +299,7 @@ __device__ __forceinline__ Tile decode_tile(const G2Args& g, int tile, int tiles
   t.split = rest % g.splits;
   t.grp = rest / g.splits;
   t.m0 = mt * BM;
-  t.n0 = nt * BN;
+  t.n0 = nt * bn;
   if (g.splits == 1) {
     t.kb0 = 0; t.nkb = total_kb;
   } else {
@@ -283,9 +318,11 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
   *reinterpret_cast<uint4*>(dst) = pk;
 }
 
-template <int EPI>
+template <int EPI, int BN_>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)   // 18 warps (allocated as 20) x 96 registers
 gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSet tma_b, const G2Args g) {
+  constexpr int BNC = Geo<BN_>::BNC, B_BYTES = Geo<BN_>::B_BYTES, STAGE_BYTES = Geo<BN_>::STAGE_BYTES;
+  constexpr int STAGES = Geo<BN_>::STAGES, TMEM_COLS = Geo<BN_>::TMEM_COLS, EPI_COLS = Geo<BN_>::EPI_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* xpose0 = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
@@ -297,7 +334,7 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN_ - 1) / BN_;
   const int total_tiles = tiles_m * tiles_n * g.groups * g.splits;
   const int total_kb = (g.K + BK - 1) / BK;
 
@@ -324,7 +361,7 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
       int s = 0;
       uint32_t ph = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
-        const Tile t = decode_tile(g, tile, tiles_m, tiles_n, total_kb);
+        const Tile t = decode_tile(g, tile, tiles_m, tiles_n, total_kb, BN_);
         const CUtensorMap* map_a = &tma_a.m[t.grp];
         const CUtensorMap* map_b = &tma_b.m[t.grp];
         const int m0 = t.m0 + (int)rank * BMC, n0 = t.n0 + (int)rank * BNC;
@@ -344,7 +381,7 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
             tma_load_2d_2sm(sb, map_b, lbar, k0, n0);
           } else {
             tma_load_2d_2sm(sb, map_b, lbar, n0, k0);
-            tma_load_2d_2sm(sb + B_BYTES / 2, map_b, lbar, n0 + 64, k0);
+            if (BNC == 128) tma_load_2d_2sm(sb + B_BYTES / 2, map_b, lbar, n0 + 64, k0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -359,20 +396,20 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
       // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major bit15, b_major bit16,
       // N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)g.a_mn_major << 15) |
-                             ((uint32_t)g.b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)g.b_mn_major << 16) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       // K-major: advance 32 B inside the 128 B swizzle row; SBO = 1024 B between 8-row groups.
       // MN-major: advance two 8-k-row groups (2 KB); LBO = 8 KB between the two 64-wide MN chunks.
       const uint64_t adesc0 = g.a_mn_major ? make_desc(smem_base, A_BYTES / 2, 1024) : make_desc(smem_base, 16, 1024);
-      const uint64_t bdesc0 = g.b_mn_major ? make_desc(smem_base + A_BYTES, B_BYTES / 2, 1024)
+      const uint64_t bdesc0 = g.b_mn_major ? make_desc(smem_base + A_BYTES, BNC == 128 ? B_BYTES / 2 : 16, 1024)
                                            : make_desc(smem_base + A_BYTES, 16, 1024);
       const uint64_t astep = (g.a_mn_major ? 2048 : 32) >> 4, bstep = (g.b_mn_major ? 2048 : 32) >> 4;
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
-        const Tile t = decode_tile(g, tile, tiles_m, tiles_n, total_kb);
+        const Tile t = decode_tile(g, tile, tiles_m, tiles_n, total_kb, BN_);
         mbar_wait_cluster(tempty0 + 8 * as, aph ^ 1);      // epilogues of both CTAs drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN_);
         for (int kb = 0; kb < t.nkb; ++kb) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
@@ -396,15 +433,42 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
     const uint32_t tempty_leader0 = mapa(tempty0, 0);
     int acc_it = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs, ++acc_it) {
-      const Tile t = decode_tile(g, tile, tiles_m, tiles_n, total_kb);
+      const Tile t = decode_tile(g, tile, tiles_m, tiles_n, total_kb, BN_);
       const int as = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
+      if (EPI == EPI_CELL_FWD || EPI == EPI_CELL_BWD) {
+        // The cell epilogues are memory-bound and their operands do not depend on the accumulator: pull this warp's
+        // rows of XP / c / gates / dh into L2 now, while the MMAs of the tile are still running (the warp would
+        // otherwise just wait on the barrier below and then pay the full DRAM latency twice per tile).
+        const int H = g.Hdim;
+        const int prow0 = t.m0 + (int)rank * BMC + q * 32;
+        if (EPI == EPI_CELL_FWD) {
+          const int U0 = t.n0 >> 2;
+          for (int idx = lane; idx < 80; idx += 32) {
+            const int ph = idx / 40, rem = idx - ph * 40, k = rem / 5, a = rem - k * 5;
+            const int rr = prow0 + slice * 8 + k;
+            const float* p = a < 4 ? g.xp + (int64_t)rr * 4 * H + a * H + U0 + 32 * ph
+                                   : (g.c_prev ? g.c_prev + (int64_t)rr * H + U0 + 32 * ph : nullptr);
+            if (rr < g.M && p) prefetch_l2(p);
+          }
+        } else {
+          const int u0 = t.n0 + slice * EPI_COLS;
+          for (int idx = lane; idx < 32 * 8; idx += 32) {
+            const int rr = prow0 + (idx >> 3), a = idx & 7;
+            const float* p = a < 4 ? g.gates_in + (int64_t)rr * 4 * H + a * H + u0
+                           : a == 4 ? g.c_cur + (int64_t)rr * H + u0
+                           : a == 5 ? (g.c_prev ? g.c_prev + (int64_t)rr * H + u0 : nullptr)
+                           : a == 6 ? g.dh_in + (int64_t)rr * H + u0 : g.dc_carry + (int64_t)rr * H + u0;
+            if (rr < g.M && u0 < g.N && p) prefetch_l2(p);
+          }
+        }
+      }
       mbar_wait(tfull0 + 8 * as, aph);
       tc_fence_after();
       const int row0 = t.m0 + (int)rank * BMC + q * 32;     // first row of this warp's 32-row band
       const int row = row0 + lane;                          // the row this thread holds after tcgen05.ld
       const int ncol0 = t.n0 + slice * EPI_COLS;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + slice * EPI_COLS);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN_ + slice * EPI_COLS);
       const bool row_ok = row < g.M;
 
       if (EPI == EPI_STORE || EPI == EPI_PARTIAL) {
@@ -566,6 +630,145 @@ gemm2_kernel(const __grid_constant__ TmaSet tma_a, const __grid_constant__ TmaSe
         if (row_ok && ncol0 < g.N) {
           const int64_t o = (int64_t)row * g.nchunks + (ncol0 / EPI_COLS);
           g.pmax[o] = mx; g.psum[o] = se; g.pidx[o] = mi;
+        }
+      } else if (EPI == EPI_CELL_FWD) {
+        // Columns are GATE-INTERLEAVED 64 units at a time (sn_cast_bf16_gate_interleave): the 256-column tile holds the
+        // four gate pre-activations of units U0..U0+63, one gate per 64-column slice = per epilogue warp of a lane
+        // quadrant.  The four warps of a quadrant (same 32 rows) exchange their gates through shared memory, 32 units
+        // per phase, then each warp finishes 8 of the 32 rows with lane = unit: every global access of the cell update
+        // (XP, c, h, gates) is a full 128-byte row segment.  (One row per thread, as tcgen05.ld delivers the data,
+        // costs 32 cache lines per instruction and was LSU-bound at 3x the HBM time.)
+        const int H = g.Hdim;
+        const bool lstm = g.cell == SN_CELL_LSTM;
+        float* qbuf = xpose0 + q * (4 * 32 * 32);          // [4 gates][32 rows][32 units], swizzled rows
+        const int bar_id = 1 + q;
+        const int U0 = t.n0 >> 2;                            // first unit of this tile
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {
+          uint32_t r[32];
+          tmem_ld32_issue(taddr + 32 * ph, r);
+          tmem_ld_wait(r);
+          if (ph == 1) {      // accumulator fully read: hand the TMEM stage back before the memory-bound part
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * as);
+          }
+          {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            xpose_write(qbuf + slice * 1024, lane, v);       // gate `slice`, row = lane
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          const int unit = U0 + 32 * ph + lane;
+          float bh[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) bh[k] = g.bhh ? __ldg(g.bhh + k * H + unit) : 0.f;
+          const int sw = lane >> 2, lo = lane & 3;
+#pragma unroll 8
+          for (int k = 0; k < 8; ++k) {
+            const int rl = slice * 8 + k;                    // row inside the quadrant
+            const int rr = row0 + rl;
+            if (rr >= g.M) continue;
+            const float* xp = g.xp + (int64_t)rr * 4 * H + unit;
+            const int so = rl * 32 + ((sw ^ (rl & 7)) << 2) + lo;
+            const float z0 = qbuf[so] + __ldg(xp) + bh[0];
+            const float z1 = qbuf[1024 + so] + __ldg(xp + H) + bh[1];
+            const float z2 = qbuf[2048 + so] + __ldg(xp + 2 * H) + bh[2];
+            const float z3 = qbuf[3072 + so] + __ldg(xp + 3 * H) + bh[3];
+            const float cp = g.c_prev ? __ldg(g.c_prev + (int64_t)rr * H + unit) : 0.f;
+            // gate blocks: FactoredLSTM (i, f, o, c~), h = o*c ; LSTM (i, f, g, o), h = o*tanh(c)
+            const float gi = fast_sigmoid(z0), gf = fast_sigmoid(z1);
+            const float g2 = lstm ? fast_tanh(z2) : fast_sigmoid(z2);
+            const float g3 = lstm ? fast_sigmoid(z3) : fast_tanh(z3);
+            const float go = lstm ? g3 : g2, gc = lstm ? g2 : g3;
+            const float c = gf * cp + gi * gc;
+            const float h = lstm ? go * fast_tanh(c) : go * c;
+            g.hb_out[(int64_t)rr * H + unit] = __float2bfloat16(h);
+            if (g.h_out) g.h_out[(int64_t)rr * H + unit] = h;
+            if (g.c_out) g.c_out[(int64_t)rr * H + unit] = c;
+            if (g.gates_out) {
+              float* gp = g.gates_out + (int64_t)rr * 4 * H + unit;
+              gp[0] = gi; gp[H] = gf; gp[2 * H] = g2; gp[3 * H] = g3;
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        }
+        continue;                                            // TMEM stage already released above
+      } else if (EPI == EPI_CELL_BWD) {
+        // accumulator = dh_rec[row, unit] = dZ_{t+1} W_hh.  Transposed through shared memory so that a lane holds 4
+        // consecutive units of a row: all loads / stores of the cell backward are float4 and row-contiguous
+        // (4 rows x 128 B per instruction).
+        const int H = g.Hdim;
+        const bool lstm = g.cell == SN_CELL_LSTM;
+#pragma unroll 1
+        for (int c0 = 0; c0 < EPI_COLS; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32_issue(taddr + c0, r);
+          tmem_ld_wait(r);
+          if (row0 >= g.M || ncol0 + c0 >= g.N) continue;       // warp-uniform
+          {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            __syncwarp();
+            xpose_write(xbuf, lane, v);
+            __syncwarp();
+          }
+          const int u4 = ncol0 + c0 + 4 * (lane & 7);
+#pragma unroll 2
+          for (int i = 0; i < 8; ++i) {
+            const int rr = row0 + 4 * i + (lane >> 3);
+            const float4 acc4 = xpose_read(xbuf, lane, i);
+            if (rr >= g.M) continue;
+            const float* gp = g.gates_in + (int64_t)rr * 4 * H + u4;
+            const float4 g0 = *reinterpret_cast<const float4*>(gp), g1 = *reinterpret_cast<const float4*>(gp + H);
+            const float4 g2 = *reinterpret_cast<const float4*>(gp + 2 * H), g3 = *reinterpret_cast<const float4*>(gp + 3 * H);
+            const float4 cc4 = *reinterpret_cast<const float4*>(g.c_cur + (int64_t)rr * H + u4);
+            const float4 cp4 = g.c_prev ? *reinterpret_cast<const float4*>(g.c_prev + (int64_t)rr * H + u4)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 dh4 = *reinterpret_cast<const float4*>(g.dh_in + (int64_t)rr * H + u4);
+            float4 dcar4 = *reinterpret_cast<const float4*>(g.dc_carry + (int64_t)rr * H + u4);
+            const float acc[4] = {acc4.x, acc4.y, acc4.z, acc4.w};
+            const float gt0[4] = {g0.x, g0.y, g0.z, g0.w}, gt1[4] = {g1.x, g1.y, g1.z, g1.w};
+            const float gt2[4] = {g2.x, g2.y, g2.z, g2.w}, gt3[4] = {g3.x, g3.y, g3.z, g3.w};
+            const float cc[4] = {cc4.x, cc4.y, cc4.z, cc4.w}, cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
+            const float dh[4] = {dh4.x, dh4.y, dh4.z, dh4.w};
+            float dcar[4] = {dcar4.x, dcar4.y, dcar4.z, dcar4.w};
+            float zz[4][4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float dht = dh[e] + acc[e];
+              const float gi = gt0[e], gf = gt1[e];
+              const float go = lstm ? gt3[e] : gt2[e], gc = lstm ? gt2[e] : gt3[e];
+              float d_o, dc;
+              if (lstm) {
+                const float tc = fast_tanh(cc[e]);
+                d_o = dht * tc;
+                dc = dcar[e] + dht * go * (1.f - tc * tc);
+              } else {
+                d_o = dht * cc[e];
+                dc = dcar[e] + dht * go;
+              }
+              const float di = dc * gc, df = dc * cp[e], dg = dc * gi;
+              dcar[e] = dc * gf;
+              const float zi = di * gi * (1.f - gi), zf = df * gf * (1.f - gf);
+              const float zo = d_o * go * (1.f - go), zc = dg * (1.f - gc * gc);
+              zz[0][e] = zi; zz[1][e] = zf;
+              zz[2][e] = lstm ? zc : zo; zz[3][e] = lstm ? zo : zc;
+            }
+            *reinterpret_cast<float4*>(g.dc_carry + (int64_t)rr * H + u4) = make_float4(dcar[0], dcar[1], dcar[2], dcar[3]);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              if (g.dz_out)
+                *reinterpret_cast<float4*>(g.dz_out + (int64_t)rr * 4 * H + qq * H + u4) =
+                    make_float4(zz[qq][0], zz[qq][1], zz[qq][2], zz[qq][3]);
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(zz[qq][0], zz[qq][1]), p1 = __floats2bfloat162_rn(zz[qq][2], zz[qq][3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+              *reinterpret_cast<uint2*>(g.dzb_out + (int64_t)rr * 4 * H + qq * H + u4) = pk;
+            }
+          }
         }
       } else {  // EPI_GRAD
         const int64_t tgt = row_ok ? g.targets[row] : -1;
@@ -738,8 +941,10 @@ int32_t encode_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t row
   return 0;
 }
 
+// a_rows: valid rows of a K-major A (rows beyond are zero-filled by TMA; default M)
 int32_t make_maps(int32_t op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb,
-                  int32_t batch, int64_t strideA, int64_t strideB, TmaSet& ta, TmaSet& tb, G2Args& g) {
+                  int32_t batch, int64_t strideA, int64_t strideB, TmaSet& ta, TmaSet& tb, G2Args& g, int64_t a_rows = -1, int bn = BN) {
+  if (a_rows < 0) a_rows = M;
   g.a_mn_major = (op == SN_OP_TN) ? 1 : 0;
   g.b_mn_major = (op == SN_OP_NT) ? 0 : 1;
   const __nv_bfloat16* Ab = (const __nv_bfloat16*)A;
@@ -747,27 +952,27 @@ int32_t make_maps(int32_t op, int64_t M, int64_t N, int64_t K, const void* A, in
   for (int i = 0; i < 4; ++i) {
     int gi = i < batch ? i : 0;
     int32_t rc;
-    if (!g.a_mn_major) rc = encode_2d(&ta.m[i], Ab + gi * strideA, K, M, lda, BK, BMC);     // A[M,K]
+    if (!g.a_mn_major) rc = encode_2d(&ta.m[i], Ab + gi * strideA, K, a_rows, lda, BK, BMC);     // A[M,K]
     else rc = encode_2d(&ta.m[i], Ab + gi * strideA, M, K, lda, 64, BK);                      // A stored [K,M]
     if (rc) return rc;
-    if (!g.b_mn_major) rc = encode_2d(&tb.m[i], Bb + gi * strideB, K, N, ldb, BK, BNC);     // B[N,K]
+    if (!g.b_mn_major) rc = encode_2d(&tb.m[i], Bb + gi * strideB, K, N, ldb, BK, bn / 2);  // B[N,K]
     else rc = encode_2d(&tb.m[i], Bb + gi * strideB, N, K, ldb, 64, BK);                      // B stored [K,N]
     if (rc) return rc;
   }
   return 0;
 }
 
-template <int EPI>
+template <int EPI, int BN_ = BN>
 int32_t launch(const TmaSet& ta, const TmaSet& tb, const G2Args& g, cudaStream_t st, const char* what) {
   static thread_local bool configured = false;
   if (!configured) {
-    SN_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SN_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<BN_>::SMEM_BYTES));
     configured = true;
   }
-  const int64_t tiles = (int64_t)((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.groups * g.splits;
+  const int64_t tiles = (int64_t)((g.M + BM - 1) / BM) * ((g.N + BN_ - 1) / BN_) * g.groups * g.splits;
   int64_t pairs = sn::dev_info().sm_count / 2;
   if (tiles < pairs) pairs = tiles;
-  gemm2_kernel<EPI><<<(unsigned)(2 * pairs), NTHREADS, SMEM_BYTES, st>>>(ta, tb, g);
+  gemm2_kernel<EPI, BN_><<<(unsigned)(2 * pairs), NTHREADS, Geo<BN_>::SMEM_BYTES, st>>>(ta, tb, g);
   return sn::check_launch(what);
 }
 
@@ -887,6 +1092,129 @@ extern "C" int32_t sn_vocab_nll_bwd(int64_t N, int64_t V, int64_t H, const void*
   if (top5hit) {
     rank_hit_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(above, N, 5, top5hit);
     return sn::check_launch("sn_vocab_nll_bwd(top5)");
+  }
+  return 0;
+}
+
+// ---- K3, large-batch form: one tcgen05 GEMM per time step with the cell fused into the epilogue ------------------
+namespace {
+
+// Wp[ublk*256 + q*64 + uu, :] = bf16(W[q*H + ublk*64 + uu, :])  (rows of the four gate blocks interleaved 64 units at a
+// time: a 256-column accumulator tile = all four gates of 64 units, one gate per epilogue warp of a lane quadrant)
+__global__ void gate_interleave_kernel(const float* __restrict__ W, int64_t H, int64_t K, int64_t ldw,
+                                       __nv_bfloat16* __restrict__ Wp, int64_t ldp) {
+  const int64_t total = 4 * H * ldp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / ldp, k = i - n * ldp;
+    const int64_t ublk = n >> 8, q = (n >> 6) & 3, uu = n & 63;
+    const int64_t src_row = q * H + ublk * 64 + uu;
+    Wp[n * ldp + k] = __float2bfloat16(k < K ? W[src_row * ldw + k] : 0.f);
+  }
+}
+
+// Hprevb[row(b,t), :] = Hb[row(b,t-1), :] (zeros at t = 0): the h_{t-1} operand of dW_hh = dZ^T Hprev
+__global__ void hprev_gather_kernel(const __nv_bfloat16* __restrict__ Hb, const int32_t* __restrict__ row_b,
+                                    const int32_t* __restrict__ row_t, const int32_t* __restrict__ off, int64_t N,
+                                    int64_t H, __nv_bfloat16* __restrict__ Hprevb) {
+  const int64_t per_row = H >> 3;                      // 16-byte pieces
+  const int64_t total = N * per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / per_row, c = (i - r * per_row) << 3;
+    const int t = row_t[r];
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (t > 0) v = *reinterpret_cast<const uint4*>(Hb + ((int64_t)off[t - 1] + row_b[r]) * H + c);
+    *reinterpret_cast<uint4*>(Hprevb + r * H + c) = v;
+  }
+}
+
+}  // namespace
+
+extern "C" int32_t sn_cast_bf16_gate_interleave(const float* W, int64_t H, int64_t K, int64_t ldw, void* Wp, int64_t ldp,
+                                                void* stream) {
+  SN_REQUIRE(W && Wp && H > 0 && (H % 64) == 0 && K > 0 && ldw >= K && ldp >= K && (ldp % 8) == 0,
+             "sn_cast_bf16_gate_interleave: bad arguments");
+  int64_t blocks = (4 * H * ldp + 255) / 256;
+  int64_t cap = (int64_t)sn::dev_info().sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  gate_interleave_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(W, H, K, ldw, (__nv_bfloat16*)Wp, ldp);
+  return sn::check_launch("sn_cast_bf16_gate_interleave");
+}
+
+extern "C" int32_t sn_recur_fwd_gemm(int32_t cell, int64_t H, int64_t B, const int32_t* bs_host, const int32_t* off_host,
+                                     int32_t T, const float* XP, const void* Wp_bf16, const float* bhh, float* Hall,
+                                     void* Hb, float* Call, float* gates, const void* zeros_bf16, void* stream) {
+  SN_REQUIRE(cell == SN_CELL_FACTORED || cell == SN_CELL_LSTM, "sn_recur_fwd_gemm: bad cell %d", cell);
+  SN_REQUIRE(H > 0 && (H % 64) == 0 && B > 0 && T > 0, "sn_recur_fwd_gemm: hidden size must be a multiple of 64");
+  SN_REQUIRE(bs_host && off_host && XP && Wp_bf16 && Hb && Call && zeros_bf16, "sn_recur_fwd_gemm: null argument");
+  int32_t rc = check_operands("sn_recur_fwd_gemm", Hb, H, Wp_bf16, H, 0, 0);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* Hbb = (__nv_bfloat16*)Hb;
+  for (int t = 0; t < T; ++t) {
+    const int64_t M = bs_host[t], r0 = off_host[t];
+    if (M <= 0) break;
+    TmaSet ta, tb;
+    G2Args g = {};
+    g.M = (int)M; g.N = (int)(4 * H); g.K = (int)H; g.groups = 1; g.splits = 1;
+    // A = h_{t-1} rows of the samples still alive (zeros before the first step)
+    const void* A = t == 0 ? zeros_bf16 : (const void*)(Hbb + (int64_t)off_host[t - 1] * H);
+    rc = make_maps(SN_OP_NT, M, 4 * H, H, A, H, Wp_bf16, H, 1, 0, 0, ta, tb, g);
+    if (rc) return rc;
+    g.cell = cell; g.Hdim = (int)H;
+    g.xp = XP + r0 * 4 * H; g.bhh = bhh;
+    g.c_prev = t == 0 ? nullptr : Call + (int64_t)off_host[t - 1] * H;
+    g.h_out = Hall ? Hall + r0 * H : nullptr; g.hb_out = Hbb + r0 * H;
+    g.c_out = Call + r0 * H; g.gates_out = gates ? gates + r0 * 4 * H : nullptr;
+    rc = launch<EPI_CELL_FWD>(ta, tb, g, st, "sn_recur_fwd_gemm");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int32_t sn_recur_hprev(const void* Hb, const int32_t* row_b, const int32_t* row_t, const int32_t* offsets,
+                                  int64_t N, int64_t H, void* Hprevb, void* stream) {
+  SN_REQUIRE(Hb && row_b && row_t && offsets && Hprevb && N >= 0 && H > 0 && (H % 8) == 0, "sn_recur_hprev: bad arguments");
+  if (N == 0) return 0;
+  int64_t blocks = (N * (H >> 3) + 255) / 256;
+  int64_t cap = (int64_t)sn::dev_info().sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  hprev_gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)Hb, row_b, row_t, offsets, N, H,
+                                                                          (__nv_bfloat16*)Hprevb);
+  return sn::check_launch("sn_recur_hprev");
+}
+
+extern "C" int32_t sn_recur_bwd_gemm(int32_t cell, int64_t H, int64_t B, const int32_t* bs_host, const int32_t* off_host,
+                                     int32_t T, const void* Whh_bf16, const float* Call, const float* gates,
+                                     const float* dHall, float* dZ, void* dZb, float* dc_carry, const void* zeros_bf16,
+                                     void* stream) {
+  SN_REQUIRE(cell == SN_CELL_FACTORED || cell == SN_CELL_LSTM, "sn_recur_bwd_gemm: bad cell %d", cell);
+  SN_REQUIRE(H > 0 && (H % 64) == 0 && B > 0 && T > 0, "sn_recur_bwd_gemm: hidden size must be a multiple of 64");
+  SN_REQUIRE(bs_host && off_host && Whh_bf16 && Call && gates && dHall && dZb && dc_carry && zeros_bf16,
+             "sn_recur_bwd_gemm: null argument");
+  int32_t rc = check_operands("sn_recur_bwd_gemm", dZb, 4 * H, Whh_bf16, H, 0, 0);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  SN_CUDA(cudaMemsetAsync(dc_carry, 0, sizeof(float) * (size_t)B * (size_t)H, st));
+  __nv_bfloat16* dZbb = (__nv_bfloat16*)dZb;
+  for (int t = T - 1; t >= 0; --t) {
+    const int64_t M = bs_host[t], r0 = off_host[t];
+    if (M <= 0) continue;
+    const int64_t Mnext = (t + 1 < T) ? bs_host[t + 1] : 0;
+    TmaSet ta, tb;
+    G2Args g = {};
+    g.M = (int)M; g.N = (int)H; g.K = (int)(4 * H); g.groups = 1; g.splits = 1;
+    // A = dZ_{t+1} rows of the samples alive at t+1; the other samples of step t (and all of the last step) read
+    // zeros: rows past the tensor map's extent are zero-filled by TMA
+    const void* A = Mnext > 0 ? (const void*)(dZbb + (int64_t)off_host[t + 1] * 4 * H) : zeros_bf16;
+    rc = make_maps(SN_OP_NN, M, H, 4 * H, A, 4 * H, Whh_bf16, H, 1, 0, 0, ta, tb, g, Mnext > 0 ? Mnext : 1, 128);
+    if (rc) return rc;
+    g.cell = cell; g.Hdim = (int)H;
+    g.gates_in = gates + r0 * 4 * H; g.c_cur = Call + r0 * H;
+    g.c_prev = t == 0 ? nullptr : Call + (int64_t)off_host[t - 1] * H;
+    g.dh_in = dHall + r0 * H; g.dc_carry = dc_carry;
+    g.dz_out = dZ ? dZ + r0 * 4 * H : nullptr; g.dzb_out = dZbb + r0 * 4 * H;
+    rc = launch<EPI_CELL_BWD, 128>(ta, tb, g, st, "sn_recur_bwd_gemm");
+    if (rc) return rc;
   }
   return 0;
 }

@@ -245,16 +245,10 @@ class _DecoderBase(nn.Module):
         c.upper = self._upper_layers_init(c, save)     # layers above the first (stack.py); [] for the reference models
         c.top = c.upper[-1] if c.upper else c
 
+        c.c_state = c_state
+
         def run(t0, t1):
-            h_init = None
-            if t0 > 0:
-                h_init = c.Hall[plan.off[t0 - 1]:]
-            if use_tc:
-                ops.recur_fwd_bf16(self.cell, H, B, d["bs"], d["off"], t0, t1, c.XP, c.w16["Whh"], bhh, h_init,
-                                   c.Hall, c.Hb, c.Hpb, c.Call, c.gates, c_state)
-            else:
-                ops.recur_fwd(self.cell, H, B, d["bs"], d["off"], t0, t1, c.XP, Whh, bhh, h_init, c.Hall,
-                              c.Call, c.Hprev, c.gates, c_state)
+            self._recur_fwd(c, c, t0, t1)
             if c.upper:
                 self._upper_layers_fwd(c, t0, t1)
 
@@ -296,6 +290,34 @@ class _DecoderBase(nn.Module):
             c.X = c.XP = None
         return c
 
+    def _recur_fwd(self, c, cl, t0, t1):
+        """K3 forward of one layer over steps [t0, t1).  Two kernels behind one call: the persistent, latency-optimised
+        recurrence (any batch, any segment) and -- for whole teacher-forced sequences of >= ops.RECUR_GEMM_MIN_BATCH
+        samples in bf16 mode -- one tcgen05 GEMM per step with the cell fused into the epilogue (throughput regime)."""
+        plan = c.plan
+        d = plan.dev(cl.XP.device)
+        H, B, T = self.hidden_size, plan.B, plan.T
+        L = getattr(cl, "layer", 0)
+        Whh, bhh = self._recurrent_weights(L)
+        if cl.Hb is not None:
+            if t0 == 0 and t1 == T and B >= ops.RECUR_GEMM_MIN_BATCH[0] and H % 64 == 0:
+                if "Whh_il" not in cl.w16:
+                    cl.w16["Whh_il"] = ops.cast_gate_interleave(Whh)
+                if cl.Call is None:
+                    cl.Call = torch.empty(plan.N, H, dtype=torch.float32, device=cl.XP.device)
+                ops.recur_fwd_gemm(self.cell, H, B, plan, cl.XP, cl.w16["Whh_il"], bhh, cl.Hall, cl.Hb, cl.Call, cl.gates)
+                if cl.Hpb is not None:
+                    ops.recur_hprev(cl.Hb, d, plan.N, H, cl.Hpb)
+                cl.recur_gemm = True
+                return
+            h_init = cl.Hall[plan.off[t0 - 1]:] if t0 > 0 else None
+            ops.recur_fwd_bf16(self.cell, H, B, d["bs"], d["off"], t0, t1, cl.XP, cl.w16["Whh"], bhh, h_init,
+                               cl.Hall, cl.Hb, cl.Hpb, cl.Call, cl.gates, cl.c_state)
+        else:
+            h_init = cl.Hall[plan.off[t0 - 1]:] if t0 > 0 else None
+            ops.recur_fwd(self.cell, H, B, d["bs"], d["off"], t0, t1, cl.XP, Whh, bhh, h_init, cl.Hall,
+                          cl.Call, cl.Hprev, cl.gates, cl.c_state)
+
     def _upper_layers_init(self, c, save):
         return []
 
@@ -318,8 +340,11 @@ class _DecoderBase(nn.Module):
         gW, gbW = self._recurrent_grads(gbuf, L)
         if cl.Hpb is not None:
             cl.dZb = torch.empty(N, 4 * H, dtype=torch.bfloat16, device=dev)
-            ops.recur_bwd_bf16(self.cell, H, B, d["bs"], d["off"], 0, T, cl.w16["Whh"], None, cl.Call, cl.gates, dHall,
-                               dZ, cl.dZb, dh, dc)
+            if getattr(cl, "recur_gemm", False):
+                ops.recur_bwd_gemm(self.cell, H, B, plan, cl.w16["Whh"], cl.Call, cl.gates, dHall, dZ, cl.dZb, dc)
+            else:
+                ops.recur_bwd_bf16(self.cell, H, B, d["bs"], d["off"], 0, T, cl.w16["Whh"], None, cl.Call, cl.gates,
+                                   dHall, dZ, cl.dZb, dh, dc)
             with torch.cuda.stream(self._fork()):
                 ops.gemm_bf16(ops.OP_TN, cl.dZb, cl.Hpb, 4 * H, H, N, 4 * H, H, C=gW, ldc=H)
                 ops.colsum(dZ, N, 4 * H, 4 * H, gbW)

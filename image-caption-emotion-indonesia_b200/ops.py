@@ -294,6 +294,66 @@ def recur_bwd_bf16(cell, H, B, bs, off, t0, t1, Whh_b, c_init, Call, gates, dHal
                                   _stream()), "sn_recur_bwd_bf16")
 
 
+# ---- K3, large-batch form (one tcgen05 GEMM per step, cell fused into the epilogue) -----------------------------
+RECUR_GEMM_MIN_BATCH = [1024]      # samples per GPU from which the per-step GEMM form replaces the persistent kernel
+
+
+def _host_steps(plan):
+    hs = plan.__dict__.get("_host_steps")
+    if hs is None:
+        T = plan.T
+        hs = ((ctypes.c_int32 * T)(*[int(x) for x in plan.bs]), (ctypes.c_int32 * T)(*[int(x) for x in plan.off[:T]]))
+        plan.__dict__["_host_steps"] = hs
+    return hs
+
+
+_zeros_b16 = {}
+
+
+def _zeros_bf16(device, n):
+    z = _zeros_b16.get(device)
+    if z is None or z.numel() < n:
+        z = torch.zeros(n, dtype=torch.bfloat16, device=device)
+        _zeros_b16[device] = z
+    return z
+
+
+def cast_gate_interleave(W):
+    """bf16 copy of W_hh [4H, H] with the rows of the four gate blocks interleaved 64 units at a time."""
+    H4, K = W.shape
+    H = H4 // 4
+    Kp = (K + 7) // 8 * 8
+    out = torch.empty(H4, Kp, dtype=torch.bfloat16, device=W.device)
+    check(lib().sn_cast_bf16_gate_interleave(_ptr(_req(W)), H, K, W.stride(0), _ptr(out), Kp, _stream()),
+          "sn_cast_bf16_gate_interleave")
+    return out
+
+
+def recur_fwd_gemm(cell, H, B, plan, XP, Wp, bhh, Hall, Hb, Call, gates):
+    bs_h, off_h = _host_steps(plan)
+    z = _zeros_bf16(XP.device, max(B * H, 4 * H))
+    check(lib().sn_recur_fwd_gemm(cell, H, B, ctypes.cast(bs_h, ctypes.c_void_p), ctypes.cast(off_h, ctypes.c_void_p),
+                                  plan.T, _ptr(_req(XP)), _ptr(_req(Wp, torch.bfloat16)), _ptr(bhh), _ptr(Hall),
+                                  _ptr(_req(Hb, torch.bfloat16)), _ptr(_req(Call)), _ptr(gates), _ptr(z), _stream()),
+          "sn_recur_fwd_gemm")
+    LAUNCHES[0] += plan.T - 1
+
+
+def recur_hprev(Hb, d, N, H, Hprevb):
+    check(lib().sn_recur_hprev(_ptr(_req(Hb, torch.bfloat16)), _ptr(d["row_b"]), _ptr(d["row_t"]), _ptr(d["off"]), N, H,
+                               _ptr(_req(Hprevb, torch.bfloat16)), _stream()), "sn_recur_hprev")
+
+
+def recur_bwd_gemm(cell, H, B, plan, Whh_b, Call, gates, dHall, dZ, dZb, dc_carry):
+    bs_h, off_h = _host_steps(plan)
+    z = _zeros_bf16(dZb.device, max(B * H, 4 * H))
+    check(lib().sn_recur_bwd_gemm(cell, H, B, ctypes.cast(bs_h, ctypes.c_void_p), ctypes.cast(off_h, ctypes.c_void_p),
+                                  plan.T, _ptr(_req(Whh_b, torch.bfloat16)), _ptr(_req(Call)), _ptr(_req(gates)),
+                                  _ptr(_req(dHall)), _ptr(dZ), _ptr(_req(dZb, torch.bfloat16)), _ptr(_req(dc_carry)),
+                                  _ptr(z), _stream()), "sn_recur_bwd_gemm")
+    LAUNCHES[0] += plan.T
+
+
 def adam_clamp_dev(p, g, m, v, ranges, step_idx, steps_dev, lr_dev, coef_ws, beta1, beta2, eps, clip):
     """Clamp + Adam with step counters / learning rate in device memory (CUDA-graph replayable)."""
     n = len(ranges)

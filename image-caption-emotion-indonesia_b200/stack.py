@@ -121,8 +121,6 @@ class DecoderFactoredLSTMStack(DecoderFactoredLSTM):
         """Steps t0..t1 of every layer above the first: project layer l-1's hidden rows of the segment through
         U S V (K2), then one recurrence launch over the segment (K3)."""
         plan = c.plan
-        d = plan.dev(c.XP.device)
-        H, B = self.hidden_size, plan.B
         r0 = plan.off[t0]
         n = (plan.off[t1] if t1 < plan.T else plan.N) - r0
         below = c
@@ -132,14 +130,7 @@ class DecoderFactoredLSTMStack(DecoderFactoredLSTM):
             else:
                 cl.X = X = below.Hall
             self._input_projection(cl, X, c.mode, r0, n)
-            Whh, bhh = self._recurrent_weights(cl.layer)
-            h_init = cl.Hall[plan.off[t0 - 1]:] if t0 > 0 else None
-            if cl.Hb is not None:
-                ops.recur_fwd_bf16(self.cell, H, B, d["bs"], d["off"], t0, t1, cl.XP, cl.w16["Whh"], bhh, h_init,
-                                   cl.Hall, cl.Hb, cl.Hpb, cl.Call, cl.gates, cl.c_state)
-            else:
-                ops.recur_fwd(self.cell, H, B, d["bs"], d["off"], t0, t1, cl.XP, Whh, bhh, h_init, cl.Hall,
-                              cl.Call, cl.Hprev, cl.gates, cl.c_state)
+            self._recur_fwd(c, cl, t0, t1)
             below = cl
 
     # -- decode ----------------------------------------------------------------------------------------

@@ -167,6 +167,32 @@ int32_t sn_recur_bwd_bf16(int32_t cell, int64_t H, int64_t B, const int32_t* bat
                           const float* dHall, float* dZ, void* dZb, float* dh_carry, float* dc_carry,
                           void* ws, void* stream);
 
+/* K3 in the LARGE-BATCH regime (B >= ~1000 samples per GPU): one tcgen05 CTA-pair GEMM per time step with the
+ * cell fused into the epilogue, instead of the latency-optimised persistent kernel above.
+ * replaces the same call sites: forward_step's W_g(h) + gate math  stylenet/model.py:119-153, nn.LSTMCell nic/model.py:77
+ *   forward, step t:  Z = h_{t-1} Wp^T  (M = batch_sizes[t], N = 4H, K = H), epilogue adds XP_t + b_hh, applies the gate
+ *     nonlinearities, updates c, writes h_t (fp32 + bf16), c_t and the activated gates.  Wp = W_hh with the rows of the
+ *     four gate blocks interleaved 64 units at a time (sn_cast_bf16_gate_interleave): a 256-column accumulator tile
+ *     then holds all four gates of 64 units and the epilogue warps of a lane quadrant exchange them through shared
+ *     memory, so every global access of the cell update is a full 128-byte row segment.
+ *   backward, step t: dh_rec = dZ_{t+1} W_hh (M = batch_sizes[t], N = H, K = 4H; rows of samples that ended at t read
+ *     zeros), epilogue applies the cell backward and writes dZ_t (fp32 optional + bf16) and the carried dc.
+ * bs_host / off_host: HOST copies of batch_sizes / offsets (the host issues one launch per step).  Whole sequences
+ * only (t = 0..T-1, zero initial state).  zeros_bf16: >= max(B*H, 4H) zero bf16 elements.  H % 64 == 0. */
+int32_t sn_cast_bf16_gate_interleave(const float* W, int64_t H, int64_t K, int64_t ldw, void* Wp,
+                                     int64_t ldp, void* stream);
+int32_t sn_recur_fwd_gemm(int32_t cell, int64_t H, int64_t B, const int32_t* bs_host,
+                          const int32_t* off_host, int32_t T, const float* XP, const void* Wp_bf16,
+                          const float* bhh, float* Hall, void* Hb, float* Call, float* gates,
+                          const void* zeros_bf16, void* stream);
+/* Hprevb[row(b,t)] = Hb[row(b,t-1)] (zeros at t = 0): the bf16 h_{t-1} operand of dW_hh = dZ^T Hprev */
+int32_t sn_recur_hprev(const void* Hb, const int32_t* row_b, const int32_t* row_t,
+                       const int32_t* offsets, int64_t N, int64_t H, void* Hprevb, void* stream);
+int32_t sn_recur_bwd_gemm(int32_t cell, int64_t H, int64_t B, const int32_t* bs_host,
+                          const int32_t* off_host, int32_t T, const void* Whh_bf16, const float* Call,
+                          const float* gates, const float* dHall, float* dZ, void* dZb, float* dc_carry,
+                          const void* zeros_bf16, void* stream);
+
 /* ---- K5/K6: log-softmax + NLL (+ gradient) over logits, arg-max, top-5 ------------------------
  * replaces nn.CrossEntropyLoss (train_multitask.py:134,383), output.max(1) (model.py:190) and
  * utils.accuracy top-5 (utils.py:127-140).

@@ -121,3 +121,93 @@ def test_vocab_fused_nll(ops, N, V, H):
     above.zero_()
     ops.vocab_nll_bwd(Hb, Wb, bias, tgt, N, V, H, tl, lse, scale, dLb=None, above=above, top5hit=t5)
     assert torch.equal(above, want_above)
+
+
+@pytest.mark.parametrize("cell", [0, 1])
+@pytest.mark.parametrize("B,H,lengths", [(1100, 512, None), (700, 64, "ragged"), (1300, 256, "ragged")])
+def test_recurrence_gemm_form(ops, cell, B, H, lengths):
+    """Large-batch K3 (one CTA-pair GEMM per step, cell fused into the epilogue): forward against a float64 unroll with
+    the same bf16 roundings of W_hh / h, backward against the fp32 persistent kernel on the same saved activations."""
+    import icei_b200
+    T = 7
+    g = torch.Generator().manual_seed(B * 7 + H + cell + 100)
+    if lengths is None:
+        lengths = [T] * B
+    else:
+        lengths = sorted(torch.randint(2, T + 1, (B,), generator=g).tolist(), reverse=True)
+        lengths[0] = T
+    plan = icei_b200.get_plan(lengths)
+    d = plan.dev("cuda")
+    N, T = plan.N, plan.T
+    XP = (torch.randn(N, 4 * H, generator=g) * 0.7).cuda()
+    W = (torch.randn(4 * H, H, generator=g) / H ** 0.5).cuda()
+    Wb = W.bfloat16().contiguous()
+    Wil = ops.cast_gate_interleave(W)
+    # the interleaved shadow is a row permutation of the plain one
+    n = torch.arange(4 * H, device="cuda")
+    src = ((n >> 6) & 3) * H + (n >> 8) * 64 + (n & 63)
+    assert torch.equal(Wil, Wb[src])
+    bhh = (torch.randn(4 * H, generator=g) * 0.1).cuda()
+    dH = torch.randn(N, H, generator=g).cuda()
+    Hall = torch.empty(N, H, device="cuda"); Call = torch.empty(N, H, device="cuda")
+    Hb = torch.empty(N, H, device="cuda", dtype=torch.bfloat16); Hpb = torch.empty_like(Hb)
+    gates = torch.empty(N, 4 * H, device="cuda")
+    ops.recur_fwd_gemm(cell, H, B, plan, XP, Wil, bhh, Hall, Hb, Call, gates)
+    ops.recur_hprev(Hb, d, N, H, Hpb)
+    torch.cuda.synchronize()
+    w, b, xp = Wb.double().cpu(), bhh.double().cpu(), XP.double().cpu()
+    h = torch.zeros(B, H, dtype=torch.float64); c = torch.zeros(B, H, dtype=torch.float64)
+    hs, cs, hp = [], [], []
+    for t, bt in enumerate(plan.bs):
+        hq = h[:bt].bfloat16().double()
+        hp.append(hq)
+        z = xp[plan.off[t]:plan.off[t] + bt] + hq @ w.t() + b
+        if cell == 0:
+            i, f, o, gg = z[:, :H], z[:, H:2 * H], z[:, 2 * H:3 * H], z[:, 3 * H:]
+        else:
+            i, f, gg, o = z[:, :H], z[:, H:2 * H], z[:, 2 * H:3 * H], z[:, 3 * H:]
+        c = torch.sigmoid(f) * c[:bt] + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * (c if cell == 0 else torch.tanh(c))
+        hs.append(h); cs.append(c)
+    hall, call = torch.cat(hs, 0), torch.cat(cs, 0)
+    assert _rel(Hall.cpu(), hall) < 3e-3
+    assert _rel(Call.cpu(), call) < 3e-3
+    assert _rel(Hb.float().cpu(), hall) < 6e-3
+    assert _rel(Hpb.float().cpu(), torch.cat(hp, 0)) < 6e-3
+    # backward vs the fp32 persistent kernel on the SAME saved activations (only the dZ exchange is rounded)
+    dZ = torch.empty(N, 4 * H, device="cuda"); dZb = torch.empty(N, 4 * H, device="cuda", dtype=torch.bfloat16)
+    dc = torch.empty(B, H, device="cuda")
+    ops.recur_bwd_gemm(cell, H, B, plan, Wb, Call, gates, dH, dZ, dZb, dc)
+    dZ32 = torch.empty(N, 4 * H, device="cuda")
+    dh2 = torch.zeros(B, H, device="cuda"); dc2 = torch.zeros(B, H, device="cuda")
+    ops.recur_bwd(cell, H, B, d["bs"], d["off"], 0, T, Wb.float(), None, Call, gates, dH, dZ32, dh2, dc2)
+    assert _rel(dZ, dZ32) < 1e-2
+    assert _rel(dZb.float(), dZ32) < 1.5e-2
+    assert _rel(dc, dc2) < 1e-2
+
+
+def test_large_batch_training_step_uses_gemm_recurrence_and_matches():
+    """End to end at a batch above ops.RECUR_GEMM_MIN_BATCH: loss and gradients of the bf16 decoder with the per-step
+    GEMM recurrence == the same decoder forced onto the persistent kernel (both bf16 mode), within bf16 noise."""
+    import random
+    import icei_b200 as sn
+    from icei_b200 import ops
+    from oracle import port
+    E, H, F, V, B, T = 300, 512, 512, 1000, 1200, 6
+    torch.manual_seed(3)
+    dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0).cuda().set_precision("bf16")
+    dec.train()
+    cap, lens, feats = port.synthetic_batch(B, T, V, E=E, ragged=True, seed=4)
+    cap, feats = cap.cuda(), feats.cuda()
+    res = []
+    for thr in (10 ** 9, 1024):
+        ops.RECUR_GEMM_MIN_BATCH[0] = thr
+        dec.zero_grad()
+        random.seed(1)
+        loss, _ = dec.forward_loss(cap, lens, feats, teacher_forcing_ratio=1.0, mode="happy")
+        res.append((loss.item(), {n: p.grad.clone() for n, p in dec.named_parameters() if p.grad is not None}))
+    ops.RECUR_GEMM_MIN_BATCH[0] = 1024
+    assert abs(res[0][0] - res[1][0]) < 2e-3 * abs(res[0][0])
+    assert set(res[0][1]) == set(res[1][1])
+    for n in res[0][1]:
+        assert _rel(res[1][1][n], res[0][1][n]) < 2e-2, n
