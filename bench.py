@@ -573,10 +573,14 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--workload", default="factored", choices=["factored", "att", "nic", "stack3"])
+    ap.add_argument("--batch", type=int, default=None,
+                    help="samples per GPU (default: the BASELINE config, 96; e.g. 4096 = throughput regime, a supplementary point)")
     ap.add_argument("--segmented", action="store_true", help="force the 3-graph (data-parallel) replay form on one GPU")
     args = ap.parse_args()
-    global WORKLOAD
+    global WORKLOAD, B_PER_GPU
     WORKLOAD = args.workload
+    if args.batch:
+        B_PER_GPU = args.batch
     if args.impl == "reference":
         run_reference(args)
     else:
