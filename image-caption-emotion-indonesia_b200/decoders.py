@@ -235,6 +235,7 @@ class _DecoderBase(nn.Module):
         c_state = torch.zeros(B, H, dtype=torch.float32, device=dev)
         c.aux_argmax = None
         Whh, bhh = self._recurrent_weights()
+        c.Whh, c.bhh = Whh, bhh
         use_tc = self.bf16 and H % 32 == 0
         c.Hb = c.Hpb = None
         if use_tc:
@@ -297,8 +298,7 @@ class _DecoderBase(nn.Module):
         plan = c.plan
         d = plan.dev(cl.XP.device)
         H, B, T = self.hidden_size, plan.B, plan.T
-        L = getattr(cl, "layer", 0)
-        Whh, bhh = self._recurrent_weights(L)
+        Whh, bhh = cl.Whh, cl.bhh          # cached per forward: arena lookups are host work, this runs once per segment
         if cl.Hb is not None:
             if t0 == 0 and t1 == T and B >= ops.RECUR_GEMM_MIN_BATCH[0] and H % 64 == 0:
                 if "Whh_il" not in cl.w16:

@@ -109,9 +109,9 @@ class DecoderFactoredLSTMStack(DecoderFactoredLSTM):
             if self.bf16 and not use_tc:
                 cl.Xb = torch.empty(N, (H + 7) // 8 * 8, **b16)
             cl.Hb = cl.Hpb = None
+            cl.Whh, cl.bhh = self._recurrent_weights(l)
             if use_tc:
-                Whh, _ = self._recurrent_weights(l)
-                cl.w16["Whh"] = self._shadow(Whh)
+                cl.w16["Whh"] = self._shadow(cl.Whh)
                 cl.Hb = torch.empty(N, H, **b16)
                 cl.Hpb = torch.empty(N, H, **b16) if save else None
             upper.append(cl)
