@@ -26,11 +26,12 @@ SIGNATURES = {
     "sn_gemm_bf16": (_I32, [_I32, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _I64, _I64, _I64, _I64, _I64, _P]),
     "sn_gemm_bf16_splitk": (_I32, [_I32, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _I64, _I64, _I64, _I64, _I64, _I32, _P]),
     "sn_gemm2_ws_bytes": (_I64, [_I64, _I64, _I32, _I32]),
-    "sn_gemm2_bf16": (_I32, [_I32, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _I64, _I64, _I64, _I64, _I64, _I32, _P, _I64, _P]),
+    "sn_gemm2_bf16": (_I32, [_I32, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _F, _I32, _I64, _I64, _I64, _I64, _I64, _I32, _P, _I64, _I32, _P]),
     "sn_vocab_ws_bytes": (_I64, [_I64, _I64]),
     "sn_vocab_nll_fwd": (_I32, [_I64, _I64, _I64, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "sn_vocab_nll_bwd": (_I32, [_I64, _I64, _I64, _P, _I64, _P, _I64, _P, _P, _P, _P, _F, _P, _I64, _P, _P, _P]),
     "sn_cast_bf16": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P]),
+    "sn_cast_bf16_ex": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I32, _P]),
     "sn_colsum": (_I32, [_P, _I64, _I64, _I64, _P, _F, _P]),
     "sn_recur_ws_bytes": (_I64, [_I64, _I64]),
     "sn_recur_fwd": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

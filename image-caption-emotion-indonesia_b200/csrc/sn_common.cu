@@ -1,3 +1,5 @@
+#include <stdlib.h>
+
 #include "sn_common.cuh"
 
 #include <cuda.h>
@@ -43,6 +45,16 @@ const DevInfo& dev_info() {
   return g_info[dev];
 }
 
+}  // namespace sn
+
+namespace sn {
+bool recur_cooperative() {
+  static const bool coop = [] {
+    const char* e = getenv("SN_RECUR_COOP");
+    return e && e[0] == '1';
+  }();
+  return coop;
+}
 }  // namespace sn
 
 extern "C" {

@@ -21,6 +21,12 @@ struct DevInfo {
 };
 // immutable per-device attribute cache (std::call_once per device)
 const DevInfo& dev_info();
+// Launch mode of the persistent recurrence kernels.  Their CTAs exchange data through flags in global memory, so every
+// CTA of the grid must become resident.  The grid is sized to at most one CTA per SM and nothing that can occupy an SM
+// in this library waits on these kernels, so a plain launch always makes progress; it avoids the ~8-10 us per launch
+// that a cooperative launch costs inside a CUDA graph (timeline, profiles/r1_l).  SN_RECUR_COOP=1 forces cooperative
+// launches (the driver then guarantees co-residency, e.g. when other processes share the GPU).
+bool recur_cooperative();
 
 #define SN_REQUIRE(cond, ...)                         \
   do {                                                \

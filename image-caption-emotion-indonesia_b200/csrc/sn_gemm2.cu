@@ -963,7 +963,7 @@ int32_t make_maps(int32_t op, int64_t M, int64_t N, int64_t K, const void* A, in
 }
 
 template <int EPI, int BN_ = BN>
-int32_t launch(const TmaSet& ta, const TmaSet& tb, const G2Args& g, cudaStream_t st, const char* what) {
+int32_t launch(const TmaSet& ta, const TmaSet& tb, const G2Args& g, cudaStream_t st, const char* what, int max_pairs = 0) {
   static thread_local bool configured = false;
   if (!configured) {
     SN_CUDA(cudaFuncSetAttribute(gemm2_kernel<EPI, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<BN_>::SMEM_BYTES));
@@ -971,6 +971,7 @@ int32_t launch(const TmaSet& ta, const TmaSet& tb, const G2Args& g, cudaStream_t
   }
   const int64_t tiles = (int64_t)((g.M + BM - 1) / BM) * ((g.N + BN_ - 1) / BN_) * g.groups * g.splits;
   int64_t pairs = sn::dev_info().sm_count / 2;
+  if (max_pairs > 0 && max_pairs < pairs) pairs = max_pairs;     // leave SMs to kernels on other streams
   if (tiles < pairs) pairs = tiles;
   gemm2_kernel<EPI, BN_><<<(unsigned)(2 * pairs), NTHREADS, Geo<BN_>::SMEM_BYTES, st>>>(ta, tb, g);
   return sn::check_launch(what);
@@ -996,7 +997,8 @@ extern "C" int64_t sn_gemm2_ws_bytes(int64_t M, int64_t N, int32_t batch, int32_
 extern "C" int32_t sn_gemm2_bf16(int32_t op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                                  int64_t ldb, float* C, int64_t ldc, void* Cb, int64_t ldcb, const float* bias, float beta,
                                  int32_t batch, int64_t strideA, int64_t strideB, int64_t strideC, int64_t strideCb,
-                                 int64_t strideBias, int32_t splits, void* ws, int64_t ws_bytes, void* stream) {
+                                 int64_t strideBias, int32_t splits, void* ws, int64_t ws_bytes, int32_t max_pairs,
+                                 void* stream) {
   SN_REQUIRE(op >= 0 && op <= 2, "sn_gemm2_bf16: bad op %d", op);
   SN_REQUIRE(batch >= 1 && batch <= 4, "sn_gemm2_bf16: 1..4 groups supported, got %d", batch);
   SN_REQUIRE(M >= 0 && N >= 0 && K > 0, "sn_gemm2_bf16: bad dims");
@@ -1015,12 +1017,12 @@ extern "C" int32_t sn_gemm2_bf16(int32_t op, int64_t M, int64_t N, int64_t K, co
   g.C = C; g.Cb = (__nv_bfloat16*)Cb; g.ldc = ldc; g.ldcb = ldcb; g.bias = bias; g.beta = beta;
   g.strideC = strideC; g.strideCb = strideCb; g.strideBias = strideBias;
   cudaStream_t st = (cudaStream_t)stream;
-  if (splits == 1) return launch<EPI_STORE>(ta, tb, g, st, "sn_gemm2_bf16");
+  if (splits == 1) return launch<EPI_STORE>(ta, tb, g, st, "sn_gemm2_bf16", max_pairs);
   SN_REQUIRE((N % 4) == 0, "sn_gemm2_bf16: split-K needs N %% 4 == 0");
   SN_REQUIRE(ws && ws_bytes >= sn_gemm2_ws_bytes(M, N, batch, splits), "sn_gemm2_bf16: split-K work space too small");
   SN_REQUIRE(((uintptr_t)ws & 15) == 0, "sn_gemm2_bf16: work space must be 16-byte aligned");
   g.ws = (float*)ws;
-  rc = launch<EPI_PARTIAL>(ta, tb, g, st, "sn_gemm2_bf16(split-K)");
+  rc = launch<EPI_PARTIAL>(ta, tb, g, st, "sn_gemm2_bf16(split-K)", max_pairs);
   if (rc) return rc;
   for (int gi = 0; gi < batch; ++gi) {
     int64_t blocks = (M * N / 4 + 255) / 256;

@@ -412,16 +412,43 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, int64_t R, int64_
     dst[r * ldd + c] = __float2bfloat16(c < Cc ? src[r * lds + c] : 0.f);
   }
 }
+// dense, unpadded, 8 elements per thread: 2 x 128-bit loads -> one 128-bit store
+__global__ void cast_vec8_kernel(const float* __restrict__ src, int64_t n8, __nv_bfloat16* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+    reinterpret_cast<uint4*>(dst)[i] = pk;
+  }
+}
 }  // namespace
 
-extern "C" int32_t sn_cast_bf16(const float* src, int64_t R, int64_t Cc, int64_t lds, void* dst, int64_t Cp, int64_t ldd,
-                                void* stream) {
+extern "C" int32_t sn_cast_bf16_ex(const float* src, int64_t R, int64_t Cc, int64_t lds, void* dst, int64_t Cp, int64_t ldd,
+                                   int32_t max_blocks, void* stream) {
   SN_REQUIRE(R >= 0 && Cc >= 0 && Cp >= Cc && ldd >= Cp, "sn_cast_bf16: bad dims");
   if (R == 0 || Cp == 0) return 0;
   int64_t total = R * Cp;
-  int64_t blocks = (total + 255) / 256;
   int64_t cap = (int64_t)sn::dev_info().sm_count * 16;
+  if (max_blocks > 0 && max_blocks < cap) cap = max_blocks;
+  const bool dense = Cc == Cp && lds == Cc && ldd == Cp && (total % 8) == 0 && ((uintptr_t)src & 15) == 0 &&
+                     ((uintptr_t)dst & 15) == 0;
+  if (dense) {
+    int64_t blocks = (total / 8 + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    cast_vec8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, total / 8, (__nv_bfloat16*)dst);
+    return sn::check_launch("sn_cast_bf16");
+  }
+  int64_t blocks = (total + 255) / 256;
   if (blocks > cap) blocks = cap;
   cast_pad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, R, Cc, lds, (__nv_bfloat16*)dst, Cp, ldd);
   return sn::check_launch("sn_cast_bf16");
+}
+
+extern "C" int32_t sn_cast_bf16(const float* src, int64_t R, int64_t Cc, int64_t lds, void* dst, int64_t Cp, int64_t ldd,
+                                void* stream) {
+  return sn_cast_bf16_ex(src, R, Cc, lds, dst, Cp, ldd, 0, stream);
 }

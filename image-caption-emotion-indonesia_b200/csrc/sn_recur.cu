@@ -420,7 +420,13 @@ int32_t launch_coop(K kernel, const Plan& p, RecurArgs& a, cudaStream_t stream, 
   SN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   void* params[] = {&a};
   dim3 grid((unsigned)(p.n_ub * p.nbb)), block(NT);
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kernel, grid, block, params, p.smem, stream);
+  cudaError_t e;
+  if (sn::recur_cooperative()) {
+    e = cudaLaunchCooperativeKernel((const void*)kernel, grid, block, params, p.smem, stream);
+  } else {
+    if ((int)grid.x > sn::dev_info().sm_count) return sn::fail(-1, "%s: grid of %u CTAs exceeds the %d SMs", what, grid.x, sn::dev_info().sm_count);
+    e = cudaLaunchKernel((const void*)kernel, grid, block, params, p.smem, stream);   // see sn::recur_cooperative()
+  }
   if (e != cudaSuccess) return sn::fail((int32_t)e, "%s: cooperative launch failed: %s", what, cudaGetErrorString(e));
   return 0;
 }

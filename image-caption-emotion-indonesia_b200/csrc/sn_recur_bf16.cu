@@ -426,7 +426,13 @@ int32_t launch(Kern kernel, RArgs& a, size_t smem, cudaStream_t stream, const ch
   SN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* params[] = {&a};
   dim3 grid((unsigned)(a.n_ub * a.nbb)), block(NT);
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kernel, grid, block, params, smem, stream);
+  cudaError_t e;
+  if (sn::recur_cooperative()) {
+    e = cudaLaunchCooperativeKernel((const void*)kernel, grid, block, params, smem, stream);
+  } else {
+    if ((int)grid.x > sn::dev_info().sm_count) return sn::fail(-1, "%s: grid of %u CTAs exceeds the %d SMs", what, grid.x, sn::dev_info().sm_count);
+    e = cudaLaunchKernel((const void*)kernel, grid, block, params, smem, stream);   // see sn::recur_cooperative()
+  }
   if (e != cudaSuccess) return sn::fail((int32_t)e, "%s: cooperative launch failed: %s", what, cudaGetErrorString(e));
   return 0;
 }

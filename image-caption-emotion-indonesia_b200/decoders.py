@@ -133,25 +133,56 @@ class _DecoderBase(nn.Module):
     def _publish(self, names, gbuf):
         self.arena().publish_grads(names, gbuf)
 
-    def _side(self):
-        """Second CUDA stream for GEMMs that are independent of the critical chain (weight gradients): each has
-        only 45-320 tiles, so two of them side by side fill the 148 SMs where one cannot.  Works eagerly and
-        under CUDA-graph capture (fork/join become parallel graph branches)."""
-        st = self.__dict__.get("_side_stream")
+    def _side(self, i=0):
+        """Side CUDA streams for work that is independent of the critical chain: weight-gradient GEMMs (each has only
+        45-320 tiles, two of them side by side fill the 148 SMs where one cannot), bf16 weight shadows, loss
+        bookkeeping.  Works eagerly and under CUDA-graph capture (fork/join become parallel graph branches).
+        Stream 0 and 1 carry the weight gradients, stream 2 the weight shadows of the forward pass."""
+        sts = self.__dict__.setdefault("_side_streams", {})
+        st = sts.get(i)
         if st is None:
             st = torch.cuda.Stream()
-            self.__dict__["_side_stream"] = st
+            sts[i] = st
         return st
 
-    def _fork(self):
-        side = self._side()
+    def _fork(self, i=0):
+        side = self._side(i)
         side.wait_stream(torch.cuda.current_stream())
         return side
 
     def _join(self):
-        st = self.__dict__.get("_side_stream")
-        if st is not None:
+        for st in self.__dict__.get("_side_streams", {}).values():
             torch.cuda.current_stream().wait_stream(st)
+
+    def _take_out_shadow(self):
+        """The prefetched bf16 shadow of the vocabulary weight (or None), after making the current stream wait for it."""
+        Wb = self.__dict__.pop("_out_w16_pref", None)
+        ev = self.__dict__.pop("_out_w16_ev", None)
+        if Wb is not None and ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        return Wb
+
+    def _shadows_async(self, specs):
+        """bf16 operand shadows of fp32 weights, cast on side stream 2 while the main stream gathers / projects.
+        ``specs``: [(dict, key, fp32 2-D weight)].  The output tensors are allocated on the CURRENT stream (so the
+        caching allocator ties their lifetime to it) and only written on the side stream.  Returns the event the main
+        stream must wait for before the first use (``_shadows_wait``)."""
+        main = torch.cuda.current_stream()
+        outs = []
+        for dct, key, w in specs:
+            R, C = w.shape
+            Cp = (C + 7) // 8 * 8
+            out = torch.empty(R, Cp, dtype=torch.bfloat16, device=w.device)
+            dct[key] = out
+            outs.append((w, out, R, C, Cp))
+        side = self._side(2)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for w, out, R, C, Cp in outs:
+                ops.cast_bf16(w, R, C, w.stride(0), out, Cp, Cp, max_blocks=24)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return ev
 
     def _next_seed(self, dev, p_drop):
         """Dropout randomness = hash(seed + device counter, row, col).  The counter lives in device memory
@@ -216,6 +247,16 @@ class _DecoderBase(nn.Module):
             c.tok_override = torch.full((N,), -1, dtype=torch.int32, device=dev)
         c.Ein = E
         c.w16 = {}      # bf16 weight shadows of this call (refreshed every forward)
+        c.ev_early = c.ev_late = None
+        if self.bf16:
+            # every weight shadow except the first GEMM's is cast on a side stream, under the gather / first GEMM
+            early, late = self._shadow_specs(c, mode)
+            if early:
+                c.ev_early = self._shadows_async(early)
+            if late:
+                c.ev_late = self._shadows_async(late)
+            # the vocabulary weight (the largest cast) is only needed after the recurrence: its own event
+            self.__dict__["_out_w16_ev"] = self._shadows_async([(self.__dict__, "_out_w16_pref", self._out().weight)])
         if self.bf16:
             # bf16 mode: the packed input rows are produced directly as the K-padded bf16 GEMM operand
             X = None
@@ -238,8 +279,11 @@ class _DecoderBase(nn.Module):
         c.Whh, c.bhh = Whh, bhh
         use_tc = self.bf16 and H % 32 == 0
         c.Hb = c.Hpb = None
+        if c.ev_late is not None:
+            torch.cuda.current_stream().wait_event(c.ev_late)
         if use_tc:
-            c.w16["Whh"] = self._shadow(Whh)
+            if "Whh" not in c.w16:
+                c.w16["Whh"] = self._shadow(Whh)
             c.Hb = torch.empty(N, H, dtype=torch.bfloat16, device=dev)
             c.Hpb = torch.empty(N, H, dtype=torch.bfloat16, device=dev) if save else None
             c.Hprev = None
@@ -317,6 +361,15 @@ class _DecoderBase(nn.Module):
             h_init = cl.Hall[plan.off[t0 - 1]:] if t0 > 0 else None
             ops.recur_fwd(self.cell, H, B, d["bs"], d["off"], t0, t1, cl.XP, Whh, bhh, h_init, cl.Hall,
                           cl.Call, cl.Hprev, cl.gates, cl.c_state)
+
+    def _shadow_specs(self, c, mode):
+        """(early, late) lists of (dict, key, fp32 weight) to cast to bf16 on the side stream at the start of a forward:
+        `early` = needed by the second GEMM of the input projection, `late` = needed from the recurrence on."""
+        H = self.hidden_size
+        late = []
+        if H % 32 == 0:
+            late.append((c.w16, "Whh", self._recurrent_weights()[0]))
+        return [], late
 
     def _upper_layers_init(self, c, save):
         return []
@@ -397,7 +450,9 @@ class _DecoderBase(nn.Module):
             N = Hall.shape[0]
             if Hb is None:
                 Hb = ops.to_bf16_padded(Hall.contiguous())
-            Wb = ops.to_bf16_padded(out.weight)
+            Wb = self._take_out_shadow()
+            if Wb is None:
+                Wb = ops.to_bf16_padded(out.weight)
             self.__dict__["_out_w16"] = Wb          # reused by the matching backward of this step
             logits = torch.empty(N, V, dtype=torch.float32, device=Hall.device)
             ops.gemm_bf16(ops.OP_NT, Hb, Wb, N, V, H, Hb.stride(0), Wb.stride(0), C=logits, ldc=V, bias=out.bias)
@@ -423,11 +478,15 @@ class _DecoderBase(nn.Module):
             if Wb is None:
                 Wb = ops.to_bf16_padded(out.weight)
             if have_b16:
-                # dC / db_C do not feed the recurrence: side stream, joined by the caller (_join)
-                with torch.cuda.stream(self._fork()):
-                    ops.gemm_bf16(ops.OP_TN, dLb, Hb, V, H, N, dLb.stride(0), Hb.stride(0), C=gC, ldc=H)
-                    ops.colsum_bf16(dLb, N, V, dLb.stride(0), gb)
+                # dH feeds the reverse recurrence: issued FIRST so its tiles get the SMs; dC / db_C do not feed anything
+                # before Adam: side stream, joined by the caller (_join)
+                side = self._fork()
                 ops.gemm_bf16(ops.OP_NN, dLb, Wb, N, H, V, dLb.stride(0), Wb.stride(0), C=dHall, ldc=H)
+                with torch.cuda.stream(side):
+                    # capped at 10 SM pairs: dC then fits on the 20 SMs the 128-CTA reverse recurrence leaves free and
+                    # runs under it instead of holding every SM in front of the dH reduction (timeline, profiles/r1_l)
+                    ops.gemm_bf16(ops.OP_TN, dLb, Hb, V, H, N, dLb.stride(0), Hb.stride(0), C=gC, ldc=H, max_pairs=10)
+                    ops.colsum_bf16(dLb, N, V, dLb.stride(0), gb)
                 return dHall
             ops.gemm_bf16(ops.OP_NN, dLb, Wb, N, H, V, dLb.stride(0), Wb.stride(0), C=dHall, ldc=H)
             ops.gemm_bf16(ops.OP_TN, dLb, Hb, V, H, N, dLb.stride(0), Hb.stride(0), C=gC, ldc=H)
@@ -454,7 +513,9 @@ class _DecoderBase(nn.Module):
         if self.bf16:
             if Hb is None:
                 Hb = ops.to_bf16_padded(Hall.contiguous())
-            Wb = ops.to_bf16_padded(out.weight)
+            Wb = self._take_out_shadow()                      # cast on the side stream at the start of the forward
+            if Wb is None:
+                Wb = ops.to_bf16_padded(out.weight)
             self.__dict__["_out_w16"] = Wb              # reused by the matching _vocab_backward
             self.__dict__["_out_h16"] = Hb
             tl = torch.empty(N, dtype=torch.float32, device=dev)
@@ -488,12 +549,14 @@ class _DecoderBase(nn.Module):
         return _HiddenFn.apply(anchor, features, self, plan, captions, coins, mode, save), plan
 
     def forward_loss(self, captions, lengths, features=None, targets=None, teacher_forcing_ratio=1.0,
-                     mode="factual", backward=True, n_global=None, grad_hook=None):
+                     mode="factual", backward=True, n_global=None, grad_hook=None, early_step=None):
         """Fused training entry point (an addition beside the kept surface):
         forward -> mean token NLL -> (optionally) backward, with log-softmax/NLL/gradient fused in one
         pass over the logits and no autograd graph.  Populates ``.grad`` like ``loss.backward()`` after
         ``zero_grad()`` would.  Returns ``(loss[1], stats)`` with stats = dict(argmax, top5hit).
-        ``n_global``: token count to normalise by (data parallel: the global count)."""
+        ``n_global``: token count to normalise by (data parallel: the global count).
+        ``early_step(names) -> bool``: called (bf16 mode, on side stream 0, right behind dC / db_C) when the gradients
+        of the vocabulary projection are final, so that the optimizer can update them under the reverse recurrence."""
         self._check_inputs(captions, features)
         plan = get_plan(lengths)
         coins = self._coins(plan.T, teacher_forcing_ratio)
@@ -508,14 +571,33 @@ class _DecoderBase(nn.Module):
                 if features is None:
                     raise ValueError("forward_loss: pass `targets` when features is None (language-only "
                                      "pass: inputs captions[:, :-1], targets packed captions[:, 1:])")
-                targets = self._default_targets(captions, plan, True)
+                if self.bf16:
+                    # gathered on the shadow stream (forked from the main stream at the start of this forward, after
+                    # `captions` existed) while the recurrence runs; allocated here, written there
+                    targets = torch.empty(N, dtype=captions.dtype, device=dev)
+                    side = self._side(2)
+                    with torch.cuda.stream(side):
+                        self._default_targets(captions, plan, True, out=targets)
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                    torch.cuda.current_stream().wait_event(ev)
+                else:
+                    targets = self._default_targets(captions, plan, True)
             denom = float(n_global if n_global is not None else N)
             row_loss, argmax, top5, logits, dLb = self._vocab_nll(c.top.Hall, c.top.Hb, targets, denom, backward)
             loss = torch.empty(1, dtype=torch.float32, device=dev)
-            ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
+            if not (backward and dLb is not None):
+                ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
             if backward:
                 gbuf = self._grad_target(c.grad_names + list(self._out_names()))
                 dHall = self._vocab_backward(c.top.Hall, logits, gbuf, c.top.Hb, dLb)
+                if dLb is not None:
+                    # the scalar loss is bookkeeping: reduce it behind dC on side stream 0, not in front of dH
+                    with torch.cuda.stream(self._side(0)):
+                        ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
+                        if early_step is not None and gbuf is self.arena().gflat:
+                            self._publish(list(self._out_names()), gbuf)
+                            early_step(list(self._out_names()))
                 if grad_hook is not None and gbuf is self.arena().gflat:
                     self._join()
                     grad_hook(list(self._out_names()))       # bucket 0 is final: overlap its all-reduce
@@ -529,7 +611,7 @@ class _DecoderBase(nn.Module):
                     features.grad = dfeat if features.grad is None else features.grad + dfeat
         return loss, {"argmax": argmax, "top5hit": top5, "n_tokens": N}
 
-    def _default_targets(self, captions, plan, has_feat):
+    def _default_targets(self, captions, plan, has_feat, out=None):
         """Packed targets = what pack_padded_sequence(captions, lengths)[0] holds (train_multitask.py:377-379):
         one gather through a flat (b*T + t) index cached with the plan."""
         d = plan.dev(captions.device)
@@ -538,6 +620,8 @@ class _DecoderBase(nn.Module):
         if idx is None:
             idx = (d["row_b"].long() * captions.shape[1] + d["row_t"].long() + (0 if has_feat else 1)).contiguous()
             d[key] = idx
+        if out is not None:
+            return torch.index_select(captions.reshape(-1), 0, idx, out=out)
         return captions.reshape(-1).index_select(0, idx)
 
 
@@ -609,6 +693,14 @@ class DecoderFactoredLSTM(_DecoderBase):
             return self._gview(gbuf, names, shape)
         return self.arena().block(names, shape)
 
+    def _shadow_specs(self, c, mode):
+        H, F = self.hidden_size, self.factored_size
+        early, late = super()._shadow_specs(c, mode)
+        if mode in STYLES:
+            # (V stays on the main stream: its K = 300 -> 304 padded cast is the scalar kernel, 39 us under the block cap)
+            early = [(c.w16, "S", self._style_stack(mode, (4 * F, F))), (c.w16, "U", self._stack("U_", (4 * H, F)))]
+        return early, late
+
     def _recurrent_weights(self, layer=0):
         H = self.hidden_size
         return self._stack("W_", (4 * H, H), layer=layer), self._stack("W_", (4 * H,), bias=True, layer=layer)
@@ -646,7 +738,9 @@ class DecoderFactoredLSTM(_DecoderBase):
         if self.bf16:
             w16 = c.__dict__.setdefault("w16", {})
             if "V" not in w16:
-                w16["V"], w16["S"], w16["U"] = self._shadow(Vc), self._shadow(Sc), self._shadow(Uc)
+                w16["V"] = self._shadow(Vc)
+            if "S" not in w16:
+                w16["S"], w16["U"] = self._shadow(Sc), self._shadow(Uc)
             Vb, Sb, Ub = w16["V"], w16["S"], w16["U"]
             Ep, Fp = Vb.stride(0), Sb.stride(0)
             if full:
@@ -658,6 +752,10 @@ class DecoderFactoredLSTM(_DecoderBase):
                 ops.cast_bf16(X, n, Ein, Ein, c.Xb, Ep, Ep, src_off=r0 * Ein, dst_off=r0 * Ep)
             ops.gemm_bf16(ops.OP_NT, c.Xb, Vb, n, 4 * F, Ep, Ep, Ep, Cb=c.A1, ldcb=4 * F, bias=bV, a_off=r0 * Ep,
                           cb_off=r0 * 4 * F)
+            ev = c.__dict__.get("ev_early")
+            if ev is not None:                  # the S / U shadows come from the side stream
+                torch.cuda.current_stream().wait_event(ev)
+                c.ev_early = None
             ops.gemm_bf16(ops.OP_NT, c.A1, Sb, n, F, F, 4 * F, Fp, Cb=c.A2, ldcb=4 * F, bias=bS, batch=4, sA=F,
                           sB=F * Fp, sCb=F, sBias=F, a_off=r0 * 4 * F, cb_off=r0 * 4 * F)
             ops.gemm_bf16(ops.OP_NT, c.A2, Ub, n, H, F, 4 * F, Fp, C=c.XP, ldc=4 * H, bias=bU, batch=4, sA=F,
@@ -715,25 +813,26 @@ class DecoderFactoredLSTM(_DecoderBase):
         f32 = dict(dtype=torch.float32, device=dev)
         b16 = dict(dtype=torch.bfloat16, device=dev)
         main = torch.cuda.current_stream()
-        side = self._side()
-        # critical chain (main stream): dZ -> dA2 -> dA1 -> dX ; weight / bias gradients trail on the side stream
+        sa, sb = self._side(0), self._side(1)
+        # critical chain (main stream): dZ -> dA2 -> dA1 -> dX ; the weight / bias gradients trail on TWO side streams
+        # (U on stream 0 behind dW_hh, S and V on stream 1) so that Adam does not wait for a serial tail of GEMMs
         dA2, dA2b = torch.empty(N, 4 * F, **f32), torch.empty(N, 4 * F, **b16)
         dA1, dA1b = torch.empty(N, 4 * F, **f32), torch.empty(N, 4 * F, **b16)
         dX = torch.empty(N, Ein, **f32)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
+        sa.wait_stream(main)
+        with torch.cuda.stream(sa):
             ops.gemm_bf16(ops.OP_TN, dZb, c.A2, H, F, N, 4 * H, 4 * F, C=gU, ldc=F, batch=4, sA=H, sB=F, sC=H * F)
             ops.colsum(dZ, N, 4 * H, 4 * H, gbU)
         ops.gemm_bf16(ops.OP_NN, dZb, Ub, N, F, H, 4 * H, Fp, C=dA2, ldc=4 * F, Cb=dA2b, ldcb=4 * F, batch=4, sA=H,
                       sB=H * Fp, sC=F, sCb=F)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
+        sb.wait_stream(main)
+        with torch.cuda.stream(sb):
             ops.gemm_bf16(ops.OP_TN, dA2b, c.A1, F, F, N, 4 * F, 4 * F, C=gS, ldc=F, batch=4, sA=F, sB=F, sC=F * F)
             ops.colsum(dA2, N, 4 * F, 4 * F, gbS)
         ops.gemm_bf16(ops.OP_NN, dA2b, Sb, N, F, F, 4 * F, Fp, C=dA1, ldc=4 * F, Cb=dA1b, ldcb=4 * F, batch=4, sA=F,
                       sB=F * Fp, sC=F, sCb=F)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
+        sb.wait_stream(main)
+        with torch.cuda.stream(sb):
             ops.gemm_bf16(ops.OP_TN, dA1b, c.Xb, 4 * F, Ein, N, 4 * F, Ep, C=gV, ldc=Ein)
             ops.colsum(dA1, N, 4 * F, 4 * F, gbV)
         ops.gemm_bf16(ops.OP_NN, dA1b, Vb, N, Ein, 4 * F, 4 * F, Ep, C=dX, ldc=Ein)

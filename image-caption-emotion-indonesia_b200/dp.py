@@ -135,9 +135,17 @@ class DataParallelTrainer:
         if self.world > 1:
             def hook(names):
                 self.sync.launch(a.gflat, merged_ranges(a, names))
+        early = []
+        if self.world == 1 and getattr(self.decoder, "bf16", False) and not hasattr(self.decoder, "attention"):
+            # single GPU: Adam of the vocabulary projection runs on the side stream as soon as dC is final (under the
+            # reverse recurrence); the rest follows at the end
+            def early_step(names):
+                self.optimizer.step(only=names)
+                early.extend(names)
+            kw = dict(kw, early_step=early_step)
         loss, stats = self.forward_backward(captions, lengths, features, n_global=n_global, b_global=b_global,
                                             grad_hook=hook, **kw)
         if self.world > 1:
             self.sync.wait()
-        self.optimizer.step()
+        self.optimizer.step(skip=early or None)
         return loss, stats

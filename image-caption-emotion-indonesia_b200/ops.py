@@ -197,7 +197,9 @@ def _pick_splits(M, N, K, batch):
     """Split-K factor for the pair kernel: fill the 74 SM pairs when the tile count alone cannot."""
     tiles = ((M + 255) // 256) * ((N + 255) // 256) * batch
     kb = (K + 63) // 64
-    if tiles * 2 > _SM_PAIRS or kb < 16:
+    # only long-K problems (dH = dL C, K = vocabulary): for the K = tokens weight-gradient GEMMs (30 k-blocks at
+    # configs[1]) the partial GEMM + reduction launches cost more than the 16 unsplit tiles (timeline, profiles/r1_l)
+    if tiles * 2 > _SM_PAIRS or kb < 64:
         return 1
     return max(1, min(_SM_PAIRS // tiles, kb // 8, 16))
 
@@ -217,10 +219,11 @@ def _gemm2_ws(device, nbytes):
 
 def gemm_bf16(op, A, B, M, N, K, lda, ldb, C=None, ldc=0, Cb=None, ldcb=0, bias=None, beta=0.0, batch=1,
               sA=0, sB=0, sC=0, sCb=0, sBias=0, a_off=0, b_off=0, c_off=0, cb_off=0, bias_off=0, splits=1,
-              impl=None):
+              impl=None, max_pairs=0):
     """tcgen05 GEMM: A, B bf16; C fp32 and/or Cb bf16.  Offsets in elements of the respective tensor.
     Pair kernel: splits=1 -> automatic split-K (deterministic work-space reduction) for few-tile / long-K shapes.
-    Single-CTA kernel: splits: 1 = off, 0 = automatic, n = forced (fp32 atomics)."""
+    Single-CTA kernel: splits: 1 = off, 0 = automatic, n = forced (fp32 atomics).
+    max_pairs (pair kernel): cap the grid at that many SM pairs (side-stream GEMMs)."""
     _req(A, torch.bfloat16); _req(B, torch.bfloat16)
     impl = impl or GEMM_IMPL[0]
     if impl == "pair" or (impl == "auto" and M >= 256):
@@ -234,8 +237,8 @@ def gemm_bf16(op, A, B, M, N, K, lda, ldb, C=None, ldc=0, Cb=None, ldcb=0, bias=
             LAUNCHES[0] += batch
         check(lib().sn_gemm2_bf16(op, M, N, K, _bptr(A, a_off, 2), lda, _bptr(B, b_off, 2), ldb,
                                   _bptr(C, c_off, 4), ldc, _bptr(Cb, cb_off, 2), ldcb, _bptr(bias, bias_off, 4),
-                                  float(beta), batch, sA, sB, sC, sCb, sBias, sp, _ptr(ws), wsb, _stream()),
-              "sn_gemm2_bf16")
+                                  float(beta), batch, sA, sB, sC, sCb, sBias, sp, _ptr(ws), wsb, int(max_pairs),
+                                  _stream()), "sn_gemm2_bf16")
         return
     check(lib().sn_gemm_bf16_splitk(op, M, N, K, _bptr(A, a_off, 2), lda, _bptr(B, b_off, 2), ldb,
                                     _bptr(C, c_off, 4), ldc, _bptr(Cb, cb_off, 2), ldcb, _bptr(bias, bias_off, 4),
@@ -264,9 +267,10 @@ def vocab_nll_bwd(Hb, Wb, bias, targets, N, V, H, tlogit, lse, grad_scale, dLb=N
         LAUNCHES[0] += 1
 
 
-def cast_bf16(src, R, C, lds, dst, Cp, ldd, src_off=0, dst_off=0):
-    check(lib().sn_cast_bf16(_bptr(_req(src), src_off, 4), R, C, lds, _bptr(dst, dst_off, 2), Cp, ldd, _stream()),
-          "sn_cast_bf16")
+def cast_bf16(src, R, C, lds, dst, Cp, ldd, src_off=0, dst_off=0, max_blocks=0):
+    """max_blocks > 0 caps the grid (side-stream casts: a cast block on an SM keeps a CTA-pair GEMM off it)."""
+    check(lib().sn_cast_bf16_ex(_bptr(_req(src), src_off, 4), R, C, lds, _bptr(dst, dst_off, 2), Cp, ldd, max_blocks,
+                                _stream()), "sn_cast_bf16")
 
 
 def to_bf16_padded(x, pad_to=8):

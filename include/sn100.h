@@ -102,17 +102,22 @@ int32_t sn_gemm_bf16_splitk(int32_t op, int64_t M, int64_t N, int64_t K, const v
  * double-buffered TMEM accumulator; sn_gemm2.cu).  Twice the arithmetic intensity per byte fetched from L2 --
  * the kernel for the time-batched projection / vocabulary / weight-gradient GEMMs (M >= 256).
  * splits > 1: split-K through the caller-provided work space `ws` (sn_gemm2_ws_bytes), reduced by a second
- * kernel (deterministic, no atomics); any epilogue (bias, beta, bf16 copy) is applied by the reduction. */
+ * kernel (deterministic, no atomics); any epilogue (bias, beta, bf16 copy) is applied by the reduction.
+ * max_pairs > 0 caps the grid at that many SM pairs (GEMMs on a side stream: leave SMs to the critical chain). */
 int64_t sn_gemm2_ws_bytes(int64_t M, int64_t N, int32_t batch, int32_t splits);
 int32_t sn_gemm2_bf16(int32_t op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
                       const void* B, int64_t ldb, float* C, int64_t ldc, void* Cb, int64_t ldcb,
                       const float* bias, float beta, int32_t batch, int64_t strideA, int64_t strideB,
                       int64_t strideC, int64_t strideCb, int64_t strideBias, int32_t splits, void* ws,
-                      int64_t ws_bytes, void* stream);
+                      int64_t ws_bytes, int32_t max_pairs, void* stream);
 /* fp32 [R,C] (row pitch lds) -> bf16 [R,Cp] (row pitch ldd), columns C..Cp zero-filled (weight shadows and
  * activation operands of sn_gemm_bf16; Cp pads K to the TMA 16-byte rule, e.g. E=300 -> 304) */
 int32_t sn_cast_bf16(const float* src, int64_t R, int64_t C, int64_t lds, void* dst, int64_t Cp,
                      int64_t ldd, void* stream);
+/* same, with the grid capped at max_blocks CTAs (0 = no cap): for casts issued on a side stream next to CTA-pair
+ * GEMMs, which need whole SMs */
+int32_t sn_cast_bf16_ex(const float* src, int64_t R, int64_t C, int64_t lds, void* dst, int64_t Cp,
+                        int64_t ldd, int32_t max_blocks, void* stream);
 /* column sums (bias gradients): out[n] = sum_m X[m,n] + beta*out[n] */
 int32_t sn_colsum(const float* X, int64_t M, int64_t N, int64_t ldx, float* out, float beta,
                   void* stream);
