@@ -350,7 +350,7 @@ def run_gpu(args):
     line = None
     if rank == 0:
         hbm_peak, tf_peak, peak_src = measured_peaks()
-        if WORKLOAD == "att":
+        if WORKLOAD == "att" or args.no_roofline:
             roof, kernels = None, None
         else:
             roof, kernels = kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src, tf_peak)
@@ -575,6 +575,7 @@ def main():
     ap.add_argument("--workload", default="factored", choices=["factored", "att", "nic", "stack3"])
     ap.add_argument("--batch", type=int, default=None,
                     help="samples per GPU (default: the BASELINE config, 96; e.g. 4096 = throughput regime, a supplementary point)")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel roofline section (launch lists of the step only)")
     ap.add_argument("--segmented", action="store_true", help="force the 3-graph (data-parallel) replay form on one GPU")
     args = ap.parse_args()
     global WORKLOAD, B_PER_GPU

@@ -86,6 +86,9 @@ class PeerExchange:
         dist.barrier(group=group)
 
 
+EARLY_PEER_EXCHANGE = [True]     # split the peer-fused exchange+Adam: vocabulary projection early, the rest at the end
+
+
 class DataParallelTrainer:
     """forward -> loss -> backward -> gradient exchange -> fused clamp+Adam, one rank per GPU.
 
@@ -128,8 +131,16 @@ class DataParallelTrainer:
         a = self.decoder.arena()
         if self.world > 1 and self.comm == "peer":
             peers = self._peers()
+            early = []
+            if getattr(self.decoder, "bf16", False) and not hasattr(self.decoder, "attention") and EARLY_PEER_EXCHANGE[0]:
+                # the vocabulary projection (43 % of the exchanged bytes at configs[1]) is reduced / updated / gathered
+                # on the side stream as soon as dC is final, under the reverse recurrence; the rest at the end
+                def early_step(names):
+                    self.optimizer.step_peer(peers, only=names)
+                    early.extend(names)
+                kw = dict(kw, early_step=early_step)
             loss, stats = self.forward_backward(captions, lengths, features, n_global=n_global, b_global=b_global, **kw)
-            self.optimizer.step_peer(peers)
+            self.optimizer.step_peer(peers, skip=early or None)
             return loss, stats
         hook = None
         if self.world > 1:

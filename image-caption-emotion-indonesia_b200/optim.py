@@ -86,12 +86,19 @@ class FusedClampAdam:
                     self._step_tensor(p, ("extra", i))
 
     @torch.no_grad()
-    def step_peer(self, peers):
+    def step_peer(self, peers, only=None, skip=None):
         """Data-parallel step: gradient reduce-scatter + clamp/Adam on the owned shard + parameter all-gather in
-        one kernel over NVLink peer memory.  Every rank must call it with the same set of gradients."""
+        one kernel over NVLink peer memory.  Every rank must call it with the same set of gradients (``only`` /
+        ``skip`` as in ``step``: the vocabulary projection's exchange can run early, under the reverse recurrence)."""
         a = self._state()
         self._sync_lr()
         items, foreign = a.grad_ranges()
+        if only is not None:
+            keep = set(only)
+            items = [it for it in items if it[2] in keep]
+        if skip is not None:
+            drop = set(skip)
+            items = [it for it in items if it[2] not in drop]
         if foreign or any(p.grad is not None for p in self.extra):
             raise RuntimeError("peer-fused step needs every gradient in the arena")
         ranges = [(off, n) for off, n, _ in items]
