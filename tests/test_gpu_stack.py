@@ -151,3 +151,36 @@ def test_stack_config4_dimensions_vs_oracle(precision, tol):
     for n, p in dec.named_parameters():
         if p.grad is not None:
             assert rel_l2(p.grad.cpu(), ref[n]) < tol, n
+
+
+def test_early_vocab_adam_equals_single_step():
+    """The single-GPU trainer updates the vocabulary projection on a side stream as soon as dC is final and the rest at
+    the end (optimizer.step(only=...) + step(skip=...)): parameters after 3 steps == one optimizer.step() per step."""
+    import icei_b200 as sn
+    from oracle import port
+    E, H, F, V, B, T = 40, 64, 64, 517, 56, 8
+    cap, lens, feats = port.synthetic_batch(B, T, V, E=E, ragged=True, seed=3)
+    cap, feats = cap.cuda(), feats.cuda()
+    outs = []
+    for early in (True, False):
+        torch.manual_seed(5)
+        dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0).cuda().set_precision("bf16")
+        dec.train()
+        opt = sn.FusedClampAdam(dec, lr=1e-3, grad_clip=0.5)
+        tr = sn.DataParallelTrainer(dec, opt)
+        for _ in range(3):
+            random.seed(1)
+            if early:
+                loss, _ = tr.step(cap, lens, feats, teacher_forcing_ratio=1.0, mode="sad")
+            else:
+                for p in dec.parameters():
+                    p.grad = None
+                loss, _ = dec.forward_loss(cap, lens, feats, teacher_forcing_ratio=1.0, mode="sad")
+                opt.step()
+        torch.cuda.synchronize()
+        outs.append((loss.item(), {n: p.detach().clone() for n, p in dec.named_parameters()}, opt.step_counts()))
+    assert abs(outs[0][0] - outs[1][0]) < 1e-5 * abs(outs[1][0])
+    assert outs[0][2] == outs[1][2]
+    # not bit-exact by construction: the embedding / bias gradients are accumulated with fp32 atomics
+    worst = max((rel_l2(outs[0][1][n].cpu(), outs[1][1][n].cpu()), n) for n in outs[0][1])
+    assert worst[0] < 1e-5, worst
