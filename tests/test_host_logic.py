@@ -142,3 +142,62 @@ def test_merged_ranges_and_grad_ranges():
     dec.S_happy_i.weight.grad = torch.zeros_like(dec.S_happy_i.weight)   # a foreign gradient tensor
     items, foreign = a.grad_ranges()
     assert foreign == ["S_happy_i.weight"]
+
+
+def test_stack_module_layout_and_state_dict_interchange():
+    """configs[3] stack: parameter count of the survey (73 395 664 at E=300, H=512, F=1024, V=10000, 3 layers), reference
+    names for layer 0, ``l{l}_`` names above, one arena, per-layer state_dict loading from oracle-port decoders."""
+    from oracle import port
+    dec = sn.DecoderFactoredLSTMStack(300, 512, 1024, 10000, 3)
+    assert sum(p.numel() for p in dec.parameters()) == 73395664
+    ref_names = set(dict(sn.DecoderFactoredLSTM(12, 16, 20, 53, 1).named_parameters()))
+    small = sn.DecoderFactoredLSTMStack(12, 16, 20, 53, 3)
+    names = set(dict(small.named_parameters()))
+    assert ref_names <= names
+    upper = {n for n in names if n.startswith("l1_") or n.startswith("l2_")}
+    assert names == ref_names | upper
+    assert {n[3:] for n in upper if n.startswith("l1_")} == {n for n in ref_names if n[0] in "UVWS"}
+    assert dict(small.named_parameters())["l1_V_i.weight"].shape == (20, 16)      # embed_size = hidden_size above layer 0
+    a = small.arena()                                                             # binds on CPU tensors too
+    assert a.total >= sum(p.numel() for p in small.parameters())
+    H, F = 16, 20
+    blk = a.block(["l2_" + "W_" + g + ".weight" for g in "ifoc"], (4 * H, H))    # gate-stacked and contiguous
+    assert blk.data_ptr() == small.l2_W_i.weight.data_ptr()
+    layers = [port.DecoderFactoredLSTM(12 if l == 0 else 16, 16, 20, 53, 1) for l in range(3)]
+    small.load_layer_state_dicts([m.state_dict() for m in layers])
+    assert torch.equal(small.B.weight, layers[0].B.weight) and torch.equal(small.C.weight, layers[0].C.weight)
+    assert torch.equal(small.l2_S_happy_o.weight, layers[2].S_happy_o.weight)
+    g = small._seq_grad_names("sad")
+    assert "l1_S_sad_i.weight" in g and "l1_S_happy_i.weight" not in g and "l2_W_c.bias" in g and "C.weight" not in g
+    with pytest.raises(ValueError):
+        small.load_layer_state_dicts([layers[0].state_dict()])
+
+
+def test_multitask_schedule_order_and_modes():
+    """factual pass on the first trainer, then one emotion pass per available tag on the second
+    (stylenet/train_multitask.py:192-235)."""
+    calls = []
+
+    class FakeTrainer:
+        def __init__(self, name):
+            self.name = name
+
+        def step(self, cap, lengths, feat, mode):
+            calls.append((self.name, mode, cap))
+            return (len(calls),), None
+
+    sched = sn.MultitaskSchedule(FakeTrainer("A"), FakeTrainer("B"), tags=("happy", "sad", "angry"))
+    out = sched.step(("cf", [3], "ff"), {"sad": ("cs", [3], "fs"), "happy": ("ch", [3], "fh")})
+    assert calls == [("A", "factual", "cf"), ("B", "happy", "ch"), ("B", "sad", "cs")]
+    assert list(out) == ["factual", "happy", "sad"]
+
+
+def test_split_k_heuristic_and_host_step_tables():
+    from icei_b200 import ops
+    assert ops._pick_splits(1920, 512, 10000, 1) > 1          # dH = dL C: few tiles, K = vocabulary
+    assert ops._pick_splits(2048, 512, 1920, 1) == 1          # weight gradient: 30 k-blocks, unsplit
+    assert ops._pick_splits(1920, 10000, 512, 1) == 1         # plenty of tiles
+    plan = sn.get_plan([5, 3, 3, 1])
+    bs, off = ops._host_steps(plan)
+    assert list(bs) == plan.bs and list(off) == plan.off[:plan.T]
+    assert ops._host_steps(plan) is plan.__dict__["_host_steps"]
