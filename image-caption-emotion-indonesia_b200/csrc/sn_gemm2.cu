@@ -207,14 +207,6 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return y;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {      // 32-byte aligned row piece
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
 
 // ---- per-warp 32x32 fp32 transpose through shared memory -------------------------------------------------------
 // write side: thread = row, 8 x STS.128; element (row, c) lives at row*32 + ((c/4) ^ (row & 7))*4 + c%4 -> the 8 rows of
@@ -309,14 +301,6 @@ __device__ __forceinline__ Tile decode_tile(const G2Args& g, int tile, int tiles
   return t;
 }
 
-__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
-  uint4 pk;
-  pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-  pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-  *reinterpret_cast<uint4*>(dst) = pk;
-}
 
 template <int EPI, int BN_>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)   // 18 warps (allocated as 20) x 96 registers
