@@ -11,6 +11,7 @@ stylenet/model.py:181), kernel sequencing and autograd glue.  All arithmetic run
 no PyTorch/CPU fallback -- tensors must be CUDA tensors on an sm_100 device.
 """
 import random
+from collections import OrderedDict
 
 import torch
 import torch.nn as nn
@@ -18,6 +19,9 @@ import torch.nn as nn
 from . import ops
 from .arena import ParamArena
 from .packing import get_plan
+
+# greedy decoding under no_grad replays a CUDA graph from the second identical call on (see _forward_greedy)
+GREEDY_GRAPH = [True]
 
 GATES = ("i", "f", "o", "c")
 STYLES = ("factual", "happy", "sad", "angry")
@@ -531,7 +535,57 @@ class _DecoderBase(nn.Module):
                         grad_scale=1.0 / denom, argmax=argmax, top5hit=top5)
         return row_loss, argmax, top5, logits, None
 
+    # ---- greedy decoding (validation path) replayed from a CUDA graph ------------------------------------
+    def _forward_greedy(self, captions, lengths, features, mode):
+        """``forward(teacher_forcing_ratio=0)`` under ``no_grad`` -- the reference's validation / greedy-decode path
+        (stylenet/train_multitask.py:296-299): every step feeds back the arg-max of the previous step, all on the
+        device, so the ~10 launches x T steps are host-bound when issued one by one.  From the second call with the
+        same (lengths, shapes, mode, precision) the whole forward is replayed from a captured CUDA graph; inputs are
+        copied into its static buffers, the returned logits are a copy of its static output."""
+        key = (tuple(int(l) for l in lengths), mode, tuple(captions.shape),
+               None if features is None else tuple(features.shape), self.precision, self.training,
+               captions.device.index)
+        cache = self.__dict__.setdefault("_greedy_graphs", OrderedDict())
+        sess = cache.get(key)
+        if sess is None:
+            sess = cache[key] = _Ctx()
+            sess.calls, sess.graph = 0, None
+            while len(cache) > 4:                      # each entry pins its logits and activations
+                cache.popitem(last=False)
+        cache.move_to_end(key)
+        sess.calls += 1
+        plan = get_plan(lengths)
+        coins = self._coins(plan.T, 0.0)               # consumes the host RNG stream exactly like the reference
+        if sess.graph is None and sess.calls < 2:
+            c = self._run_forward(plan, captions.contiguous(), features, coins, mode, save=False)
+            return self._vocab_logits(c.top.Hall, c.top.Hb)
+        if sess.graph is None:
+            sess.captions = captions.contiguous().clone()
+            sess.features = None if features is None else features.detach().clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                c = self._run_forward(plan, sess.captions, sess.features, coins, mode, save=False)
+                sess.out = self._vocab_logits(c.top.Hall, c.top.Hb)
+            sess.graph = g
+        sess.captions.copy_(captions, non_blocking=True)
+        if features is not None:
+            sess.features.copy_(features, non_blocking=True)
+        sess.graph.replay()
+        return sess.out.clone()
+
     # ---- public API --------------------------------------------------------------------------------
+    def _greedy_eligible(self, captions, lengths, features, teacher_forcing_ratio):
+        if torch.is_grad_enabled() or teacher_forcing_ratio > 0.0 or not GREEDY_GRAPH[0] or not captions.is_cuda:
+            return False
+        if torch.cuda.is_current_stream_capturing():
+            return False
+        if features is not None and features.shape[-1] != self._emb().weight.shape[1]:
+            return False                      # let the regular path raise its error
+        plan = get_plan(lengths)
+        T_in = captions.shape[1] + (1 if features is not None else 0)
+        return plan.B == captions.shape[0] and plan.T <= T_in
+
     def _forward_hidden(self, captions, lengths, features, teacher_forcing_ratio, mode):
         self._check_inputs(captions, features)
         if features is not None and features.shape[-1] != self._emb().weight.shape[1]:
@@ -843,6 +897,8 @@ class DecoderFactoredLSTM(_DecoderBase):
         """Same call and return as stylenet/model.py:157-196: packed logits [sum(lengths), V]."""
         if mode not in STYLES:
             raise ValueError("mode name wrong: %r (expected one of %s)" % (mode, STYLES))
+        if self._greedy_eligible(captions, lengths, features, teacher_forcing_ratio):
+            return self._forward_greedy(captions, lengths, features, mode)
         hall, _ = self._forward_hidden(captions, lengths, features, teacher_forcing_ratio, mode)
         return _LogitsFn.apply(hall, self.C.weight, self)
 
@@ -943,6 +999,8 @@ class DecoderRNN(_DecoderBase):
 
     def forward(self, captions, lengths, features, teacher_forcing_ratio=0.8):
         """Same call and return as nic/model.py:81-115."""
+        if self._greedy_eligible(captions, lengths, features, teacher_forcing_ratio):
+            return self._forward_greedy(captions, lengths, features, None)
         hall, _ = self._forward_hidden(captions, lengths, features, teacher_forcing_ratio, None)
         return _LogitsFn.apply(hall, self.linear.weight, self)
 

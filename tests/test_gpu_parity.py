@@ -395,3 +395,54 @@ def test_peer_fused_adam_degenerate_world1():
     # sums) differ in the last bits between runs, and 3 Adam steps carry that into the weights
     for (n, p), (_, q) in zip(d1.named_parameters(), d2.named_parameters()):
         assert rel_l2(q.detach().cpu(), p.detach().cpu()) < 1e-5, n
+
+
+def _greedy_case(name, precision):
+    """(decoder factory, captions, lengths, features, kwargs, golden greedy ids or None)"""
+    import icei_b200 as sn
+    from oracle import port
+    if precision == "fp32":
+        att, modes = CASES[name]
+        rec = load_golden(name)
+        cap, lens, feats = _inputs(rec)
+        kw = {} if modes[-1] is None else {"mode": modes[-1]}
+        tag = "" if modes[-1] is None else "." + modes[-1]
+        return (lambda: build_cuda(name, rec)), cap, lens, feats, kw, rec["tf0.argmax" + tag], int(rec["meta.V"])
+    # bf16 mode needs TMA-aligned dimensions (the golden cases are deliberately awkward: F = 20)
+    E, H, F, V, B, T = 40, 64, 64, 517, 24, 9
+    cap, lens, feats = port.synthetic_batch(B, T, V, E=E, ragged=True, seed=6)
+
+    def make():
+        torch.manual_seed(11)
+        m = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0) if name == "factored" else sn.DecoderRNN(E, H, V, 1, dropout=0.0)
+        return m.cuda().set_precision("bf16")
+    return make, cap.cuda(), lens, feats.cuda(), ({"mode": "happy"} if name == "factored" else {}), None, V
+
+
+@pytest.mark.parametrize("name", ["factored", "nic"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_greedy_forward_graph_replay_is_identical(name, precision):
+    """forward(tf=0) under no_grad: the CUDA-graph replay (2nd call onwards) returns exactly what the eager first call
+    returns, follows new inputs, and in fp32 mode still matches the golden greedy ids bit-exactly."""
+    make, cap, lens, feats, kw, golden_ids, V = _greedy_case(name, precision)
+    dec = make()
+    dec.eval()
+    outs = []
+    with torch.no_grad():
+        for _ in range(4):
+            random.seed(1234)
+            outs.append(dec(cap, lens, feats, teacher_forcing_ratio=0.0, **kw))
+        assert len(dec.__dict__["_greedy_graphs"]) == 1 and next(iter(dec.__dict__["_greedy_graphs"].values())).graph is not None
+        for o in outs[1:]:
+            assert torch.equal(o, outs[0])
+        if golden_ids is not None:
+            assert np.array_equal(outs[-1].argmax(1).cpu().numpy(), golden_ids)
+        # new inputs through the same graph == a fresh eager decoder on those inputs
+        cap2 = cap.clone()
+        cap2[:, 0] = (cap2[:, 0] + 3) % V
+        feats2 = feats * 0.5 + 0.1
+        got = dec(cap2, lens, feats2, teacher_forcing_ratio=0.0, **kw)
+        fresh = make()
+        fresh.eval()
+        want = fresh(cap2, lens, feats2, teacher_forcing_ratio=0.0, **kw)
+        assert torch.equal(got, want)
