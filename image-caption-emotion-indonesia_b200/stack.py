@@ -110,8 +110,16 @@ class DecoderFactoredLSTMStack(DecoderFactoredLSTM):
                 cl.Xb = torch.empty(N, (H + 7) // 8 * 8, **b16)
             cl.Hb = cl.Hpb = None
             cl.Whh, cl.bhh = self._recurrent_weights(l)
+            cl.ev_pre = None
+            if self.bf16:
+                # this layer's weight shadows are cast on the side stream while the layers below run
+                specs = [(cl.w16, "V", self._stack("V_", (4 * F, H), layer=l)),
+                         (cl.w16, "S", self._style_stack(c.mode, (4 * F, F), layer=l)),
+                         (cl.w16, "U", self._stack("U_", (4 * H, F), layer=l))]
+                if use_tc:
+                    specs.append((cl.w16, "Whh", cl.Whh))
+                cl.ev_pre = self._shadows_async(specs)
             if use_tc:
-                cl.w16["Whh"] = self._shadow(cl.Whh)
                 cl.Hb = torch.empty(N, H, **b16)
                 cl.Hpb = torch.empty(N, H, **b16) if save else None
             upper.append(cl)
@@ -129,6 +137,9 @@ class DecoderFactoredLSTMStack(DecoderFactoredLSTM):
                 cl.Xb, X = below.Hb, None            # the recurrence below already wrote its h_t as the bf16 operand
             else:
                 cl.X = X = below.Hall
+            if cl.ev_pre is not None:
+                torch.cuda.current_stream().wait_event(cl.ev_pre)
+                cl.ev_pre = None
             self._input_projection(cl, X, c.mode, r0, n)
             self._recur_fwd(c, cl, t0, t1)
             below = cl
