@@ -20,3 +20,14 @@ def test_dp2_equals_single_gpu(comm):
            "127.0.0.1", "--master-port", "29611" if comm == "peer" else "29612", os.path.join(HERE, "dp_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, SN_DP_COMM=comm))
     assert "DP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_dp2_early_vocab_exchange_equals_single_exchange():
+    """bf16 mode, peer-fused exchange: the vocabulary projection's reduce-scatter + Adam + all-gather issued early (under
+    the reverse recurrence) == one exchange at the end of the step; all ranks end with identical parameters."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29613", os.path.join(HERE, "dp_early_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert "DP_EARLY_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
