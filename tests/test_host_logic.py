@@ -201,3 +201,17 @@ def test_split_k_heuristic_and_host_step_tables():
     bs, off = ops._host_steps(plan)
     assert list(bs) == plan.bs and list(off) == plan.off[:plan.T]
     assert ops._host_steps(plan) is plan.__dict__["_host_steps"]
+
+
+def test_header_and_ctypes_signatures_agree_on_arity():
+    """Every declaration in include/sn100.h has as many parameters as its ctypes signature in _lib.py (a silent
+    mismatch would shift every argument after it)."""
+    hdr = open(os.path.join(ROOT, "include", "sn100.h")).read()
+    seen = 0
+    for m in re.finditer(r"\b(?:int32_t|int64_t|const char\*)\s+(sn_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, re.S):
+        name, args = m.group(1), m.group(2)
+        n = 0 if args.strip() in ("void", "") else len(args.split(","))
+        assert name in _lib.SIGNATURES, name
+        assert len(_lib.SIGNATURES[name][1]) == n, (name, n, len(_lib.SIGNATURES[name][1]))
+        seen += 1
+    assert seen == len(_lib.SIGNATURES)
