@@ -9,6 +9,19 @@ import torch
 
 ALIGN = 64  # elements (256 B)
 
+# Bumped whenever ANY module registers a parameter (``decoder.B.weight = nn.Parameter(pretrained)`` goes through
+# Module.register_parameter): arenas compare it with the epoch they were bound at and re-validate every parameter
+# OBJECT, not just the storage pointers of two sentinels, when it moved.
+PARAM_EPOCH = [0]
+
+
+def _on_register_parameter(module, name, param):
+    PARAM_EPOCH[0] += 1
+    return None
+
+
+torch.nn.modules.module.register_module_parameter_registration_hook(_on_register_parameter)
+
 
 class ParamArena:
     def __init__(self, module, groups):
@@ -37,6 +50,7 @@ class ParamArena:
         self.gflat = None
         self.version = 0
         self._sentinels = (listed[0], listed[-1])
+        self._epoch = PARAM_EPOCH[0]
 
     # -- binding -------------------------------------------------------------------------------
     def bound(self):
@@ -45,6 +59,16 @@ class ParamArena:
         (This runs several times per decode step: a full walk over 59-89 parameters each time was measurable.)"""
         if self.flat is None:
             return False
+        if self._epoch != PARAM_EPOCH[0]:
+            # some module registered a parameter since the last check: a Parameter object of this decoder may have
+            # been replaced -> compare object identities, adopt the new objects and rebuild if anything changed
+            self._epoch = PARAM_EPOCH[0]
+            live = dict(self.module.named_parameters())
+            if set(live) != set(self.named) or any(live[n] is not self.named[n] for n in live):
+                if set(live) != set(self.named):
+                    raise RuntimeError("the decoder's parameter set changed after the arena was laid out")
+                self.named = live
+                return False
         base = self.flat.data_ptr()
         self._checks = getattr(self, "_checks", 0) + 1
         if self._checks & 255 != 1:

@@ -294,14 +294,24 @@ __global__ void __launch_bounds__(256) dp_adam_fused_kernel(DpPeers P, AdamRange
   if (blockIdx.x == 0 && threadIdx.x < P.world) st_release_sys(P.pad[threadIdx.x] + PAD_ARRIVE + P.rank, e);
   if (threadIdx.x < P.world) { while (ld_acquire_sys(mypad + PAD_ARRIVE + threadIdx.x) < e) { } }
   __syncthreads();
-  // 3. my chunks: reduce over the peers (fixed rank order), clamp, Adam, store the new parameters everywhere
+  // 3. my chunks: reduce over the peers (fixed rank order), clamp, Adam, store the new parameters everywhere.
+  // Ownership is a function of the ABSOLUTE arena offset only -- element i belongs to rank (i / ADAM_CHUNK) % world --
+  // so it does not move when the set of active ranges changes between calls (early / late exchange, accumulation,
+  // only= / skip=): the Adam moments of an element always live on the same rank.  Chunks are therefore cut on the
+  // absolute ADAM_CHUNK grid and clipped to their range; a slot of W consecutive chunks holds (about) one owned chunk.
   const int64_t total_chunks = R.chunk_start[R.n];
-  for (int64_t ch = P.rank + (int64_t)P.world * blockIdx.x; ch < total_chunks; ch += (int64_t)P.world * gridDim.x) {
+  const int64_t nslots = (total_chunks + W - 1) / W;
+  for (int64_t slot = blockIdx.x; slot < nslots; slot += gridDim.x)
+  for (int j = 0; j < W; ++j) {
+    const int64_t ch = slot * W + j;
+    if (ch >= total_chunks) break;
     int r = 0;
     while (ch >= R.chunk_start[r + 1]) ++r;
-    const int64_t base = R.off[r] + (ch - R.chunk_start[r]) * ADAM_CHUNK;
+    const int64_t aid = R.off[r] / ADAM_CHUNK + (ch - R.chunk_start[r]);      // absolute chunk id
+    if ((int)(aid % W) != P.rank) continue;
     const int64_t end = R.off[r] + R.len[r];
-    const int64_t lim = base + ADAM_CHUNK < end ? base + ADAM_CHUNK : end;
+    const int64_t base = aid * ADAM_CHUNK > R.off[r] ? aid * ADAM_CHUNK : R.off[r];
+    const int64_t lim = (aid + 1) * ADAM_CHUNK < end ? (aid + 1) * ADAM_CHUNK : end;
     const float ss = coef[2 * r], bc = coef[2 * r + 1];
     if ((base & 3) == 0 && lim - base == ADAM_CHUNK) {
 #pragma unroll
@@ -527,7 +537,9 @@ int32_t sn_dp_adam_fused(int32_t world, int32_t rank, void* const* grad_ptrs, vo
     R.off[i] = ranges[2 * i]; R.len[i] = ranges[2 * i + 1]; R.step_idx[i] = step_idx[i];
     R.step_size[i] = 0.f; R.bc2_sqrt[i] = 1.f;
     SN_REQUIRE(R.off[i] >= 0 && R.len[i] >= 0, "sn_dp_adam_fused: bad range %d", i);
-    R.chunk_start[i + 1] = R.chunk_start[i] + (R.len[i] + ADAM_CHUNK - 1) / ADAM_CHUNK;
+    // chunks on the absolute ADAM_CHUNK grid of the arena (ownership must not depend on the active set, see the kernel)
+    R.chunk_start[i + 1] = R.chunk_start[i] +
+        (R.len[i] > 0 ? (R.off[i] + R.len[i] - 1) / ADAM_CHUNK - R.off[i] / ADAM_CHUNK + 1 : 0);
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (n_ranges > 0) adam_prepare_kernel<<<1, 64, 0, st>>>(R, steps_dev, lr_dev, coef_ws, beta1, beta2);

@@ -97,6 +97,18 @@ class _DecoderBase(nn.Module):
     cell = ops.CELL_FACTORED
     precision = "fp32"
 
+    # per-process caches that must not travel with a pickled decoder (CUDA graphs, streams and events cannot be
+    # pickled; the arena is rebuilt on first use).  The reference pickles the whole decoder every epoch
+    # (save_checkpoint, stylenet/utils.py:62-90) and un-pickles it to resume (train_multitask.py:169-176).
+    _TRANSIENT = ("_greedy_graphs", "_decode_sessions", "_side_streams", "_out_w16", "_out_w16_pref", "_out_w16_ev",
+                  "_out_h16", "_seed_dev", "_arena", "_att_cache")
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        for k in self._TRANSIENT:
+            st.pop(k, None)
+        return st
+
     def set_precision(self, precision):
         """"fp32": every GEMM in fp32 FFMA (reference-exact mode, <=1e-5).  "bf16": GEMM operands in bf16 on
         the tcgen05 tensor cores, fp32 accumulation in TMEM; recurrence state, gate math, softmax/NLL,
@@ -544,7 +556,7 @@ class _DecoderBase(nn.Module):
         copied into its static buffers, the returned logits are a copy of its static output."""
         key = (tuple(int(l) for l in lengths), mode, tuple(captions.shape),
                None if features is None else tuple(features.shape), self.precision, self.training,
-               captions.device.index)
+               captions.device.index, self.arena().version)
         cache = self.__dict__.setdefault("_greedy_graphs", OrderedDict())
         sess = cache.get(key)
         if sess is None:

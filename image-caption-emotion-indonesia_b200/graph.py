@@ -1,7 +1,8 @@
 """CUDA-graph capture of one whole training step (forward + fused loss + backward + clamp/Adam).  The step
 issues ~40 kernels whose total device time at the reference batch sizes (64-96) is under 1 ms: launched one by
 one from Python the step is launch-bound, replayed from a graph it is not.  Everything step-dependent lives in
-device memory (dropout counter, Adam step counters, learning rate), so a replay is a real, fresh training step.
+device memory (dropout counter, Adam step counters, learning rate -- re-synchronised from ``param_groups`` before every
+replay), so a replay is a real, fresh training step.
 
 Data parallel (world > 1): the step is captured as THREE graphs split at the two points where a gradient bucket
 becomes final, and the NCCL all-reduces are issued eagerly between the replays:
@@ -79,6 +80,10 @@ class GraphedTrainStep:
         if features is not None:
             self.features.copy_(features, non_blocking=True)
         tr = self.trainer
+        # the learning rate is read from device memory by the captured Adam kernels: refresh it (eagerly, same stream)
+        # when adjust_learning_rate (stylenet/utils.py:116-124) changed param_groups since the last replay
+        tr.optimizer._state()
+        tr.optimizer._sync_lr()
         last = len(self.segments) - 1
         for i, (g, ranges) in enumerate(self.segments):
             if i == last and last > 0:

@@ -282,7 +282,34 @@ def to_bf16_padded(x, pad_to=8):
     return out
 
 
+# K3 implementation in bf16 mode: "auto" = the cluster form (sn_recur_cl.cu) whenever the hidden size supports it and all
+# sample slices fit the device at once, else the flag-synchronised persistent kernel; "cluster" / "flags" force one.
+RECUR_IMPL = ["auto"]
+_cl_max = {}
+
+
+def recur_cluster_ok(H, B):
+    impl = RECUR_IMPL[0]
+    if impl == "flags" or H not in (128, 256, 512):
+        return False
+    key = (torch.cuda.current_device(), H)
+    n = _cl_max.get(key)
+    if n is None:
+        n = _cl_max[key] = int(lib().sn_recur_cl_max_clusters(H))
+    if impl == "cluster":
+        if n < 1:
+            raise _lib.SnError("cluster form of the recurrence is not available for H=%d on this device" % H)
+        return True
+    return n >= 1 and (B + 15) // 16 <= n
+
+
 def recur_fwd_bf16(cell, H, B, bs, off, t0, t1, XP, Whh_b, bhh, h_init, Hall, Hb, Hprevb, Call, gates, c_state):
+    if recur_cluster_ok(H, B):
+        check(lib().sn_recur_fwd_cl(cell, H, B, _ptr(bs), _ptr(off), t0, t1, _ptr(_req(XP)),
+                                    _ptr(_req(Whh_b, torch.bfloat16)), _ptr(bhh), _ptr(h_init), _ptr(Hall),
+                                    _ptr(_req(Hb, torch.bfloat16)), _ptr(Hprevb), _ptr(Call), _ptr(gates),
+                                    _ptr(c_state), _stream()), "sn_recur_fwd_cl")
+        return
     ws = _recur_ws(XP.device, t1 + 1)
     check(lib().sn_recur_fwd_bf16(cell, H, B, _ptr(bs), _ptr(off), t0, t1, _ptr(_req(XP)),
                                   _ptr(_req(Whh_b, torch.bfloat16)), _ptr(bhh), _ptr(h_init), _ptr(Hall),
@@ -291,6 +318,12 @@ def recur_fwd_bf16(cell, H, B, bs, off, t0, t1, XP, Whh_b, bhh, h_init, Hall, Hb
 
 
 def recur_bwd_bf16(cell, H, B, bs, off, t0, t1, Whh_b, c_init, Call, gates, dHall, dZ, dZb, dh_carry, dc_carry):
+    if recur_cluster_ok(H, B):
+        check(lib().sn_recur_bwd_cl(cell, H, B, _ptr(bs), _ptr(off), t0, t1, _ptr(_req(Whh_b, torch.bfloat16)),
+                                    _ptr(c_init), _ptr(Call), _ptr(gates), _ptr(_req(dHall)), _ptr(dZ),
+                                    _ptr(_req(dZb, torch.bfloat16)), _ptr(dh_carry), _ptr(dc_carry), _stream()),
+              "sn_recur_bwd_cl")
+        return
     ws = _recur_ws(dZb.device, t1 + 1)
     check(lib().sn_recur_bwd_bf16(cell, H, B, _ptr(bs), _ptr(off), t0, t1, _ptr(_req(Whh_b, torch.bfloat16)),
                                   _ptr(c_init), _ptr(Call), _ptr(gates), _ptr(_req(dHall)), _ptr(dZ),

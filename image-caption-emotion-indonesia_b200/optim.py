@@ -26,13 +26,20 @@ class FusedClampAdam:
     # -- state -----------------------------------------------------------------------------------------
     def _state(self):
         a = self.decoder.arena()
-        if self._arena_version != a.version:
+        if self._arena_version != a.version or self.m is None:
             dev = a.flat.device
-            self.m = torch.zeros_like(a.flat)
-            self.v = torch.zeros_like(a.flat)
-            self.names = list(a.named)
+            names = list(a.named)
+            if self.m is not None and self.m.numel() == a.total and getattr(self, "names", None) == names:
+                # the arena was re-bound (.to() / .cuda(), an un-pickled checkpoint, a replaced Parameter): the layout
+                # is a pure function of the parameter shapes, so moments and step counters carry over
+                self.m, self.v = self.m.to(dev), self.v.to(dev)
+                self.steps_dev = self.steps_dev.to(dev)
+            else:
+                self.m = torch.zeros_like(a.flat)
+                self.v = torch.zeros_like(a.flat)
+                self.steps_dev = torch.zeros(len(names), dtype=torch.int32, device=dev)
+            self.names = names
             self.index = {n: i for i, n in enumerate(self.names)}
-            self.steps_dev = torch.zeros(len(self.names), dtype=torch.int32, device=dev)
             self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
             self.coef_ws = torch.zeros(2 * len(self.names) + 2, dtype=torch.float32, device=dev)
             self._lr_on_device = None
@@ -53,6 +60,73 @@ class FusedClampAdam:
     def zero_grad(self):
         for p in self.param_groups[0]["params"]:
             p.grad = None
+
+    # -- checkpointing -----------------------------------------------------------------------------------
+    def __getstate__(self):
+        """Whole-object pickling (the reference's save_checkpoint pickles optimizers, stylenet/utils.py:62-90)."""
+        st = self.__dict__.copy()
+        st["_lr_on_device"] = None
+        return st
+
+    def state_dict(self):
+        """torch.optim.Adam's schema: {"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [...]} with i
+        the position in ``param_groups[0]["params"]``; only parameters that took at least one step have state.
+        Under the peer-fused data-parallel step each rank holds the moments of the chunks it owns only (ZeRO-1
+        style, ownership = (arena offset / 4096) % world): all-reduce ``m`` / ``v`` (SUM) before saving there."""
+        a = self._state()
+        params = self.param_groups[0]["params"]
+        by_id = {id(p): n for n, p in a.named.items()}
+        steps = self.steps_dev.tolist()
+        state = {}
+        for i, p in enumerate(params):
+            n = by_id.get(id(p))
+            if n is not None:
+                st = self.extra_state.get(("arena", n))
+                if st is not None and int(st["step"].item()) > 0:      # stepped through a foreign gradient tensor
+                    state[i] = {"step": st["step"].float().reshape(()).clone(), "exp_avg": st["m"].clone(),
+                                "exp_avg_sq": st["v"].clone()}
+                elif steps[self.index[n]] > 0:
+                    o, k = a.offset[n], a.numel[n]
+                    state[i] = {"step": torch.tensor(float(steps[self.index[n]])),
+                                "exp_avg": self.m[o:o + k].view(p.shape).clone(),
+                                "exp_avg_sq": self.v[o:o + k].view(p.shape).clone()}
+        for j, p in enumerate(self.extra):
+            st = self.extra_state.get(("extra", j))
+            if st is not None and int(st["step"].item()) > 0:
+                state[len(params) - len(self.extra) + j] = {
+                    "step": st["step"].float().reshape(()).clone(), "exp_avg": st["m"].clone(), "exp_avg_sq": st["v"].clone()}
+        group = {"lr": self.param_groups[0]["lr"], "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0,
+                 "amsgrad": False, "grad_clip": self.grad_clip, "params": list(range(len(params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        a = self._state()
+        params = self.param_groups[0]["params"]
+        group = sd["param_groups"][0]
+        if len(group["params"]) != len(params):
+            raise ValueError("loaded state dict has a different number of parameters")
+        self.param_groups[0]["lr"] = float(group["lr"])
+        self.betas, self.eps = tuple(group.get("betas", self.betas)), float(group.get("eps", self.eps))
+        by_id = {id(p): n for n, p in a.named.items()}
+        self.m.zero_(); self.v.zero_(); self.steps_dev.zero_()
+        self.extra_state = {}
+        steps = [0] * len(self.names)
+        for i, st in sd["state"].items():
+            p = params[int(i)]
+            n = by_id.get(id(p))
+            if n is not None:
+                o, k = a.offset[n], a.numel[n]
+                self.m[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                self.v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                steps[self.index[n]] = int(float(st["step"]))
+            else:
+                j = int(i) - (len(params) - len(self.extra))
+                self.extra_state[("extra", j)] = {
+                    "m": st["exp_avg"].to(p.device).clone(), "v": st["exp_avg_sq"].to(p.device).clone(),
+                    "step": torch.full((1,), int(float(st["step"])), dtype=torch.int32, device=p.device),
+                    "coef": torch.zeros(2, dtype=torch.float32, device=p.device)}
+        self.steps_dev.copy_(torch.tensor(steps, dtype=torch.int32))
+        self._lr_on_device = None
 
     # -- step ------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -172,6 +172,25 @@ int32_t sn_recur_bwd_bf16(int32_t cell, int64_t H, int64_t B, const int32_t* bat
                           const float* dHall, float* dZ, void* dZb, float* dh_carry, float* dc_carry,
                           void* ws, void* stream);
 
+/* K3, bf16 mode, CLUSTER form (sn_recur_cl.cu) -- same contract and arguments as sn_recur_{fwd,bwd}_bf16 (no work
+ * space: nothing is exchanged through global memory).  Each slice of 16 samples runs inside one thread-block cluster
+ * of H/32 CTAs for all steps: the bf16 W_hh slice of a CTA stays in registers, h_t (forward) / the fp32 dh partials
+ * (backward) travel through distributed shared memory with st.async + mbarrier complete_tx.  Clusters are independent,
+ * so there is no co-residency requirement (a plain launch cannot deadlock).  H in {128, 256, 512}.
+ * replaces: stylenet/model.py:147-153,180-187 ; nic/model.py:77 (as above).
+ * sn_recur_cl_max_clusters: how many such clusters the device can run at once (0 = form not available for this H). */
+int32_t sn_recur_cl_max_clusters(int64_t H);
+int32_t sn_recur_fwd_cl(int32_t cell, int64_t H, int64_t B, const int32_t* batch_sizes,
+                        const int32_t* offsets, int32_t t0, int32_t t1, const float* XP,
+                        const void* Whh_bf16, const float* bhh, const float* h_init, float* Hall,
+                        void* Hb, void* Hprevb, float* Call, float* gates, float* c_state,
+                        void* stream);
+int32_t sn_recur_bwd_cl(int32_t cell, int64_t H, int64_t B, const int32_t* batch_sizes,
+                        const int32_t* offsets, int32_t t0, int32_t t1, const void* Whh_bf16,
+                        const float* c_init, const float* Call, const float* gates,
+                        const float* dHall, float* dZ, void* dZb, float* dh_carry, float* dc_carry,
+                        void* stream);
+
 /* K3 in the LARGE-BATCH regime (B >= ~1000 samples per GPU): one tcgen05 CTA-pair GEMM per time step with the
  * cell fused into the epilogue, instead of the latency-optimised persistent kernel above.
  * replaces the same call sites: forward_step's W_g(h) + gate math  stylenet/model.py:119-153, nn.LSTMCell nic/model.py:77

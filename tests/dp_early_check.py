@@ -24,19 +24,22 @@ def main():
     idx, my_lens = sn.shard_lengths(lens, world, rank)
     cap_d, feats_d = cap[idx].to(dev), feats[idx].to(dev)
     res = []
-    for early in (True, False):
-        dp.EARLY_PEER_EXCHANGE[0] = early
+    # all early / all late / ALTERNATING: the set of ranges in one exchange call changes from step to step in the last
+    # schedule, which must not move the ownership of an element (its Adam moments live on exactly one rank)
+    for schedule in ((True,) * 4, (False,) * 4, (True, False, True, False)):
         torch.manual_seed(0)
         dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0).to(dev).train().set_precision("bf16")
         tr = sn.DataParallelTrainer(dec, sn.FusedClampAdam(dec, lr=5e-4), comm="peer")
-        for _ in range(3):
+        for early in schedule:
+            dp.EARLY_PEER_EXCHANGE[0] = early
             loss, _ = tr.step(cap_d, my_lens, feats_d, n_global=n_global, mode="sad")
         torch.cuda.synchronize()
         dist.barrier()
         res.append((loss.item(), {n: p.detach().clone() for n, p in dec.named_parameters()}))
     dp.EARLY_PEER_EXCHANGE[0] = True
-    worst = max(((res[0][1][n] - res[1][1][n]).norm() / res[1][1][n].norm().clamp_min(1e-30)).item() for n in res[0][1])
-    ok = worst < 1e-5 and abs(res[0][0] - res[1][0]) < 1e-5 * abs(res[1][0])
+    worst = max(((res[k][1][n] - res[1][1][n]).norm() / res[1][1][n].norm().clamp_min(1e-30)).item()
+                for k in (0, 2) for n in res[0][1])
+    ok = worst < 1e-5 and all(abs(res[k][0] - res[1][0]) < 1e-5 * abs(res[1][0]) for k in (0, 2))
     # every rank must also hold the same parameters as rank 0 (the all-gather of both calls reached everybody)
     for n, p in res[0][1].items():
         q = p.clone()

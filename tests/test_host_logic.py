@@ -215,3 +215,90 @@ def test_header_and_ctypes_signatures_agree_on_arity():
         assert len(_lib.SIGNATURES[name][1]) == n, (name, n, len(_lib.SIGNATURES[name][1]))
         seen += 1
     assert seen == len(_lib.SIGNATURES)
+
+
+def test_arena_rebinds_when_a_parameter_object_is_replaced():
+    """``decoder.B.weight = nn.Parameter(pretrained)`` (a new Parameter OBJECT in the middle of the layout) must be
+    picked up: the kernels read the arena, so a stale snapshot would silently keep using the old values."""
+    torch.manual_seed(0)
+    dec = sn.DecoderFactoredLSTM(12, 16, 20, 53, 1)
+    a = dec.arena()
+    v0 = a.version
+    new_w = torch.nn.Parameter(torch.full((16, 20), 0.25))
+    dec.U_f.weight = new_w                      # neither the first nor the last parameter of the layout
+    a2 = dec.arena()
+    assert a2.version == v0 + 1
+    assert a2.named["U_f.weight"] is dec.U_f.weight
+    o, n = a2.offset["U_f.weight"], a2.numel["U_f.weight"]
+    assert torch.equal(a2.flat[o:o + n], torch.full((n,), 0.25))
+    assert dec.U_f.weight.data_ptr() == a2.flat.data_ptr() + 4 * o
+    # unrelated registrations elsewhere only cost one identity walk, no rebuild
+    torch.nn.Linear(3, 3)
+    assert dec.arena().version == v0 + 1
+
+
+def test_decoder_and_optimizer_pickle_round_trip():
+    """save_checkpoint pickles the whole decoder and optimizers (stylenet/utils.py:62-90); per-process caches (CUDA
+    graphs, streams, events) must not travel, parameters and Adam state must."""
+    import io
+    import threading
+    torch.manual_seed(0)
+    dec = sn.DecoderFactoredLSTM(12, 16, 20, 53, 1)
+    dec.arena()
+    opt = sn.FusedClampAdam(dec, lr=3e-4)
+    a = opt._state()
+    opt.m.uniform_(-1, 1); opt.v.uniform_(0, 1); opt.steps_dev.fill_(3)
+    # what a greedy forward / sample() leave behind: objects that cannot be pickled
+    dec.__dict__["_greedy_graphs"] = {"k": threading.Lock()}
+    dec.__dict__["_decode_sessions"] = {"k": threading.Lock()}
+    dec.__dict__["_side_streams"] = {0: threading.Lock()}
+    dec.__dict__["_out_w16_ev"] = threading.Lock()
+    buf = io.BytesIO()
+    torch.save({"decoder": dec, "optimizer": opt}, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    dec2, opt2 = back["decoder"], back["optimizer"]
+    assert "_greedy_graphs" not in dec2.__dict__ and "_arena" not in dec2.__dict__
+    for (n, p), (n2, q) in zip(dec.state_dict().items(), dec2.state_dict().items()):
+        assert n == n2 and torch.equal(p, q)
+    assert opt2.decoder is dec2
+    a2 = opt2._state()                          # re-binds to the un-pickled decoder's new arena, keeps the moments
+    assert torch.equal(opt2.m, opt.m) and torch.equal(opt2.v, opt.v)
+    assert opt2.steps_dev.tolist() == opt.steps_dev.tolist()
+    assert a2.total == a.total
+
+
+def test_optimizer_state_dict_uses_the_torch_adam_schema():
+    torch.manual_seed(0)
+    dec = sn.DecoderFactoredLSTM(12, 16, 20, 53, 1)
+    opt = sn.FusedClampAdam(dec, lr=3e-4)
+    a = opt._state()
+    opt.m.uniform_(-1, 1); opt.v.uniform_(0, 1)
+    stepped = ["C.weight", "C.bias", "S_happy_i.weight"]
+    for n in stepped:
+        opt.steps_dev[opt.index[n]] = 7
+    sd = opt.state_dict()
+    params = opt.param_groups[0]["params"]
+    names = {id(p): n for n, p in dec.named_parameters()}
+    assert sorted(names[id(params[i])] for i in sd["state"]) == sorted(stepped)
+    g = sd["param_groups"][0]
+    assert g["lr"] == 3e-4 and g["betas"] == (0.9, 0.999) and g["eps"] == 1e-8 and g["params"] == list(range(len(params)))
+    for i, st in sd["state"].items():
+        n = names[id(params[i])]
+        assert float(st["step"]) == 7.0 and st["exp_avg"].shape == params[i].shape
+        assert torch.equal(st["exp_avg_sq"].reshape(-1), opt.v[a.offset[n]:a.offset[n] + a.numel[n]])
+    # torch.optim.Adam accepts it (same schema) ...
+    ref = torch.optim.Adam(dec.parameters(), lr=1.0)
+    ref.load_state_dict(sd)
+    assert ref.param_groups[0]["lr"] == 3e-4
+    # ... and a fresh FusedClampAdam restores moments, step counters and lr from it
+    dec2 = sn.DecoderFactoredLSTM(12, 16, 20, 53, 1)
+    opt2 = sn.FusedClampAdam(dec2, lr=1.0)
+    opt2.load_state_dict(sd)
+    a2 = opt2._state()
+    for n in stepped:
+        o, k = a2.offset[n], a2.numel[n]
+        assert torch.equal(opt2.m[o:o + k], opt.m[o:o + k]) and opt2.steps_dev[opt2.index[n]].item() == 7
+    o, k = a2.offset["V_i.weight"], a2.numel["V_i.weight"]
+    assert not opt2.m[o:o + k].any()             # parameters without state start from zero moments
+    assert opt2.param_groups[0]["lr"] == 3e-4
