@@ -5,6 +5,8 @@ laid out so that the gate-stacked matrices the kernels consume ([V_i;V_f;V_o;V_c
 S of a style, ...) are contiguous sub-blocks.  ``nn.Parameter``s keep the reference names and shapes
 (state_dicts interchange) but their storage is a view into the arena, so the fused clamp+Adam kernel and
 the NCCL all-reduce each run over a handful of flat ranges instead of 59-89 tensors."""
+import weakref
+
 import torch
 
 ALIGN = 64  # elements (256 B)
@@ -27,7 +29,7 @@ class ParamArena:
     def __init__(self, module, groups):
         """``groups``: list of lists of parameter names; names inside a group are laid out back to back
         (no padding) so the group can be viewed as one stacked matrix."""
-        self.module = module
+        self._module = weakref.ref(module)      # no decoder <-> arena reference cycle
         self.groups = groups
         self.named = dict(module.named_parameters())
         listed = [n for g in groups for n in g]
@@ -63,7 +65,7 @@ class ParamArena:
             # some module registered a parameter since the last check: a Parameter object of this decoder may have
             # been replaced -> compare object identities, adopt the new objects and rebuild if anything changed
             self._epoch = PARAM_EPOCH[0]
-            live = dict(self.module.named_parameters())
+            live = dict(self._module().named_parameters())
             if set(live) != set(self.named) or any(live[n] is not self.named[n] for n in live):
                 if set(live) != set(self.named):
                     raise RuntimeError("the decoder's parameter set changed after the arena was laid out")

@@ -31,7 +31,7 @@ namespace {
 
 constexpr int NTH = 512;         // threads per CTA (16 warps)
 constexpr int NS = 16;           // samples per cluster (= one m16 tile = one finisher warp per sample)
-constexpr int RP = 40;           // fp32 row pitch of the k-quarter partials (conflict-free 64-bit stores)
+constexpr int RP = 132;          // fp32 pitch of one sample row of k-quarter partials: 32 units x 4 gates + 4 (conflict-free 128-bit stores)
 constexpr int DP = 136;          // bf16 row pitch of the CTA's own dZ rows (128 + 8)
 
 struct CArgs {
@@ -84,6 +84,10 @@ __device__ __forceinline__ void st_async16(uint32_t dst_cluster, uint32_t v0, ui
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                ::"r"(dst_cluster), "r"(v0), "r"(v1), "r"(v2), "r"(v3), "r"(bar_cluster) : "memory");
 }
+__device__ __forceinline__ void st_async8(uint32_t dst_cluster, uint32_t v0, uint32_t v1, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+               ::"r"(dst_cluster), "r"(v0), "r"(v1), "r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
@@ -127,8 +131,8 @@ template <int H>
 struct FwdSmem {
   static constexpr int HP = H + 8;                                   // bf16 row pitch of the h tile (conflict-free ldmatrix)
   static constexpr size_t hbuf = 0;                                  // [2][NS][HP] bf16
-  static constexpr size_t red = hbuf + (size_t)2 * NS * HP * 2;      // [2][4 kq][4 gates][NS][RP] fp32
-  static constexpr size_t hst = red + (size_t)2 * 4 * 4 * NS * RP * 4;   // [NS][32] bf16
+  static constexpr size_t red = hbuf + (size_t)2 * NS * HP * 2;      // [2][4 kq][NS][RP]: (unit, gate) gate-fastest, fp32
+  static constexpr size_t hst = red + (size_t)2 * 4 * NS * RP * 4;   // [NS][32] bf16
   static constexpr size_t bars = hst + (size_t)NS * 32 * 2;          // [2] mbarrier
   static constexpr size_t tab = bars + 16;                           // per step: {live samples, first packed row}
   static constexpr size_t total = tab;                               // + 8 bytes per step (added at launch)
@@ -179,7 +183,9 @@ __global__ void __launch_bounds__(NTH, 1) recur_fwd_cl_kernel(CArgs a) {
   const int fs = warp, fu = lane, gs = s0 + fs, ug = u0 + fu;
   const bool live = gs < a.B;
   float c_reg = live ? a.c_state[(int64_t)gs * H + ug] : 0.f;
-  __nv_bfloat16 hprev = __float2bfloat16((live && a.h_init) ? a.h_init[(int64_t)gs * H + ug] : 0.f);
+  // h_init holds rows only for the samples alive at step t0 (the caller passes the Hall rows of step t0-1)
+  const int nv_first = clampi(a.bs[a.t0] - s0, 0, NS);
+  __nv_bfloat16 hprev = __float2bfloat16((fs < nv_first && a.h_init) ? a.h_init[(int64_t)gs * H + ug] : 0.f);
   float bh[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) bh[g] = a.bhh ? __ldg(a.bhh + g * H + ug) : 0.f;
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(NTH, 1) recur_fwd_cl_kernel(CArgs a) {
     for (int i = tid; i < NS * (H / 2); i += NTH) {
       const int r = i / (H / 2), c = (i - r * (H / 2)) * 2;
       float2 v = make_float2(0.f, 0.f);
-      if (a.h_init && s0 + r < a.B) v = *reinterpret_cast<const float2*>(a.h_init + (int64_t)(s0 + r) * H + c);
+      if (a.h_init && r < nv_first) v = *reinterpret_cast<const float2*>(a.h_init + (int64_t)(s0 + r) * H + c);
       *reinterpret_cast<__nv_bfloat162*>(hbuf + ((size_t)p0 * NS + r) * HP + c) = __floats2bfloat162_rn(v.x, v.y);
       *reinterpret_cast<__nv_bfloat162*>(hbuf + ((size_t)(p0 ^ 1) * NS + r) * HP + c) = __floats2bfloat162_rn(0.f, 0.f);
     }
@@ -243,25 +249,30 @@ __global__ void __launch_bounds__(NTH, 1) recur_fwd_cl_kernel(CArgs a) {
       }
     }
     {
-      // partial of k-quarter kq: rows = samples lane/4 (+8), columns = units oct*8 + 2*(lane%4) (+1)
-      float* rp = red + (((size_t)p * 4 + kq) * 4) * NS * RP + (lane >> 2) * RP + oct * 8 + (lane & 3) * 2;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        *reinterpret_cast<float2*>(rp + (size_t)g * NS * RP) = make_float2(acc[g][0], acc[g][1]);
-        *reinterpret_cast<float2*>(rp + (size_t)g * NS * RP + 8 * RP) = make_float2(acc[g][2], acc[g][3]);
-      }
+      // partial of k-quarter kq: rows = samples lane/4 (+8), columns = units oct*8 + 2*(lane%4) (+1); the four gates of a
+      // (sample, unit) are one float4
+      float* rp = red + (((size_t)p * 4 + kq) * NS + (lane >> 2)) * RP + (oct * 8 + (lane & 3) * 2) * 4;
+      *reinterpret_cast<float4*>(rp) = make_float4(acc[0][0], acc[1][0], acc[2][0], acc[3][0]);
+      *reinterpret_cast<float4*>(rp + 4) = make_float4(acc[0][1], acc[1][1], acc[2][1], acc[3][1]);
+      *reinterpret_cast<float4*>(rp + 8 * RP) = make_float4(acc[0][2], acc[1][2], acc[2][2], acc[3][2]);
+      *reinterpret_cast<float4*>(rp + 8 * RP + 4) = make_float4(acc[0][3], acc[1][3], acc[2][3], acc[3][3]);
     }
-    // the only CTA-wide barrier of the step.  `red` and the h buffers are double-buffered by step parity: a warp can
+    // `red` and the h buffers are double-buffered by step parity: a warp can
     // write red[p] / see peers overwrite hbuf[p] again only at step t+2, i.e. after the barrier of step t+1, which
     // every warp reaches after it finished reading them here.
     __syncthreads();
     __nv_bfloat16 hb = __float2bfloat16(0.f);
     if (valid) {
       float z[4];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float* r = red + (((size_t)p * 4) * 4 + g) * NS * RP + fs * RP + fu;
-        z[g] = ((r[0] + r[(size_t)4 * NS * RP]) + (r[(size_t)8 * NS * RP] + r[(size_t)12 * NS * RP])) + xp[g] + bh[g];
+      {
+        const float* r = red + ((size_t)p * 4 * NS + fs) * RP + fu * 4;
+        const float4 q0 = *reinterpret_cast<const float4*>(r), q1 = *reinterpret_cast<const float4*>(r + (size_t)NS * RP);
+        const float4 q2 = *reinterpret_cast<const float4*>(r + (size_t)2 * NS * RP);
+        const float4 q3 = *reinterpret_cast<const float4*>(r + (size_t)3 * NS * RP);
+        z[0] = ((q0.x + q1.x) + (q2.x + q3.x)) + xp[0] + bh[0];
+        z[1] = ((q0.y + q1.y) + (q2.y + q3.y)) + xp[1] + bh[1];
+        z[2] = ((q0.z + q1.z) + (q2.z + q3.z)) + xp[2] + bh[2];
+        z[3] = ((q0.w + q1.w) + (q2.w + q3.w)) + xp[3] + bh[3];
       }
       const float zo = a.cell == SN_CELL_LSTM ? z[3] : z[2], zc = a.cell == SN_CELL_LSTM ? z[2] : z[3];
       const float gi = sigmoid_fast(z[0]), gf = sigmoid_fast(z[1]), go = sigmoid_fast(zo), gc = tanh_fast(zc);
@@ -280,18 +291,20 @@ __global__ void __launch_bounds__(NTH, 1) recur_fwd_cl_kernel(CArgs a) {
       hprev = hb;
     }
     if (nvn > 0) {
-      // broadcast the 64 bytes (32 units, bf16) of this sample's h_t to all CS CTAs (this one included)
+      // broadcast this CTA's h_t block (NS samples x 32 units, bf16 = 1 KB) to all CS CTAs (this one included).
+      // Every st.async INSTRUCTION targets a single CTA (warp w serves CTA w when CS = 16): a warp-wide store whose
+      // lanes address 16 different CTAs is split into 16 transactions and made the forward send-bound (profiles/).
       hst[fs * 32 + fu] = hb;
-      __syncwarp();
-      if (fs < nvn) {
-        const uint32_t dst_local = smem_u32(hbuf + ((size_t)pn * NS + fs) * HP + u0);
-        for (int i = lane; i < 4 * CS; i += 32) {
-          const int dest = i >> 2, ch = i & 3;
-          const uint4 v = *reinterpret_cast<const uint4*>(hst + fs * 32 + ch * 8);
-          st_async16(mapa(dst_local + ch * 16, dest), v.x, v.y, v.z, v.w, mapa(bar0 + 8 * pn, dest));
+      __syncthreads();
+      for (int j = lane; j < 4 * CS; j += 32) {
+        const int i = warp * (4 * CS) + j;                     // (destination, 16-byte chunk) pair
+        const int dest = i >> 6, ch = i & 63, srow = ch >> 2, part = ch & 3;
+        if (srow < nvn) {
+          const uint4 v = *reinterpret_cast<const uint4*>(hst + srow * 32 + part * 8);
+          const uint32_t dst_local = smem_u32(hbuf + ((size_t)pn * NS + srow) * HP + u0 + part * 8);
+          st_async16(mapa(dst_local, dest), v.x, v.y, v.z, v.w, mapa(bar0 + 8 * pn, dest));
         }
       }
-      __syncwarp();
     }
   }
   if (live) a.c_state[(int64_t)gs * H + ug] = c_reg;
@@ -301,8 +314,8 @@ __global__ void __launch_bounds__(NTH, 1) recur_fwd_cl_kernel(CArgs a) {
 template <int H>
 struct BwdSmem {
   static constexpr int CS = H / 32;
-  static constexpr size_t recv = 0;                                        // [2][CS][NS][32] fp32
-  static constexpr size_t dzs = recv + (size_t)2 * CS * NS * 32 * 4;       // [2][NS][DP] bf16
+  static constexpr size_t recv = 0;                                        // [2][CS][NS][32] bf16 partials
+  static constexpr size_t dzs = recv + (size_t)2 * CS * NS * 32 * 2;       // [2][NS][DP] bf16
   static constexpr size_t bars = dzs + (size_t)2 * NS * DP * 2;
   static constexpr size_t tab = bars + 16;                                 // per step: {live samples, first packed row}
   static constexpr size_t stage = (size_t)64 * (H + 8) * 2;                // prologue staging of 64 W_hh rows (aliases recv/dzs)
@@ -316,7 +329,7 @@ template <int H>
 __global__ void __launch_bounds__(NTH, 1) recur_bwd_cl_kernel(CArgs a) {
   constexpr int CS = H / 32, NTB = H / 128;                   // n-tiles (8 units) per warp: 16 warps cover all H units
   extern __shared__ __align__(128) unsigned char smem[];
-  float* recv = reinterpret_cast<float*>(smem + BwdSmem<H>::recv);
+  __nv_bfloat16* recv = reinterpret_cast<__nv_bfloat16*>(smem + BwdSmem<H>::recv);
   __nv_bfloat16* dzs = reinterpret_cast<__nv_bfloat16*>(smem + BwdSmem<H>::dzs);
   const uint32_t bar0 = smem_u32(smem + BwdSmem<H>::bars);
 
@@ -354,6 +367,8 @@ __global__ void __launch_bounds__(NTH, 1) recur_bwd_cl_kernel(CArgs a) {
   const bool live = gs < a.B;
   const int64_t sidx = (int64_t)gs * H + ug;
   float dc_reg = live ? a.dc_carry[sidx] : 0.f;
+  // where unit fu sits inside a 64-byte (32 x bf16) row of partials, see the sender below
+  const int fpos = (((fu >> 4) * 2 + ((fu >> 2) & 1)) * 8) + ((fu >> 3) & 1) * 4 + (fu & 3);
 
   int2* tab = reinterpret_cast<int2*>(smem + BwdSmem<H>::total);
   for (int i = tid; i < a.t1 - a.t0; i += NTH)
@@ -376,7 +391,7 @@ __global__ void __launch_bounds__(NTH, 1) recur_bwd_cl_kernel(CArgs a) {
     if (nv == 0) continue;                                     // this cluster's samples all ended before step t
     const int nrec = (t + 1 < a.t1) ? tab[t + 1 - a.t0].x : 0;
     const int p = t & 1, pr = p ^ 1;                           // partials of dZ_t travel in buffer p, those of dZ_{t+1} in pr
-    if (tid == 0) mbar_expect_tx(bar0 + 8 * p, (uint32_t)(CS * nv * 128));
+    if (tid == 0) mbar_expect_tx(bar0 + 8 * p, (uint32_t)(CS * nv * 64));
     const bool valid = fs < nv;
     const int64_t row = (int64_t)tb.y + fs;
     float g4[4] = {0.f, 0.f, 0.f, 0.f}, cc = 0.f, cprev = 0.f, dhl = 0.f;
@@ -393,10 +408,10 @@ __global__ void __launch_bounds__(NTH, 1) recur_bwd_cl_kernel(CArgs a) {
     if (nrec > 0) {
       if (pr) { mbar_wait_cluster(bar0 + 8, ph1); ph1 ^= 1; } else { mbar_wait_cluster(bar0, ph0); ph0 ^= 1; }
       if (fs < nrec) {
-        const float* r = recv + ((size_t)pr * CS * NS + fs) * 32 + fu;
+        const __nv_bfloat16* r = recv + ((size_t)pr * CS * NS + fs) * 32 + fpos;
         float s = 0.f;
 #pragma unroll
-        for (int src = 0; src < CS; ++src) s += r[(size_t)src * NS * 32];
+        for (int src = 0; src < CS; ++src) s += __bfloat162float(r[(size_t)src * NS * 32]);
         dh_rec = s;
       }
     }
@@ -445,23 +460,38 @@ __global__ void __launch_bounds__(NTH, 1) recur_bwd_cl_kernel(CArgs a) {
 #pragma unroll
         for (int nt = 0; nt < NTB; ++nt) mma_bf16(acc[nt], af, Wr[kt][nt][0], Wr[kt][nt][1]);
       }
-      // lane pairs swap halves so that each lane owns 4 consecutive units of ONE sample: even lanes keep sample
-      // lane/4, odd lanes sample lane/4 + 8 -> one 16-byte st.async per lane and n-tile to the owner CTA
+      // lane pairs swap halves so that each lane owns 4 consecutive units of ONE sample (even lanes keep sample lane/4,
+      // odd lanes sample lane/4 + 8); the partials travel as bf16 (the owner sums the CS of them in fp32 -- the same
+      // rounding the exchanged dZ itself already has), two n-tiles per 16-byte st.async.  Position of local unit
+      // u = lnt*8 + r inside the 64-byte row: chunk (lnt/2)*2 + (r/4), then (lnt%2)*4 + r%4  (see fpos above).
       const bool odd = lane & 1;
       const int srow = (lane >> 2) + (odd ? 8 : 0);
       const int ub = ((lane & 3) >> 1) * 4;
+      uint32_t pk[NTB][2];
 #pragma unroll
       for (int nt = 0; nt < NTB; ++nt) {
         const float x0 = odd ? acc[nt][0] : acc[nt][2], x1 = odd ? acc[nt][1] : acc[nt][3];
         const float y0 = __shfl_xor_sync(0xffffffffu, x0, 1), y1 = __shfl_xor_sync(0xffffffffu, x1, 1);
         const float v0 = odd ? y0 : acc[nt][0], v1 = odd ? y1 : acc[nt][1];
         const float v2 = odd ? acc[nt][2] : y0, v3 = odd ? acc[nt][3] : y1;
-        if (srow < nv) {
-          const int unit = (warp * NTB + nt) * 8 + ub;          // first of the 4 units, in [0, H)
-          const int dest = unit >> 5;
-          const uint32_t dst_local = smem_u32(recv + (((size_t)p * CS + rank) * NS + srow) * 32 + (unit & 31));
-          st_async16(mapa(dst_local, dest), __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2),
-                     __float_as_uint(v3), mapa(bar0 + 8 * p, dest));
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+        pk[nt][0] = *reinterpret_cast<uint32_t*>(&lo);
+        pk[nt][1] = *reinterpret_cast<uint32_t*>(&hi);
+      }
+      if (srow < nv) {
+        const __nv_bfloat16* rowp = recv + (((size_t)p * CS + rank) * NS + srow) * 32;
+        if (NTB >= 2) {
+#pragma unroll
+          for (int nt = 0; nt + 1 < NTB; nt += 2) {
+            const int gnt = warp * NTB + nt;                    // global n-tile (8 units); even
+            const int dest = gnt >> 2, lnt = gnt & 3;
+            const uint32_t dst_local = smem_u32(rowp + ((lnt >> 1) * 2 + (ub >> 2)) * 8);
+            st_async16(mapa(dst_local, dest), pk[nt][0], pk[nt][1], pk[nt + 1][0], pk[nt + 1][1], mapa(bar0 + 8 * p, dest));
+          }
+        } else {
+          const int gnt = warp, dest = gnt >> 2, lnt = gnt & 3;
+          const uint32_t dst_local = smem_u32(rowp + ((lnt >> 1) * 2 + (ub >> 2)) * 8 + (lnt & 1) * 4);
+          st_async8(mapa(dst_local, dest), pk[0][0], pk[0][1], mapa(bar0 + 8 * p, dest));
         }
       }
     }
@@ -474,10 +504,10 @@ __global__ void __launch_bounds__(NTH, 1) recur_bwd_cl_kernel(CArgs a) {
       const int p = a.t0 & 1;
       if (p) mbar_wait_cluster(bar0 + 8, ph1); else mbar_wait_cluster(bar0, ph0);
       if (fs < nv0) {
-        const float* r = recv + ((size_t)p * CS * NS + fs) * 32 + fu;
+        const __nv_bfloat16* r = recv + ((size_t)p * CS * NS + fs) * 32 + fpos;
         float s = 0.f;
 #pragma unroll
-        for (int src = 0; src < CS; ++src) s += r[(size_t)src * NS * 32];
+        for (int src = 0; src < CS; ++src) s += __bfloat162float(r[(size_t)src * NS * 32]);
         dh_rec = s;
       }
     }

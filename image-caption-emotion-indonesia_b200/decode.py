@@ -2,6 +2,7 @@
 (stylenet/model.py:198-294, nic/model.py:117-207, app/backend/model.py:386-487) for n_img images at
 once, with all bookkeeping on the device and no host synchronisation inside the step loop."""
 import ctypes
+import weakref
 
 import torch
 
@@ -122,7 +123,8 @@ class _DecodeSession:
         E, H = emb.weight.shape[1], dec.hidden_size
         out = dec._out()
         V = out.weight.shape[0]
-        self.dec, self.mode, self.end_token = dec, mode, end_token
+        self._dec = weakref.ref(dec)          # the decoder owns its sessions: no reference cycle
+        self.mode, self.end_token = mode, end_token
         self.st = BeamState(n_img, k, dec.max_seq_length, start_token, dev)
         R = self.st.R
         f32 = dict(dtype=torch.float32, device=dev)
@@ -144,7 +146,7 @@ class _DecodeSession:
         self.arena_version = dec.arena().version
 
     def step(self, step, feed_image, device_step):
-        dec, st = self.dec, self.st
+        dec, st = self._dec(), self.st
         emb, out = dec._emb(), dec._out()
         R, H = st.R, dec.hidden_size
         if feed_image and step == 1:
@@ -173,7 +175,7 @@ class _DecodeSession:
             self.step(2, False, True)            # warm-up on the capture side stream (allocator, lazy state)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        with torch.cuda.graph(g):
+        with ops.no_gc_during_capture(), torch.cuda.graph(g):
             self.step(2, False, True)
         self.graph = g
 

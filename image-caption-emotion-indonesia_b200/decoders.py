@@ -576,7 +576,7 @@ class _DecoderBase(nn.Module):
             sess.features = None if features is None else features.detach().clone()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with ops.no_gc_during_capture(), torch.cuda.graph(g):
                 c = self._run_forward(plan, sess.captions, sess.features, coins, mode, save=False)
                 sess.out = self._vocab_logits(c.top.Hall, c.top.Hb)
             sess.graph = g
@@ -926,6 +926,13 @@ class DecoderFactoredLSTM(_DecoderBase):
         from .decode import beam_sample
         return beam_sample(self, features, start_token, end_token, k, mode, feed_image)[0]
 
+    def sample_batch(self, features, start_token, end_token, k=5, mode="factual", feed_image=False):
+        """``sample()`` for every row of ``features [n_img, E]`` in one batched beam search (an addition beside the kept
+        surface; replaces the per-image loop of stylenet/evaluator.py:74-81).  Returns a list of
+        LongTensor [1, L_i], element i identical to ``sample(features[i:i+1], ...)``."""
+        from .decode import beam_sample
+        return beam_sample(self, features, start_token, end_token, k, mode, feed_image)
+
 
 class DecoderRNN(_DecoderBase):
     """NIC LSTM decoder -- signature of nic/model.py:31-38."""
@@ -1024,3 +1031,8 @@ class DecoderRNN(_DecoderBase):
         """Beam search, nic/model.py:117-207 (``feed_image=True``: app/backend variant)."""
         from .decode import beam_sample
         return beam_sample(self, features, start_token, end_token, k, None, feed_image)[0]
+
+    def sample_batch(self, features, start_token, end_token, k=5, feed_image=False):
+        """Batched ``sample()``: one beam search over every row of ``features [n_img, E]`` (see DecoderFactoredLSTM)."""
+        from .decode import beam_sample
+        return beam_sample(self, features, start_token, end_token, k, None, feed_image)

@@ -144,7 +144,12 @@ class _AttBase(_DecoderBase):
             c.meanb = c.featsb = None
         self._lin(c, c.mean, c.meanb, self.init_h.weight, "init_h", self.init_h.bias, h0, B)
         self._lin(c, c.mean, c.meanb, self.init_c.weight, "init_c", self.init_c.bias, c.c0, B)
-        self._lin(c, feats.view(B * P, D), c.featsb, att.encoder_att.weight, "We", att.encoder_att.bias, c.att1, B * P)
+        # att1 (and att2 below) feed relu(att1 + att2): their sum decides a 0/1 mask, so an operand rounded to bf16 flips
+        # the mask wherever |att1 + att2| is below the rounding error and the attention net's gradients pick up a full
+        # w_f * dE term per flip (2.6e-2 at configs[2] dimensions, over the 2e-2 budget).  Both stay exact fp32
+        # contractions in bf16 mode; only GEMMs whose result is used linearly run on bf16 operands.
+        ops.gemm(ops.OP_NT, feats.view(B * P, D), att.encoder_att.weight, c.att1, B * P, A, D, D, D, A,
+                 bias=att.encoder_att.bias)
         all_tf = all(coins)
         c.tok_override = None if all_tf else torch.full((N,), -1, dtype=torch.int32, device=dev)
         if c.tc:
@@ -202,8 +207,8 @@ class _AttBase(_DecoderBase):
                 ops.gather_pack_fwd(captions, emb.weight, None, False, d["row_b"], d["row_t"], c.tok_override, n,
                                     c.X, c.p_drop, c.seed, row_off=r0, seed_dev=c.seed_dev, Xb=c.Xb)
                 self._proj_embed_part(c, r0, n)
-            self._lin(c, hprev, hprev_b, att.decoder_att.weight, "Wd", att.decoder_att.bias, c.att2, n, r0_out=r0,
-                      x_off_rows=hoff)
+            ops.gemm(ops.OP_NT, hprev, att.decoder_att.weight, c.att2, n, A, H, H, H, A, bias=att.decoder_att.bias,
+                     c_off=r0 * A)
             self._lin(c, hprev, hprev_b, self.f_beta.weight, "Wbeta", self.f_beta.bias, c.gate_pre, n, r0_out=r0,
                       x_off_rows=hoff)
             ops.att_step_fwd(c.att1, c.att2[r0:], feats, wfull, 0.0, c.gate_pre[r0:], n, P, A, D,
@@ -598,6 +603,12 @@ class DecoderFactoredLSTMAtt(_AttBase):
         from .decode import beam_sample_att
         return beam_sample_att(self, features, start_token, end_token, k, mode)[0]
 
+    def sample_batch(self, features, start_token, end_token, k=5, mode="factual"):
+        """``sample()`` for every image of ``features [n_img, S, S, D]`` in one batched beam search; returns a list of
+        LongTensor [1, L_i] (replaces the per-image loop of stylenet/evaluator.py:74-81)."""
+        from .decode import beam_sample_att
+        return beam_sample_att(self, features, start_token, end_token, k, mode)
+
 
 class DecoderRNNAtt(_AttBase):
     """Signature of nic/model_att.py:74-82."""
@@ -742,3 +753,8 @@ class DecoderRNNAtt(_AttBase):
         """Beam search with attention, nic/model_att.py:204-306."""
         from .decode import beam_sample_att
         return beam_sample_att(self, features, start_token, end_token, k, None)[0]
+
+    def sample_batch(self, features, start_token, end_token, k=5):
+        """Batched ``sample()`` over every image of ``features [n_img, S, S, D]``."""
+        from .decode import beam_sample_att
+        return beam_sample_att(self, features, start_token, end_token, k, None)

@@ -15,6 +15,7 @@ Only fully teacher-forced steps are captured (teacher_forcing_ratio >= 1): sched
 coin per time step (stylenet/model.py:181) that changes the kernel sequence."""
 import torch
 
+from . import ops
 from .dp import merged_ranges
 
 
@@ -40,7 +41,7 @@ class GraphedTrainStep:
         self.segments = []          # [(graph, ranges to all-reduce after it | None)]
         if (trainer.world == 1 or getattr(trainer, 'comm', 'nccl') == 'peer') and not force_segmented:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with ops.no_gc_during_capture(), torch.cuda.graph(g):
                 self.loss, self.stats = self.trainer.step(self.captions, self.lengths, self.features, **self.kw)
             self.segments.append((g, None))
         else:
@@ -67,10 +68,12 @@ class GraphedTrainStep:
             end(merged_ranges(arena, names))
             begin()
 
-        begin()
-        self.loss, self.stats = tr.forward_backward(self.captions, self.lengths, self.features, grad_hook=hook, **self.kw)
-        tr.optimizer.step()
-        end(None)
+        with ops.no_gc_during_capture():
+            begin()
+            self.loss, self.stats = tr.forward_backward(self.captions, self.lengths, self.features, grad_hook=hook,
+                                                        **self.kw)
+            tr.optimizer.step()
+            end(None)
 
     def __call__(self, captions=None, features=None):
         """Copy new inputs into the static buffers (async, same stream) and replay.  Returns the static loss

@@ -19,6 +19,24 @@ def check(rc, what=""):
 LAUNCHES = [0]
 
 
+class no_gc_during_capture:
+    """CUDA-graph capture runs in the global capture mode: if Python's cyclic garbage collector happens to free an
+    OLDER torch.cuda.CUDAGraph while a capture is in progress, its cudaGraphExecDestroy invalidates the capture
+    ("operation not permitted when stream is capturing (function reset)").  Collect first, then keep the collector off
+    for the duration of the capture."""
+
+    def __enter__(self):
+        import gc
+        gc.collect()
+        self.was = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *a):
+        import gc
+        if self.was:
+            gc.enable()
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 

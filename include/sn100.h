@@ -335,6 +335,25 @@ int32_t sn_beam_step(const float* logits, int64_t ld, int64_t V, int32_t n_img, 
                      int32_t* n_done, int32_t* out_seq, int32_t* out_len, int32_t* n_unfinished,
                      const int32_t* step_dev, void* stream);
 
+/* ---- encoder tail -> decoder hand-off ---------------------------------------------------
+ * sn_pool_nhwc_fwd: AdaptiveAvgPool2d((S,S)) + permute(0,2,3,1) of the trunk output (stylenet/model_att.py:24-28),
+ *   one pass: x [B,D,h,w] (NCHW) -> out [B,S,S,D] contiguous fp32, optional bf16 copy (GEMM operand) and optional
+ *   mean over the S*S pixels [B,D] (what init_hidden_state needs, model_att.py:185-194).  h*w <= 1024.
+ * sn_pool_nhwc_bwd: its backward (dx [B,D,h,w]); only needed when the trunk is fine-tuned.
+ * sn_bn1d_fwd / _bwd: BatchNorm1d(E, momentum) behind Linear(2048,E) (stylenet/model.py:19-26): batch statistics +
+ *   running-statistics update when training != 0, running statistics otherwise.  save_mean / save_invstd [E] feed
+ *   the backward (pass the running mean and rsqrt(running_var + eps) in eval mode). */
+int32_t sn_pool_nhwc_fwd(const float* x, int64_t B, int64_t D, int64_t h, int64_t w, int64_t S, float* out,
+                         void* out_bf16, float* mean, void* stream);
+int32_t sn_pool_nhwc_bwd(const float* dout, int64_t B, int64_t D, int64_t h, int64_t w, int64_t S, float* dx,
+                         void* stream);
+int32_t sn_bn1d_fwd(const float* x, int64_t B, int64_t E, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps, int32_t training,
+                    float* y, float* save_mean, float* save_invstd, void* stream);
+int32_t sn_bn1d_bwd(const float* x, const float* dy, int64_t B, int64_t E, const float* gamma,
+                    const float* save_mean, const float* save_invstd, int32_t training, float* dx,
+                    float* dgamma, float* dbeta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
