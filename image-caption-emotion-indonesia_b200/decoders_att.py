@@ -117,6 +117,9 @@ class _AttBase(_DecoderBase):
             feats = feats.float()
         feats = feats.reshape(B, -1, D).contiguous()
         P = feats.shape[1]
+        # produced by the fused encoder tail (encoders.EncoderCNNAtt) in the same pass that wrote `features`
+        pre_mean = getattr(features, "sn_mean", None)
+        pre_b16 = getattr(features, "sn_bf16", None)
         att = self._att_module(mode)
         c = _Ctx()
         c.plan, c.mode, c.captions, c.has_feat = plan, mode, captions, False
@@ -129,8 +132,11 @@ class _AttBase(_DecoderBase):
         b16 = dict(dtype=torch.bfloat16, device=dev)
         Whh, bhh = self._recurrent_weights()
         # hoisted, time-invariant pieces
-        c.mean = torch.empty(B, D, **f32)
-        ops.mean_pixels(feats, B, P, D, c.mean)
+        if pre_mean is not None and tuple(pre_mean.shape) == (B, D) and pre_mean.device == dev:
+            c.mean = pre_mean
+        else:
+            c.mean = torch.empty(B, D, **f32)
+            ops.mean_pixels(feats, B, P, D, c.mean)
         h0 = torch.empty(B, H, **f32)
         c.c0 = torch.empty(B, H, **f32)
         c.att1 = torch.empty(B * P, A, **f32)
@@ -139,7 +145,10 @@ class _AttBase(_DecoderBase):
                            ("We", att.encoder_att.weight), ("Wbeta", self.f_beta.weight), ("Whh", Whh)):
                 c.w16[key] = ops.to_bf16_padded(w)
             c.meanb = ops.to_bf16_padded(c.mean)
-            c.featsb = ops.to_bf16_padded(feats.view(B * P, D))
+            if pre_b16 is not None and pre_b16.numel() == B * P * D and pre_b16.device == dev:
+                c.featsb = pre_b16.view(B * P, D)
+            else:
+                c.featsb = ops.to_bf16_padded(feats.view(B * P, D))
         else:
             c.meanb = c.featsb = None
         self._lin(c, c.mean, c.meanb, self.init_h.weight, "init_h", self.init_h.bias, h0, B)

@@ -468,3 +468,31 @@ def ipc_open(handle):
     base = ctypes.c_void_p(0)
     _check(lib().sn_ipc_open(ctypes.cast(h, ctypes.c_void_p), ctypes.byref(base)), "sn_ipc_open")
     return base.value
+
+
+# ---- encoder tail -> decoder hand-off -----------------------------------------------------
+def pool_nhwc_fwd(x, S, out, out_bf16=None, mean=None):
+    """AdaptiveAvgPool2d((S,S)) + permute(0,2,3,1) of an NCHW map in one pass (stylenet/model_att.py:24-28)."""
+    B, D, h, w = x.shape
+    check(lib().sn_pool_nhwc_fwd(_ptr(_req(x)), B, D, h, w, S, _ptr(_req(out)), _ptr(out_bf16), _ptr(mean), _stream()),
+          "sn_pool_nhwc_fwd")
+    return out
+
+
+def pool_nhwc_bwd(dout, h, w, dx):
+    B, S, _, D = dout.shape
+    check(lib().sn_pool_nhwc_bwd(_ptr(_req(dout)), B, D, h, w, S, _ptr(_req(dx)), _stream()), "sn_pool_nhwc_bwd")
+    return dx
+
+
+def bn1d_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, training, y, save_mean, save_invstd):
+    B, E = x.shape
+    check(lib().sn_bn1d_fwd(_ptr(_req(x)), B, E, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+                            float(momentum), float(eps), 1 if training else 0, _ptr(_req(y)), _ptr(save_mean),
+                            _ptr(save_invstd), _stream()), "sn_bn1d_fwd")
+
+
+def bn1d_bwd(x, dy, gamma, save_mean, save_invstd, training, dx, dgamma, dbeta):
+    B, E = x.shape
+    check(lib().sn_bn1d_bwd(_ptr(_req(x)), _ptr(_req(dy)), B, E, _ptr(gamma), _ptr(save_mean), _ptr(save_invstd),
+                            1 if training else 0, _ptr(dx), _ptr(dgamma), _ptr(dbeta), _stream()), "sn_bn1d_bwd")

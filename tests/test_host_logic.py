@@ -302,3 +302,22 @@ def test_optimizer_state_dict_uses_the_torch_adam_schema():
     o, k = a2.offset["V_i.weight"], a2.numel["V_i.weight"]
     assert not opt2.m[o:o + k].any()             # parameters without state start from zero moments
     assert opt2.param_groups[0]["lr"] == 3e-4
+
+
+def test_encoder_signatures_and_state_dict_names_match_reference():
+    import inspect
+    import torch.nn as nn
+    assert list(inspect.signature(sn.EncoderCNN.__init__).parameters)[:2] == ["self", "embed_size"]
+    assert list(inspect.signature(sn.EncoderCNNAtt.__init__).parameters)[:2] == ["self", "encoded_image_size"]
+    assert inspect.signature(sn.EncoderCNNAtt.__init__).parameters["encoded_image_size"].default == 14
+    trunk = nn.Sequential(nn.Conv2d(3, 8, 3), nn.AdaptiveAvgPool2d((1, 1)))
+    enc = sn.EncoderCNN(12, backbone=trunk, in_features=8)
+    keys = list(enc.state_dict())
+    assert keys[:2] == ["resnet.0.weight", "resnet.0.bias"]
+    assert keys[2:] == ["linear.weight", "linear.bias", "bn.weight", "bn.bias", "bn.running_mean", "bn.running_var",
+                        "bn.num_batches_tracked"]
+    assert enc.bn.momentum == 0.01
+    with pytest.raises(RuntimeError):
+        enc(torch.randn(2, 3, 8, 8))            # CPU tensors: the tail has no CPU fallback
+    att = sn.EncoderCNNAtt(backbone=nn.Sequential(nn.Conv2d(3, 8, 3)))
+    assert att.encoded_image_size == 14 and list(att.state_dict()) == ["resnet.0.weight", "resnet.0.bias"]
