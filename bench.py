@@ -58,17 +58,36 @@ def workload_config(n_gpus, dtype, tokens_per_gpu=None, batch=None):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference modules on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, max_seconds=None):
+def _cpu_modules(workload):
+    """(decoder class source, kind): the UNMODIFIED reference module when /root/reference is importable in this
+    process (the build container), else the oracle port (the GPU box has no /root/reference)."""
+    from oracle import port
+    from oracle import reference_loader as rl
+    if rl.available():
+        try:
+            name = {"factored": "stylenet", "stack3": "stylenet", "att": "stylenet_att", "nic": "nic"}[workload]
+            return rl.load(name), "reference"
+        except Exception:
+            pass
+    return port, "port"
+
+
+def cpu_reference_run(steps, warmup, max_seconds=None, workload=None, batch=None):
     import random
     import torch
     from oracle import port
+    workload = workload or WORKLOAD
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    cap, lens, feats = port.synthetic_batch(B_PER_GPU, T, V, E=E, ragged=False, seed=0)
-    if WORKLOAD == "stack3":
+    bsz = batch or (64 if workload == "nic" else B_PER_GPU)
+    mod, kind = _cpu_modules(workload)
+    att = workload == "att"
+    cap, lens, feats = port.synthetic_batch(bsz, T, V, E=None if att else E, feat_shape=(7, 7, 2048) if att else None,
+                                            ragged=False, seed=0)
+    if workload == "stack3":
         from oracle.stack import stack_forward, stack_parameters
-        layers = [port.DecoderFactoredLSTM(E if l == 0 else H, H, 1024, V, 1, dropout=0.5) for l in range(3)]
+        layers = [mod.DecoderFactoredLSTM(E if l == 0 else H, H, 1024, V, 1, dropout=0.5) for l in range(3)]
         for layer in layers:
             layer.train()
         params = stack_parameters(layers)
@@ -87,12 +106,18 @@ def cpu_reference_run(steps, warmup, max_seconds=None):
             port.clip_gradient(opts[i], 0.5)
             opts[i].step()
     else:
-        dec = port.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5)
+        if workload == "att":
+            dec = mod.DecoderFactoredLSTMAtt(512, E, H, F, V, 1, dropout=0.5)
+        elif workload == "nic":
+            dec = mod.DecoderRNN(E, H, V, 1, dropout=0.5)
+        else:
+            dec = mod.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5)
         dec.train()
         opt = torch.optim.Adam(dec.parameters(), lr=5e-4)
+        mode = None if workload == "nic" else MODE
 
         def one_step():
-            port.train_step(dec, opt, cap, lens, feats, mode=MODE, teacher_forcing_ratio=1.0)
+            port.train_step(dec, opt, cap, lens, feats, mode=mode, teacher_forcing_ratio=1.0, attention=att)
     random.seed(0)
     for _ in range(warmup):
         one_step()
@@ -104,10 +129,12 @@ def cpu_reference_run(steps, warmup, max_seconds=None):
         if max_seconds is not None and time.perf_counter() - t0 > max_seconds:
             break
     dt = time.perf_counter() - t0
-    tok = done * sum(lens)
-    return {"value": tok / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d full steps of the same workload (B=%d, T=%d) in %.1f s, torch %s CPU, %d threads"
-                      % (done, B_PER_GPU, T, dt, torch.__version__, torch.get_num_threads()),
+    ntok = sum(lens) - (len(lens) if att else 0)
+    tok = done * ntok
+    return {"value": tok / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d full steps of the same workload (B=%d, T=%d) in %.1f s, %s, torch %s CPU, %d threads"
+                      % (done, bsz, T, dt, "unmodified reference module" if kind == "reference" else "oracle port",
+                         torch.__version__, torch.get_num_threads()),
             "ms_per_step": 1e3 * dt / done, "steps": done}
 
 
@@ -124,8 +151,9 @@ def run_reference(args):
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference = oracle/port.py (restatement of stylenet/model.py + train_multitask.py:377-389) on the "
-                "host cores; the reference is pure Python/torch so there is nothing to compile into oracle/_ref",
+        "note": "reference arm on the host cores: the unmodified reference module when /root/reference is importable "
+                "(build container), else oracle/port.py (its restatement, pinned at 1e-10); train step = "
+                "train_multitask.py:377-389.  The reference is pure Python/torch: nothing to compile into oracle/_ref",
     }
     print(json.dumps(line), flush=True)
 
@@ -207,11 +235,236 @@ def measured_peaks():
     return 6650.0, (1590.0, 1590.0), "fallback (B200_PROFILING.md)"
 
 
+class Workload:
+    """One training workload on this rank: model + optimizer(s) + captured step + host-side pinned inputs."""
+
+    def __init__(self, name, precision, dev, rank, batch=None, no_graph=False, segmented=False):
+        import torch
+        import icei_b200 as sn
+        from icei_b200 import ops
+        self.name, self.precision, self.dev = name, precision, dev
+        torch.manual_seed(0)                        # identical weights on every rank
+        if name == "att":
+            dec = sn.DecoderFactoredLSTMAtt(512, E, H, F, V, 1, dropout=0.5).to(dev)
+        elif name == "nic":
+            dec = sn.DecoderRNN(E, H, V, 1, dropout=0.5).to(dev)
+        elif name == "stack3":
+            dec = sn.DecoderFactoredLSTMStack(E, H, 1024, V, 3, dropout=0.5).to(dev)
+        else:
+            dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5).to(dev)
+        dec.train()
+        dec.set_precision(precision)
+        self.dec = dec
+        self.arith = "bf16 operands on tcgen05, fp32 accumulate (recurrence/softmax/Adam fp32)" if precision == "bf16" \
+            else "f32 FFMA"
+        opt = sn.FusedClampAdam(dec, lr=5e-4, grad_clip=0.5)
+        self.trainer = sn.DataParallelTrainer(dec, opt)
+        self.trainer_fac = None
+        if name == "stack3":      # multitask: a second optimizer object (own Adam moments) for the factual pass
+            self.trainer_fac = sn.DataParallelTrainer(dec, sn.FusedClampAdam(dec, lr=2e-4, grad_clip=0.5))
+        self.bsz = bsz = batch or (64 if name == "nic" else B_PER_GPU)
+        cap_h, lens, feat_h = synthetic_batch(bsz, T, V, E, seed=rank)
+        self.step_kw = {"teacher_forcing_ratio": 1.0}
+        if name != "nic":
+            self.step_kw["mode"] = MODE
+        if name == "att":
+            feat_h = torch.randn(bsz, 7, 7, 2048, generator=torch.Generator().manual_seed(100 + rank))
+            full_cap = cap_h
+            cap_h = full_cap[:, :-1].contiguous()                  # inputs; targets = packed full[:, 1:]
+            lens = [l - 1 for l in lens]
+            tgt_idx = torch.cat([torch.arange(b) * T + (t + 1) for t, b in enumerate([bsz] * (T - 1))])
+            self.step_kw["targets"] = full_cap.reshape(-1)[tgt_idx].to(dev)
+        self.lens = lens
+        self.cap_pin, self.feat_pin = cap_h.pin_memory(), feat_h.pin_memory()
+        self.cap_d, self.feat_d = self.cap_pin.to(dev), self.feat_pin.to(dev)
+        self.loss_pin = torch.zeros(1).pin_memory()
+        self.n_tok = sum(lens)
+        self.h2d = self.cap_pin.numel() * 8 + self.feat_pin.numel() * 4
+        self.graphed = self.graphed_fac = None
+        self.launches_per_step = None
+        if not no_graph:
+            # the whole step (fwd + loss + bwd [+ exchange] + clamp/Adam) captured once, replayed per step
+            ops.LAUNCHES[0] = 0
+            self.graphed = sn.GraphedTrainStep(self.trainer, self.cap_d, lens, self.feat_d, warmup=3,
+                                               force_segmented=segmented, **self.step_kw)
+            self.launches_per_step = ops.LAUNCHES[0] // 4          # 3 warm-up runs + 1 capture run
+        self.kw_fac = dict(self.step_kw, mode="factual")
+        if self.trainer_fac is not None and self.graphed is not None:
+            self.graphed_fac = sn.GraphedTrainStep(self.trainer_fac, self.cap_d, lens, self.feat_d, warmup=3,
+                                                   force_segmented=segmented, **self.kw_fac)
+        self.parity = 0                                       # stack3: factual / emotion passes on alternate steps
+
+    def _pick(self):
+        if self.trainer_fac is None:
+            return self.graphed, self.trainer, self.step_kw
+        self.parity ^= 1
+        return (self.graphed_fac, self.trainer_fac, self.kw_fac) if self.parity else (self.graphed, self.trainer, self.step_kw)
+
+    def step_resident(self):
+        g, tr, kw = self._pick()
+        if g is not None:
+            return g()
+        return tr.step(self.cap_d, self.lens, self.feat_d, **kw)
+
+    def step_e2e(self):
+        import torch
+        g, tr, kw = self._pick()
+        if g is not None:
+            loss, _ = g(self.cap_pin, self.feat_pin)          # pinned host -> static device buffers, then replay
+        else:
+            c = self.cap_pin.to(self.dev, non_blocking=True)
+            f = self.feat_pin.to(self.dev, non_blocking=True)
+            loss, _ = tr.step(c, self.lens, f, **kw)
+        self.loss_pin.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_pin[0])
+
+    def measure(self, steps, warmup, world, flush, barrier):
+        """(per-step device times [ms], e2e seconds): K steps timed with CUDA events on the launching stream, L2 flushed
+        between steps; then K end-to-end steps (pinned H2D + step + D2H loss + sync) on the wall clock."""
+        import torch
+        for _ in range(max(warmup, 3)):
+            self.step_resident()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.step_resident()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        for _ in range(2):
+            self.step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step_e2e()
+        barrier()
+        return per_step, time.perf_counter() - t0
+
+
+def dp_parity_check(dev, rank, world):
+    """Data-parallel EQUALITY carried by the bench line (the driver's scaling run is the only place with N GPUs):
+    3 steps on a fixed global batch of 12*N ragged samples through the N-GPU path (peer-fused exchange + Adam) against
+    the same 3 steps on ONE GPU (computed redundantly by every rank), fp32 mode so that the only difference is the
+    summation order of the gradient shards.  Reports the worst relative parameter difference and whether all ranks
+    hold bit-identical parameters afterwards."""
+    import torch
+    import torch.distributed as dist
+    import icei_b200 as sn
+    from oracle import port     # synthetic_batch only (inputs); nothing of the oracle is executed on the path
+    Vp, Ep, Hp, Fp = 1000, 44, 128, 72
+    cap, lens, feats = port.synthetic_batch(12 * world, 9, Vp, E=Ep, ragged=True, seed=5)
+    n_global = sum(lens)
+
+    def make():
+        torch.manual_seed(0)
+        d = sn.DecoderFactoredLSTM(Ep, Hp, Fp, Vp, 1, dropout=0.0).to(dev).train()
+        return d, sn.DataParallelTrainer(d, sn.FusedClampAdam(d, lr=5e-4), comm=None)
+    one, _ = make()
+    opt1 = sn.FusedClampAdam(one, lr=5e-4)
+    for _ in range(3):
+        one.zero_grad()
+        for p in one.parameters():
+            p.grad = None
+        one.forward_loss(cap.to(dev), lens, feats.to(dev), mode="happy")
+        opt1.step()
+    dec, tr = make()
+    idx, my_lens = sn.shard_lengths(lens, world, rank)
+    for _ in range(3):
+        tr.step(cap[idx].to(dev), my_lens, feats[idx].to(dev), n_global=n_global, mode="happy")
+    torch.cuda.synchronize()
+    worst = torch.zeros(1, device=dev)
+    same = torch.ones(1, device=dev)
+    for (n, p), (_, q) in zip(dec.named_parameters(), one.named_parameters()):
+        worst = torch.maximum(worst, ((p - q).norm() / q.norm().clamp_min(1e-30)).reshape(1))
+        r0 = p.detach().clone()
+        dist.broadcast(r0, 0)
+        if not torch.equal(r0, p.detach()):
+            same.zero_()
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    return {"max_rel_param_diff_vs_1gpu": float(worst.item()), "ranks_bit_identical": bool(same.item() == 1.0),
+            "steps": 3, "global_batch": 12 * world, "comm": tr.comm,
+            "what": "fp32 mode, ragged global batch sharded over the ranks, 3 steps vs the same steps on 1 GPU"}
+
+
+def decode_section(dev, cpu_seconds):
+    """Greedy / beam decode throughput (BASELINE.json metric, second half) outside the headline timed region:
+    greedy = forward(teacher_forcing_ratio=0) under no_grad (train_multitask.py:296-299), B=96, T=20; beam = sample()
+    semantics (stylenet/model.py:198-294 with the app/backend image feed) batched over images.  Weights: reference init
+    + the decode recipe of SURVEY.md section 8c.  Each figure next to the CPU port / reference on the host cores."""
+    import torch
+    import icei_b200 as sn
+    from oracle import port
+    torch.manual_seed(0)
+    dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5)
+    port.sharpen_for_decode(dec)
+    sd = {k: v.clone() for k, v in dec.state_dict().items()}
+    dec = dec.to(dev).eval()
+    g = torch.Generator().manual_seed(1)
+    out = {}
+
+    def timed(fn, reps):
+        for _ in range(3):          # the 2nd call of a decode session captures its CUDA graph
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    B = 96
+    cap = torch.randint(4, V, (B, T), generator=g)
+    cap[:, 0] = 1
+    feats = torch.randn(B, E, generator=g)
+    cap_d, feats_d = cap.to(dev), feats.to(dev)
+    for prec in ("bf16", "fp32"):
+        dec.set_precision(prec)
+        with torch.no_grad():
+            dt = timed(lambda: dec(cap_d, [T] * B, feats_d, teacher_forcing_ratio=0.0, mode=MODE), 10)
+        out["greedy_captions_per_s_" + prec] = B / dt
+        for n_img in (1, 1024):
+            f = torch.randn(n_img, E, generator=g).to(dev)
+            dt = timed(lambda: dec.sample_batch(f, 1, 2, k=5, mode=MODE, feed_image=True), 5 if n_img == 1 else 2)
+            out["beam_k5_b%d_captions_per_s_%s" % (n_img, prec)] = n_img / dt
+    # CPU arm: same weights, greedy on the full batch, beam on a few images (bounded)
+    mod, kind = _cpu_modules("factored")
+    ref = mod.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5)
+    ref.load_state_dict(sd)
+    ref.eval()
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref(cap, [T] * B, feats, teacher_forcing_ratio=0.0, mode=MODE)
+        t0 = time.perf_counter()
+        n = 0
+        while n < 3 and time.perf_counter() - t0 < cpu_seconds / 3:
+            ref(cap, [T] * B, feats, teacher_forcing_ratio=0.0, mode=MODE)
+            n += 1
+        out["cpu_greedy_captions_per_s"] = B * n / (time.perf_counter() - t0)
+        # beam: the image-fed variant (app/backend/model.py:386-487) exists only in the port's sample(feed_image=True)
+        pref = port.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5)
+        pref.load_state_dict(sd)
+        pref.eval()
+        t0 = time.perf_counter()
+        n = 0
+        while n < 16 and time.perf_counter() - t0 < cpu_seconds / 3:
+            pref.sample(feats[n:n + 1], 1, 2, k=5, mode=MODE, feed_image=True)
+            n += 1
+        out["cpu_beam_k5_captions_per_s"] = n / (time.perf_counter() - t0)
+    out["cpu_kind"], out["cpu_cores"] = kind, os.cpu_count()
+    out["note"] = "B200 figures: wall clock incl. python, features resident, ids copied back; beam_k5_b1 = one image per call"
+    return out
+
+
 def run_gpu(args):
     import random
     import torch
     import torch.distributed as dist
-    import icei_b200 as sn
     from icei_b200 import ops
 
     rank = int(os.environ.get("RANK", "0"))
@@ -225,127 +478,33 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    torch.manual_seed(0)                        # identical weights on every rank
-    if WORKLOAD == "att":
-        dec = sn.DecoderFactoredLSTMAtt(512, E, H, F, V, 1, dropout=0.5).to(dev)
-    elif WORKLOAD == "nic":
-        dec = sn.DecoderRNN(E, H, V, 1, dropout=0.5).to(dev)
-    elif WORKLOAD == "stack3":
-        dec = sn.DecoderFactoredLSTMStack(E, H, 1024, V, 3, dropout=0.5).to(dev)
-    else:
-        dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5).to(dev)
-    dec.train()
-    dec.set_precision(args.precision)
-    arith = "bf16 operands on tcgen05, fp32 accumulate (recurrence/softmax/Adam fp32)" if args.precision == "bf16" \
-        else "f32 FFMA"
-    opt = sn.FusedClampAdam(dec, lr=5e-4, grad_clip=0.5)
-    trainer = sn.DataParallelTrainer(dec, opt)
-    trainer_fac = None
-    if WORKLOAD == "stack3":      # multitask: a second optimizer object (own Adam moments) for the factual pass
-        trainer_fac = sn.DataParallelTrainer(dec, sn.FusedClampAdam(dec, lr=2e-4, grad_clip=0.5))
-    bsz = 64 if WORKLOAD == "nic" else B_PER_GPU
-    cap_h, lens, feat_h = synthetic_batch(bsz, T, V, E, seed=rank)
-    step_kw = {"teacher_forcing_ratio": 1.0}
-    if WORKLOAD != "nic":
-        step_kw["mode"] = MODE
-    if WORKLOAD == "att":
-        feat_h = torch.randn(bsz, 7, 7, 2048, generator=torch.Generator().manual_seed(100 + rank))
-        full_cap = cap_h
-        cap_h = full_cap[:, :-1].contiguous()                  # inputs; targets = packed full[:, 1:]
-        lens = [l - 1 for l in lens]
-        tgt_idx = torch.cat([torch.arange(b) * T + (t + 1) for t, b in enumerate([bsz] * (T - 1))])
-        step_kw["targets"] = full_cap.reshape(-1)[tgt_idx].to(dev)
-    cap_pin, feat_pin = cap_h.pin_memory(), feat_h.pin_memory()
-    cap_d, feat_d = cap_pin.to(dev), feat_pin.to(dev)
-    loss_pin = torch.zeros(1).pin_memory()
-    n_tok_local = sum(lens)
-    random.seed(0)
-    flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device=dev)   # 512 MiB > L2
-
-    graphed = None
-    launches_per_step = None
-    if not args.no_graph:
-        # the whole step (fwd + loss + bwd [+ all-reduce] + clamp/Adam) captured once, replayed per step
-        ops.LAUNCHES[0] = 0
-        graphed = sn.GraphedTrainStep(trainer, cap_d, lens, feat_d, warmup=3, force_segmented=args.segmented, **step_kw)
-        launches_per_step = ops.LAUNCHES[0] // 4          # 3 warm-up runs + 1 capture run
-    graphed_fac = None
-    kw_fac = dict(step_kw, mode="factual")
-    if trainer_fac is not None and graphed is not None:
-        graphed_fac = sn.GraphedTrainStep(trainer_fac, cap_d, lens, feat_d, warmup=3, force_segmented=args.segmented, **kw_fac)
-    parity = [0]                                          # stack3: factual / emotion passes on alternate steps
-
-    def pick():
-        if trainer_fac is None:
-            return graphed, trainer, step_kw
-        parity[0] ^= 1
-        return (graphed_fac, trainer_fac, kw_fac) if parity[0] else (graphed, trainer, step_kw)
-
-    def step_resident():
-        g, tr, kw = pick()
-        if g is not None:
-            return g()
-        return tr.step(cap_d, lens, feat_d, **kw)
-
-    def step_e2e():
-        g, tr, kw = pick()
-        if g is not None:
-            loss, _ = g(cap_pin, feat_pin)                # pinned host -> static device buffers, then replay
-        else:
-            c = cap_pin.to(dev, non_blocking=True)
-            f = feat_pin.to(dev, non_blocking=True)
-            loss, _ = tr.step(c, lens, f, **kw)
-        loss_pin.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(loss_pin[0])
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    barrier()
+    dp_parity = None
+    if world > 1 and not args.no_dp_parity:
+        dp_parity = dp_parity_check(dev, rank, world)
+    random.seed(0)
+    w = Workload(WORKLOAD, args.precision, dev, rank, no_graph=args.no_graph, segmented=args.segmented,
+                 batch=args.batch)
+    flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device=dev)   # 512 MiB > L2
 
     # ---- timed region: K steps, device time per step (CUDA events on the launching stream) -----------
     sampler = ClockSampler(local)
     sampler.start()
     ops.LAUNCHES[0] = 0
-    evs = []
-    barrier()
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step_resident()
-        e1.record()
-        evs.append((e0, e1))
-    barrier()
-    launches = ops.LAUNCHES[0] if graphed is None else launches_per_step * args.steps
-    ms = sum(a.elapsed_time(b) for a, b in evs)
+    per_step, dt_e2e = w.measure(args.steps, args.warmup, world, flush, barrier)
     clocks = sampler.stop()
-    t_local = torch.tensor([ms], dtype=torch.float64, device=dev)
+    launches = ops.LAUNCHES[0] if w.graphed is None else w.launches_per_step * args.steps
+    t_local = torch.tensor([sum(per_step), dt_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
-    ms_total = float(t_local.item())
+    ms_total = float(t_local[0].item())
     ms_per_step = ms_total / args.steps
-    value = n_tok_local * world * args.steps / (ms_total / 1e3)
-
-    # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, wall clock ------------------------
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    dt = time.perf_counter() - t0
-    t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = n_tok_local * world * args.steps / float(t_e.item())
-    h2d = cap_pin.numel() * 8 + feat_pin.numel() * 4
+    value = w.n_tok * world * args.steps / (ms_total / 1e3)
+    e2e_value = w.n_tok * world * args.steps / float(t_local[1].item())
 
     line = None
     if rank == 0:
@@ -353,19 +512,51 @@ def run_gpu(args):
         if WORKLOAD == "att" or args.no_roofline:
             roof, kernels = None, None
         else:
-            roof, kernels = kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src, tf_peak)
+            roof, kernels = kernel_roofline(w.dec, w.cap_d, w.lens, w.feat_d, hbm_peak, peak_src, tf_peak)
+        srt = sorted(per_step)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": workload_config(world, arith, n_tok_local, bsz),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+            "config": workload_config(world, w.arith, w.n_tok, w.bsz),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": 4,
                     "timing": "wall clock incl. python, pinned H2D of captions+features, D2H loss, sync per step"},
-            "gpu_launches": launches, "launch_mode": "cuda-graph replay of the captured step" if graphed is not None
-            else "eager (python-issued launches)", "clocks": clocks, "roofline": roof, "kernels": kernels,
+            "gpu_launches": launches, "launch_mode": "cuda-graph replay of the captured step" if w.graphed is not None
+            else "eager (python-issued launches)", "clocks": clocks,
+            "ms_per_step_spread": {"min": srt[0], "median": srt[len(srt) // 2], "max": srt[-1], "rank": 0},
+            "roofline": roof, "kernels": kernels,
         }
+        if dp_parity is not None:
+            line["dp_parity"] = dp_parity
     if world > 1:
         dist.barrier()
+    if rank == 0 and world == 1 and not args.no_extras:
+        # ---- the rest of BASELINE.json's configs and the second half of its metric, OUTSIDE the headline region ----
+        del w
+        torch.cuda.empty_cache()
+        cpu_s = args.cpu_seconds / 2
+        extras = {}
+        for name, prec in (("factored", "fp32"), ("att", "bf16"), ("stack3", "bf16"), ("nic", "bf16")):
+            try:
+                wx = Workload(name, prec, dev, rank)
+                ps, dte = wx.measure(20, 3, 1, flush, barrier)
+                r = cpu_reference_run(8, 1, max_seconds=cpu_s, workload=name)
+                srt = sorted(ps)
+                extras[name if prec == "bf16" else "fp32_mode"] = {
+                    "workload": WORKLOAD_TEXT[name], "precision": prec, "ms_per_step": sum(ps) / len(ps),
+                    "ms_per_step_spread": {"min": srt[0], "median": srt[len(srt) // 2], "max": srt[-1]},
+                    "value": wx.n_tok * len(ps) / (sum(ps) / 1e3), "e2e": wx.n_tok * 20 / dte, "unit": UNIT,
+                    "batch": wx.bsz, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}}
+                del wx
+                torch.cuda.empty_cache()
+            except Exception as exc:          # an extra must never take the headline line down
+                extras[name if prec == "bf16" else "fp32_mode"] = {"error": repr(exc)[:300]}
+        line["fp32_mode"] = extras.pop("fp32_mode")
+        line["workloads"] = extras
+        try:
+            line["decode"] = decode_section(dev, args.cpu_seconds)
+        except Exception as exc:
+            line["decode"] = {"error": repr(exc)[:300]}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(40, 1, max_seconds=args.cpu_seconds)
@@ -577,6 +768,8 @@ def main():
                     help="samples per GPU (default: the BASELINE config, 96; e.g. 4096 = throughput regime, a supplementary point)")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel roofline section (launch lists of the step only)")
     ap.add_argument("--segmented", action="store_true", help="force the 3-graph (data-parallel) replay form on one GPU")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp32-mode / other-config / decode sections of the line")
+    ap.add_argument("--no-dp-parity", action="store_true", help="skip the N-GPU == 1-GPU equality check (N > 1)")
     args = ap.parse_args()
     global WORKLOAD, B_PER_GPU
     WORKLOAD = args.workload

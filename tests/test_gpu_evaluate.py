@@ -41,7 +41,7 @@ def test_validate_matches_reference_definitions(kind):
             random.seed(0)
             if att:
                 l1 = [l - 1 for l in lens]
-                out, _ = dec(cap[:, :-1].cuda(), l1, feats.cuda(), teacher_forcing_ratio=0.0, **kw)
+                out, alphas = dec(cap[:, :-1].cuda(), l1, feats.cuda(), teacher_forcing_ratio=0.0, **kw)
                 tgt = port.pack_targets(cap[:, 1:], l1).cuda()
                 plens = l1
             else:
