@@ -31,9 +31,17 @@ def single_step(dec, embedded, states, mode):
     R, H = h.shape
     dev = h.device
     ctx = _StepCtx()
-    ctx.XP = torch.empty(R, 4 * H, dtype=torch.float32, device=dev)
     X = embedded.detach().float().contiguous()
     with torch.no_grad():
+        ops.lib()
+        dec.arena()
+        if R <= ops.SKINNY_MAX_ROWS:
+            h_new = torch.empty(R, H, dtype=torch.float32, device=dev)
+            c_new = torch.empty(R, H, dtype=torch.float32, device=dev)
+            dec._small_step(ctx, X, mode, R, h.detach().float().contiguous(), c.detach().float().contiguous(), None,
+                            h_new, c_new)
+            return h_new, (h_new, c_new)
+        ctx.XP = torch.empty(R, 4 * H, dtype=torch.float32, device=dev)
         dec._input_projection(ctx, X, mode, 0, R)
         Whh, bhh = dec._recurrent_weights()
         h_new = torch.empty(R, H, dtype=torch.float32, device=dev)
@@ -144,6 +152,12 @@ class _DecodeSession:
         self.graph = None          # generic step (steps >= 2)
         self.calls = 0
         self.arena_version = dec.arena().version
+        # few rows (single-image beam search): matrix-vector kernels, state double-buffered (A -> B -> A ...), the beam
+        # re-ordering of the state folded into the next step's read (no index_select kernels)
+        self.skinny = R <= ops.SKINNY_MAX_ROWS
+        if self.skinny:
+            self.hB, self.cB = torch.zeros(R, H, **f32), torch.zeros(R, H, **f32)
+            self.flip = 0              # 0: the state is in (h, c); 1: in (hB, cB)
 
     def step(self, step, feed_image, device_step):
         dec, st = self._dec(), self.st
@@ -166,6 +180,42 @@ class _DecodeSession:
         c_new = self.c.index_select(0, idx)
         self.c.copy_(c_new)
         st.step_dev.add_(1)
+
+    def step_skinny(self, step, feed_image, device_step):
+        dec, st = self._dec(), self.st
+        emb, out = dec._emb(), dec._out()
+        R = st.R
+        if feed_image and step == 1:
+            ops.gather_pack_fwd(self.dummy_cap, emb.weight, self.feats, True, self.row_img, self.row_zero, None, R,
+                                self.X, 0.0, 0)
+        else:
+            ops.gather_pack_fwd(self.dummy_cap, emb.weight, None, False, self.row_img, self.row_zero, st.prev_word, R,
+                                self.X, 0.0, 0)
+        src = (self.h, self.c) if self.flip == 0 else (self.hB, self.cB)
+        dst = (self.hB, self.cB) if self.flip == 0 else (self.h, self.c)
+        dec._small_step(self.ctx, self.X, self.mode, R, src[0], src[1], st.src_row, dst[0], dst[1])
+        ops.skinny_linear(out.weight, dst[0], self.logits, R, bias=out.bias)
+        st.step(self.logits, step, self.end_token, device_step=device_step)
+        st.step_dev.add_(1)
+        self.flip ^= 1
+
+    STEPS_PER_GRAPH = 4
+
+    def capture_skinny(self):
+        """One graph = STEPS_PER_GRAPH consecutive steps (an even number: the state ends in the buffer it started in)."""
+        assert self.flip == 1 and self.STEPS_PER_GRAPH % 2 == 0
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.step_skinny(2, False, True)      # warm-up on the capture side stream
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with ops.no_gc_during_capture(), torch.cuda.graph(g):
+            for _ in range(self.STEPS_PER_GRAPH):
+                self.step_skinny(2, False, True)
+        self.graph = g
 
     def capture(self):
         g = torch.cuda.CUDAGraph()
@@ -204,11 +254,39 @@ def beam_sample(dec, features, start_token, end_token, k, mode, feed_image, sync
     dec.arena()
     feats = features.detach().to(dev).float().reshape(-1, E)
     n_img = feats.shape[0]
-    if use_graph is None:
-        use_graph = not dec.bf16           # bf16 mode refreshes weight shadows per call: stays eager
     sess = _session(dec, n_img, k, mode, start_token, end_token)
     st = sess.st
     sess.calls += 1
+    if sess.skinny:
+        # few rows: matrix-vector kernels on the fp32 weights (both precision modes), steps 2.. replayed 4 at a time
+        if use_graph is None:
+            use_graph = True
+
+        def restart():
+            st.reset()
+            sess.h.zero_()
+            sess.c.zero_()
+            sess.flip = 0
+            sess.step_skinny(1, feed_image, device_step=True)       # step 1 is special (image feed, one live row)
+        sess.feats.copy_(feats)
+        restart()
+        if use_graph and sess.graph is None and sess.calls >= 2:
+            sess.capture_skinny()                                    # (runs throw-away steps: start over)
+            restart()
+        step = 2
+        while step <= dec.max_seq_length + 1:
+            if use_graph and sess.graph is not None:
+                sess.graph.replay()
+                step += sess.STEPS_PER_GRAPH
+            else:
+                for _ in range(sess.STEPS_PER_GRAPH):
+                    sess.step_skinny(step, False, device_step=True)
+                    step += 1
+            if int(st.n_unfinished.item()) == 0:
+                break
+        return st.results()
+    if use_graph is None:
+        use_graph = not dec.bf16           # bf16 mode refreshes weight shadows per call: stays eager
     if use_graph and sess.graph is None and sess.calls >= 2:
         sess.capture()                      # first call runs eagerly (and warms everything up)
     st.reset()

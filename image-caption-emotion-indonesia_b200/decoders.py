@@ -453,6 +453,17 @@ class _DecoderBase(nn.Module):
             dfeat = dfeat.view(c.feat_shape)
         return dfeat
 
+    def _bucket_final(self, names):
+        """The gradients of ``names`` are final (all their kernels are queued on the CURRENT stream): publish them and
+        let the trainer exchange / update this bucket now, under the rest of the backward."""
+        hook = self.__dict__.get("_bucket_hook")
+        if hook is None:
+            return
+        gbuf, fn = hook
+        names = [n for n in names if n in self.arena().named]
+        self._publish(names, gbuf)
+        fn(names)
+
     def _gview(self, gbuf, names, shape):
         a = self.arena()
         o, n = a._span(names)
@@ -668,7 +679,12 @@ class _DecoderBase(nn.Module):
                     self._join()
                     grad_hook(list(self._out_names()))       # bucket 0 is final: overlap its all-reduce
                 need_dfeat = features is not None and features.requires_grad
-                dfeat = self._run_backward(c, dHall, gbuf, need_dfeat)
+                # further buckets (W_hh / U, S / V of every layer) are handed to `early_step` by the backward itself
+                self.__dict__["_bucket_hook"] = (gbuf, early_step) if (early_step is not None and gbuf is self.arena().gflat) else None
+                try:
+                    dfeat = self._run_backward(c, dHall, gbuf, need_dfeat)
+                finally:
+                    self.__dict__["_bucket_hook"] = None
                 self._join()
                 self._publish(c.grad_names + list(self._out_names()), gbuf)
                 if grad_hook is not None:
@@ -885,10 +901,14 @@ class DecoderFactoredLSTM(_DecoderBase):
         dA2, dA2b = torch.empty(N, 4 * F, **f32), torch.empty(N, 4 * F, **b16)
         dA1, dA1b = torch.empty(N, 4 * F, **f32), torch.empty(N, 4 * F, **b16)
         dX = torch.empty(N, Ein, **f32)
+        L = getattr(c, "layer", 0)
+        lp = self._lp(L)
         sa.wait_stream(main)
         with torch.cuda.stream(sa):
             ops.gemm_bf16(ops.OP_TN, dZb, c.A2, H, F, N, 4 * H, 4 * F, C=gU, ldc=F, batch=4, sA=H, sB=F, sC=H * F)
             ops.colsum(dZ, N, 4 * H, 4 * H, gbU)
+            # stream 0 also carried dW_hh / db_hh of this layer (_layer_bwd): bucket {W_hh, U} is final here
+            self._bucket_final([lp + pre + g + sfx for pre in ("W_", "U_") for g in GATES for sfx in (".weight", ".bias")])
         ops.gemm_bf16(ops.OP_NN, dZb, Ub, N, F, H, 4 * H, Fp, C=dA2, ldc=4 * F, Cb=dA2b, ldcb=4 * F, batch=4, sA=H,
                       sB=H * Fp, sC=F, sCb=F)
         sb.wait_stream(main)
@@ -901,8 +921,33 @@ class DecoderFactoredLSTM(_DecoderBase):
         with torch.cuda.stream(sb):
             ops.gemm_bf16(ops.OP_TN, dA1b, c.Xb, 4 * F, Ein, N, 4 * F, Ep, C=gV, ldc=Ein)
             ops.colsum(dA1, N, 4 * F, 4 * F, gbV)
+            self._bucket_final([lp + style_attr(c.mode, g) + sfx for g in GATES for sfx in (".weight", ".bias")] +
+                               [lp + "V_" + g + sfx for g in GATES for sfx in (".weight", ".bias")])
         ops.gemm_bf16(ops.OP_NN, dA1b, Vb, N, Ein, 4 * F, 4 * F, Ep, C=dX, ldc=Ein)
         return dX
+
+    def _small_step(self, ctx, X, mode, R, h_prev, c_prev, src_row, h_out, c_out):
+        """forward_step for R <= ops.SKINNY_MAX_ROWS rows on the matrix-vector kernels (sn_decode.cu): V and S stages as
+        skinny linears, the U stage + W_hh + gates + cell update fused (stylenet/model.py:119-153)."""
+        if mode not in STYLES:
+            raise ValueError("mode name wrong: %r (expected one of %s)" % (mode, STYLES))
+        H, F = self.hidden_size, self.factored_size
+        Ein = X.shape[1]
+        a1, a2 = ctx.__dict__.get("sk_a1"), ctx.__dict__.get("sk_a2")
+        if a1 is None or a1.shape[0] < R:
+            a1 = ctx.sk_a1 = torch.empty(max(R, ops.SKINNY_MAX_ROWS), 4 * F, dtype=torch.float32, device=X.device)
+            a2 = ctx.sk_a2 = torch.empty_like(a1)
+        ops.skinny_linear(self._stack("V_", (4 * F, Ein)), X, a1, R, bias=self._stack("V_", (4 * F,), bias=True))
+        Sc, bS = self._style_stack(mode, (4 * F, F)), self._style_stack(mode, (4 * F,), bias=True)
+        if F % 32 == 0:
+            ops.skinny_linear(Sc, a1, a2, R, bias=bS, group_n=F, group_x=F)
+        else:                      # odd factored sizes: one call per gate block
+            for g in range(4):
+                ops.skinny_linear(Sc[g * F:(g + 1) * F], a1[:, g * F:(g + 1) * F], a2[:, g * F:(g + 1) * F], R,
+                                  bias=bS[g * F:(g + 1) * F])
+        Whh, bhh = self._recurrent_weights()
+        ops.decode_cell(self.cell, H, R, self._stack("U_", (4 * H, F)), F, a2, F, self._stack("U_", (4 * H,), bias=True),
+                        Whh, bhh, h_prev, c_prev, src_row, h_out, c_out)
 
     # -- reference surface ---------------------------------------------------------------------------
     def forward(self, captions, lengths, features=None, teacher_forcing_ratio=0.8, mode="factual"):
@@ -1015,6 +1060,13 @@ class DecoderRNN(_DecoderBase):
         ops.colsum(dZ, N, 4 * H, 4 * H, gb)
         ops.gemm(ops.OP_NN, dZ, self.lstm.weight_ih, dX, N, Ein, 4 * H, 4 * H, Ein, Ein)
         return dX
+
+    def _small_step(self, ctx, X, mode, R, h_prev, c_prev, src_row, h_out, c_out):
+        """nn.LSTMCell step (nic/model.py:74-79) for R <= ops.SKINNY_MAX_ROWS rows: one fused matrix-vector kernel."""
+        H = self.hidden_size
+        self.arena()
+        ops.decode_cell(self.cell, H, R, self.lstm.weight_ih, X.shape[1], X, 0, self.lstm.bias_ih, self.lstm.weight_hh,
+                        self.lstm.bias_hh, h_prev, c_prev, src_row, h_out, c_out)
 
     def forward(self, captions, lengths, features, teacher_forcing_ratio=0.8):
         """Same call and return as nic/model.py:81-115."""

@@ -434,6 +434,7 @@ class DecoderFactoredLSTMAtt(_AttBase):
     _recurrent_weights = _F._recurrent_weights
     _recurrent_grads = _F._recurrent_grads
     _input_projection = _F._input_projection
+    _small_step = _F._small_step
     del _F
 
     def _arena_groups(self):
@@ -680,6 +681,12 @@ class DecoderRNNAtt(_AttBase):
             [p + n for n in ("encoder_att.weight", "encoder_att.bias", "decoder_att.weight", "decoder_att.bias",
                              "full_att.weight", "full_att.bias")] + \
             ["init_h.weight", "init_h.bias", "init_c.weight", "init_c.bias", "f_beta.weight", "f_beta.bias"]
+
+    def _small_step(self, ctx, X, mode, R, h_prev, c_prev, src_row, h_out, c_out):
+        H = self.hidden_size
+        self.arena()
+        ops.decode_cell(self.cell, H, R, self.lstm.weight_ih, X.shape[1], X, 0, self.lstm.bias_ih, self.lstm.weight_hh,
+                        self.lstm.bias_hh, h_prev, c_prev, src_row, h_out, c_out)
 
     def _input_projection(self, c, X, mode, r0, n):
         """Full-width projection (used by forward_step / decode where the input is already [emb, ctx])."""

@@ -53,6 +53,14 @@ class PeerExchange:
     Feeds sn_dp_adam_fused: ONE kernel per step does reduce-scatter + clamp/Adam + all-gather, no NCCL."""
 
     _opened = {}        # handle bytes -> mapped base address (an allocation can be opened once per process)
+    N_PADS = 16         # exchange calls of one step that may be in flight at the same time (one pad each)
+
+    def pads(self, bucket):
+        """Signal-pad pointers (one per rank) of bucket ``bucket``: concurrent exchange kernels on different streams
+        must not share flags."""
+        if not 0 <= bucket < self.N_PADS:
+            raise RuntimeError("too many exchange buckets in one step")
+        return [p + 128 * bucket for p in self.pad_ptrs]
 
     def __init__(self, arena, group=None):
         from . import ops
@@ -61,7 +69,7 @@ class PeerExchange:
         if self.world > 8:
             raise RuntimeError("peer exchange supports one NVSwitch box (<= 8 ranks)")
         dev = arena.flat.device
-        self.pad = torch.zeros(32, dtype=torch.int32, device=dev)
+        self.pad = torch.zeros(32 * self.N_PADS, dtype=torch.int32, device=dev)   # one signal pad per concurrent bucket
         torch.cuda.synchronize()
         mine = [ops.ipc_export(t) for t in (arena.flat, arena.gflat, self.pad)]
         gathered = [None] * self.world
@@ -129,27 +137,33 @@ class DataParallelTrainer:
 
     def step(self, captions, lengths, features, n_global=None, b_global=None, **kw):
         a = self.decoder.arena()
+        bucketed = getattr(self.decoder, "bf16", False) and not hasattr(self.decoder, "attention") and EARLY_PEER_EXCHANGE[0]
         if self.world > 1 and self.comm == "peer":
             peers = self._peers()
             early = []
-            if getattr(self.decoder, "bf16", False) and not hasattr(self.decoder, "attention") and EARLY_PEER_EXCHANGE[0]:
-                # the vocabulary projection (43 % of the exchanged bytes at configs[1]) is reduced / updated / gathered
-                # on the side stream as soon as dC is final, under the reverse recurrence; the rest at the end
+            if bucketed:
+                # gradient buckets are exchanged (reduce-scatter + Adam + all-gather, one kernel) on the side stream that
+                # produced them AS SOON AS THEY ARE FINAL: the vocabulary projection under the reverse recurrence, W_hh / U
+                # and S / V under the rest of the projection backward; only the embedding is left for the end of the step.
+                # Every bucket has its own signal pad (the kernels overlap each other).
+                calls = [0]
+
                 def early_step(names):
-                    self.optimizer.step_peer(peers, only=names)
+                    self.optimizer.step_peer(peers, only=names, bucket=calls[0])
+                    calls[0] += 1
                     early.extend(names)
                 kw = dict(kw, early_step=early_step)
             loss, stats = self.forward_backward(captions, lengths, features, n_global=n_global, b_global=b_global, **kw)
-            self.optimizer.step_peer(peers, skip=early or None)
+            self.optimizer.step_peer(peers, skip=early or None, bucket=PeerExchange.N_PADS - 1)
             return loss, stats
         hook = None
         if self.world > 1:
             def hook(names):
                 self.sync.launch(a.gflat, merged_ranges(a, names))
         early = []
-        if self.world == 1 and getattr(self.decoder, "bf16", False) and not hasattr(self.decoder, "attention"):
-            # single GPU: Adam of the vocabulary projection runs on the side stream as soon as dC is final (under the
-            # reverse recurrence); the rest follows at the end
+        if self.world == 1 and bucketed:
+            # single GPU: Adam of each bucket runs on the side stream that produced it (under the reverse recurrence /
+            # the projection backward); the rest follows at the end
             def early_step(names):
                 self.optimizer.step(only=names)
                 early.extend(names)

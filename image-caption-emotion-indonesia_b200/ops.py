@@ -496,3 +496,22 @@ def bn1d_bwd(x, dy, gamma, save_mean, save_invstd, training, dx, dgamma, dbeta):
     B, E = x.shape
     check(lib().sn_bn1d_bwd(_ptr(_req(x)), _ptr(_req(dy)), B, E, _ptr(gamma), _ptr(save_mean), _ptr(save_invstd),
                             1 if training else 0, _ptr(dx), _ptr(dgamma), _ptr(dbeta), _stream()), "sn_bn1d_bwd")
+
+
+# ---- decode steps on few rows (matrix-vector kernels, sn_decode.cu) -------------------------------------------------
+SKINNY_MAX_ROWS = 16
+
+
+def skinny_linear(W, X, out, R, bias=None, group_n=0, group_x=0, K=None):
+    """out[:R] = X[:R] W^T + bias for R <= 16 rows; W [N, K] fp32 (row pitch W.stride(0)); grouped form see sn100.h."""
+    N = W.shape[0]
+    K = K if K is not None else W.shape[1]
+    check(lib().sn_skinny_linear(_ptr(_req(W)), W.stride(0), N, K, _ptr(_req(X)), X.stride(0), R, group_n, group_x,
+                                 _ptr(bias), _ptr(_req(out)), out.stride(0), _stream()), "sn_skinny_linear")
+    return out
+
+
+def decode_cell(cell, H, R, Wx, Kx, X, group_x, bx, Wh, bh, h_prev, c_prev, src_row, h_out, c_out):
+    check(lib().sn_decode_cell(cell, H, R, _ptr(_req(Wx)), Wx.stride(0), Kx, _ptr(_req(X)), X.stride(0), group_x,
+                               _ptr(bx), _ptr(_req(Wh)), _ptr(bh), _ptr(_req(h_prev)), _ptr(_req(c_prev)),
+                               _ptr(src_row), _ptr(_req(h_out)), _ptr(_req(c_out)), _stream()), "sn_decode_cell")

@@ -160,7 +160,7 @@ class FusedClampAdam:
                     self._step_tensor(p, ("extra", i))
 
     @torch.no_grad()
-    def step_peer(self, peers, only=None, skip=None):
+    def step_peer(self, peers, only=None, skip=None, bucket=0):
         """Data-parallel step: gradient reduce-scatter + clamp/Adam on the owned shard + parameter all-gather in
         one kernel over NVLink peer memory.  Every rank must call it with the same set of gradients (``only`` /
         ``skip`` as in ``step``: the vocabulary projection's exchange can run early, under the reverse recurrence)."""
@@ -177,7 +177,7 @@ class FusedClampAdam:
             raise RuntimeError("peer-fused step needs every gradient in the arena")
         ranges = [(off, n) for off, n, _ in items]
         idx = [self.index[name] for _, _, name in items]
-        ops.dp_adam_fused(peers.world, peers.rank, peers.grad_ptrs, peers.param_ptrs, peers.pad_ptrs, self.m, self.v,
+        ops.dp_adam_fused(peers.world, peers.rank, peers.grad_ptrs, peers.param_ptrs, peers.pads(bucket), self.m, self.v,
                           ranges, idx, self.steps_dev, self.lr_dev, self.coef_ws, self.betas[0], self.betas[1],
                           self.eps, self.grad_clip)
 

@@ -335,6 +335,24 @@ int32_t sn_beam_step(const float* logits, int64_t ld, int64_t V, int32_t n_img, 
                      int32_t* n_done, int32_t* out_seq, int32_t* out_len, int32_t* n_unfinished,
                      const int32_t* step_dev, void* stream);
 
+/* ---- decode steps on FEW rows (single-image beam search, forward_step): matrix-vector kernels -----------------
+ * replaces forward_step (stylenet/model.py:115-155, nn.LSTMCell nic/model.py:77) and the per-step C(h)
+ * (model.py:234) when rows <= sn_skinny_max_rows(): one pass over the fp32 weights, rows held in shared memory.
+ * sn_skinny_linear: out[r,n] = bias[n] + W[n,:K] . X[r, xoff(n) : xoff(n)+K], xoff(n) = (n / group_n) * group_x
+ *   (group_n = 0: no groups; the four S_g / U_g blocks are groups of F resp. H features reading column block g).
+ * sn_decode_cell: z_g = Wx[g*H+u,:Kx] . x_g[r] + bx + Wh[g*H+u,:] . h_prev[src_row[r]] + bh, gates, c', h' for
+ *   every unit u and row r; x_g = X[r, g*group_x : +Kx] (group_x = 0: the same x for all gates, LSTMCell).
+ *   src_row (may be NULL) re-orders the incoming state per row (beam bookkeeping, model.py:275-279): h_out / c_out
+ *   must not alias h_prev / c_prev. */
+int32_t sn_skinny_max_rows(void);
+int32_t sn_skinny_linear(const float* W, int64_t ldw, int64_t N, int64_t K, const float* X, int64_t ldx,
+                         int64_t R, int64_t group_n, int64_t group_x, const float* bias, float* out,
+                         int64_t ldo, void* stream);
+int32_t sn_decode_cell(int32_t cell, int64_t H, int64_t R, const float* Wx, int64_t ldwx, int64_t Kx,
+                       const float* X, int64_t ldx, int64_t group_x, const float* bx, const float* Wh,
+                       const float* bh, const float* h_prev, const float* c_prev, const int32_t* src_row,
+                       float* h_out, float* c_out, void* stream);
+
 /* ---- encoder tail -> decoder hand-off ---------------------------------------------------
  * sn_pool_nhwc_fwd: AdaptiveAvgPool2d((S,S)) + permute(0,2,3,1) of the trunk output (stylenet/model_att.py:24-28),
  *   one pass: x [B,D,h,w] (NCHW) -> out [B,S,S,D] contiguous fp32, optional bf16 copy (GEMM operand) and optional
