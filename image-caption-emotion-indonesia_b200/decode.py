@@ -104,8 +104,25 @@ class BeamState:
         self.n_unfinished.fill_(self.n_img)
         self.step_dev.fill_(1)
 
+    SPLIT_MAX_IMAGES = 8          # up to here one CTA per image leaves the GPU idle: spread each image over chunks
+
     def step(self, logits, step, end_token, device_step=False):
         p = ops._ptr
+        V = logits.shape[1]
+        if self.n_img <= self.SPLIT_MAX_IMAGES and V >= 256:
+            nch = max(1, min(16, V // 128))
+            ws = self.__dict__.get("_split_ws")
+            if ws is None:
+                n = ops.lib().sn_beam_split_ws_floats(self.n_img, self.kmax, nch)
+                ws = self._split_ws = torch.empty(n, dtype=torch.float32, device=logits.device)
+            check(ops.lib().sn_beam_step_split(
+                p(logits), logits.stride(0), V, self.n_img, self.kmax, step, self.max_len, end_token,
+                p(self.k_live), p(self.run_score), p(self.prev_word), p(self.src_row), p(self.cur_buf), p(self.seqs),
+                p(self.done_seq), p(self.done_len), p(self.done_score), p(self.n_done), p(self.out_seq),
+                p(self.out_len), p(self.n_unfinished), p(self.step_dev) if device_step else None, nch, p(ws),
+                ops._stream()), "sn_beam_step_split")
+            ops.LAUNCHES[0] += 2
+            return
         check(ops.lib().sn_beam_step(
             p(logits), logits.stride(0), logits.shape[1], self.n_img, self.kmax, step, self.max_len, end_token,
             p(self.k_live), p(self.run_score), p(self.prev_word), p(self.src_row), p(self.cur_buf), p(self.seqs),

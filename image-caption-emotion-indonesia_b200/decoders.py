@@ -414,6 +414,7 @@ class _DecoderBase(nn.Module):
             else:
                 ops.recur_bwd_bf16(self.cell, H, B, d["bs"], d["off"], 0, T, cl.w16["Whh"], None, cl.Call, cl.gates,
                                    dHall, dZ, cl.dZb, dh, dc)
+            self._run_deferred()
             with torch.cuda.stream(self._fork()):
                 ops.gemm_bf16(ops.OP_TN, cl.dZb, cl.Hpb, 4 * H, H, N, 4 * H, H, C=gW, ldc=H)
                 ops.colsum(dZ, N, 4 * H, 4 * H, gbW)
@@ -451,7 +452,16 @@ class _DecoderBase(nn.Module):
                             c.p_drop, c.seed, seed_dev=c.seed_dev)
         if dfeat is not None and c.feat_shape is not None:
             dfeat = dfeat.view(c.feat_shape)
+        # the embedding is the last gradient of the step: its bucket starts right here, next to the W_hh / U and S / V
+        # buckets still running on the side streams, instead of behind the join of all of them
+        self._bucket_final([self._emb_name()])
         return dfeat
+
+    def _run_deferred(self):
+        """Side-stream work of the vocabulary backward that was held back until the reverse recurrence was launched."""
+        todo = self.__dict__.pop("_after_recur", None)
+        for fn in todo or ():
+            fn()
 
     def _bucket_final(self, names):
         """The gradients of ``names`` are final (all their kernels are queued on the CURRENT stream): publish them and
@@ -486,7 +496,7 @@ class _DecoderBase(nn.Module):
             return logits
         return ops.linear_nt(Hall.contiguous(), out.weight, out.bias)
 
-    def _vocab_backward(self, Hall, dlogits, gbuf, Hb=None, dLb=None):
+    def _vocab_backward(self, Hall, dlogits, gbuf, Hb=None, dLb=None, defer=None):
         out = self._out()
         V, H = out.weight.shape
         N = Hall.shape[0]
@@ -507,13 +517,28 @@ class _DecoderBase(nn.Module):
             if have_b16:
                 # dH feeds the reverse recurrence: issued FIRST so its tiles get the SMs; dC / db_C do not feed anything
                 # before Adam: side stream, joined by the caller (_join)
-                side = self._fork()
+                mode_dc = ops.DC_SCHEDULE[0] if defer is not None else 0
+                side = self._side(0)
+                if mode_dc != 2:
+                    side.wait_stream(torch.cuda.current_stream())           # dLb / Hb exist
                 ops.gemm_bf16(ops.OP_NN, dLb, Wb, N, H, V, dLb.stride(0), Wb.stride(0), C=dHall, ldc=H)
-                with torch.cuda.stream(side):
-                    # capped at 10 SM pairs: dC then fits on the 20 SMs the 128-CTA reverse recurrence leaves free and
-                    # runs under it instead of holding every SM in front of the dH reduction (timeline, profiles/r1_l)
-                    ops.gemm_bf16(ops.OP_TN, dLb, Hb, V, H, N, dLb.stride(0), Hb.stride(0), C=gC, ldc=H, max_pairs=10)
-                    ops.colsum_bf16(dLb, N, V, dLb.stride(0), gb)
+                if mode_dc == 1:
+                    # the cluster-form recurrence needs 16 completely free SMs per cluster: dC must not grab SMs before its
+                    # clusters are placed.  dC becomes runnable together with the recurrence (both wait for dH) but is
+                    # LAUNCHED after it, and is capped to the SMs the 6 clusters leave free.
+                    side.wait_stream(torch.cuda.current_stream())
+
+                def side_work():
+                    if mode_dc == 2:
+                        side.wait_stream(torch.cuda.current_stream())       # after the reverse recurrence, full width
+                    with torch.cuda.stream(side):
+                        ops.gemm_bf16(ops.OP_TN, dLb, Hb, V, H, N, dLb.stride(0), Hb.stride(0), C=gC, ldc=H,
+                                      max_pairs=0 if mode_dc == 2 else ops.DC_MAX_PAIRS[0])
+                        ops.colsum_bf16(dLb, N, V, dLb.stride(0), gb)
+                if mode_dc == 0:
+                    side_work()
+                else:
+                    defer.append(side_work)
                 return dHall
             ops.gemm_bf16(ops.OP_NN, dLb, Wb, N, H, V, dLb.stride(0), Wb.stride(0), C=dHall, ldc=H)
             ops.gemm_bf16(ops.OP_TN, dLb, Hb, V, H, N, dLb.stride(0), Hb.stride(0), C=gC, ldc=H)
@@ -667,15 +692,24 @@ class _DecoderBase(nn.Module):
                 ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
             if backward:
                 gbuf = self._grad_target(c.grad_names + list(self._out_names()))
-                dHall = self._vocab_backward(c.top.Hall, logits, gbuf, c.top.Hb, dLb)
+                deferred = []
+                dHall = self._vocab_backward(c.top.Hall, logits, gbuf, c.top.Hb, dLb, defer=deferred)
                 if dLb is not None:
-                    # the scalar loss is bookkeeping: reduce it behind dC on side stream 0, not in front of dH
-                    with torch.cuda.stream(self._side(0)):
-                        ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
-                        if early_step is not None and gbuf is self.arena().gflat:
-                            self._publish(list(self._out_names()), gbuf)
-                            early_step(list(self._out_names()))
+                    def loss_and_bucket():
+                        # the scalar loss is bookkeeping: reduce it behind dC on side stream 0, not in front of dH
+                        with torch.cuda.stream(self._side(0)):
+                            ops.reduce_sum(row_loss, N, 1.0 / denom, loss)
+                            if early_step is not None and gbuf is self.arena().gflat:
+                                self._publish(list(self._out_names()), gbuf)
+                                early_step(list(self._out_names()))
+                    if deferred:
+                        deferred.append(loss_and_bucket)
+                    else:
+                        loss_and_bucket()
+                # (work deferred until the reverse recurrence of the top layer has been launched, see _layer_bwd)
+                self.__dict__["_after_recur"] = deferred
                 if grad_hook is not None and gbuf is self.arena().gflat:
+                    self._run_deferred()
                     self._join()
                     grad_hook(list(self._out_names()))       # bucket 0 is final: overlap its all-reduce
                 need_dfeat = features is not None and features.requires_grad
@@ -685,6 +719,7 @@ class _DecoderBase(nn.Module):
                     dfeat = self._run_backward(c, dHall, gbuf, need_dfeat)
                 finally:
                     self.__dict__["_bucket_hook"] = None
+                self._run_deferred()
                 self._join()
                 self._publish(c.grad_names + list(self._out_names()), gbuf)
                 if grad_hook is not None:

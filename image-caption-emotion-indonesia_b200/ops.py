@@ -300,6 +300,13 @@ def to_bf16_padded(x, pad_to=8):
     return out
 
 
+# Scheduling of the vocabulary projection's weight gradient (dC) against the reverse recurrence (decoders._vocab_backward):
+# 0 = launch it immediately on the side stream; 1 = make it runnable together with the recurrence but LAUNCH it after it
+# (the cluster-form recurrence needs whole free SMs, 16 per cluster); 2 = start it only after the recurrence finished.
+import os as _os
+DC_SCHEDULE = [int(_os.environ.get("SN_DC_SCHEDULE", "0"))]     # measured: 0 is the fastest (profiles/README.md, r2)
+DC_MAX_PAIRS = [int(_os.environ.get("SN_DC_MAX_PAIRS", "37"))]     # half of the 74 SM pairs (measured best, profiles/README.md r2)
+
 # K3 implementation in bf16 mode: "auto" = the cluster form (sn_recur_cl.cu) whenever the hidden size supports it and all
 # sample slices fit the device at once, else the flag-synchronised persistent kernel; "cluster" / "flags" force one.
 RECUR_IMPL = ["auto"]

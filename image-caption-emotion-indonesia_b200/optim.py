@@ -177,6 +177,8 @@ class FusedClampAdam:
             raise RuntimeError("peer-fused step needs every gradient in the arena")
         ranges = [(off, n) for off, n, _ in items]
         idx = [self.index[name] for _, _, name in items]
+        if not ranges:
+            return          # every bucket was exchanged early (the same on every rank): no empty barrier-only call
         ops.dp_adam_fused(peers.world, peers.rank, peers.grad_ptrs, peers.param_ptrs, peers.pads(bucket), self.m, self.v,
                           ranges, idx, self.steps_dev, self.lr_dev, self.coef_ws, self.betas[0], self.betas[1],
                           self.eps, self.grad_clip)

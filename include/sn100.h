@@ -335,6 +335,18 @@ int32_t sn_beam_step(const float* logits, int64_t ld, int64_t V, int32_t n_img, 
                      int32_t* n_done, int32_t* out_seq, int32_t* out_len, int32_t* n_unfinished,
                      const int32_t* step_dev, void* stream);
 
+/* sn_beam_step for FEW images: the same step spread over nch x more CTAs (per-chunk log-sum-exp partials, per-chunk
+ * top-k of the final scores, per-image merge + bookkeeping).  Same arguments as sn_beam_step plus the chunk count
+ * (1..32) and a work space of sn_beam_split_ws_floats() floats.  Same selection rule (score descending, ties -> lower
+ * flat index); the log-sum-exp is combined from chunk partials, so scores may differ from sn_beam_step in the last bit. */
+int64_t sn_beam_split_ws_floats(int32_t n_img, int32_t kmax, int32_t nch);
+int32_t sn_beam_step_split(const float* logits, int64_t ld, int64_t V, int32_t n_img, int32_t kmax,
+                           int32_t step, int32_t max_len, int32_t end_token, int32_t* k_live,
+                           float* run_score, int32_t* prev_word, int32_t* src_row, int32_t* cur_buf,
+                           int32_t* seqs, int32_t* done_seq, int32_t* done_len, float* done_score,
+                           int32_t* n_done, int32_t* out_seq, int32_t* out_len, int32_t* n_unfinished,
+                           const int32_t* step_dev, int32_t nch, float* ws, void* stream);
+
 /* ---- decode steps on FEW rows (single-image beam search, forward_step): matrix-vector kernels -----------------
  * replaces forward_step (stylenet/model.py:115-155, nn.LSTMCell nic/model.py:77) and the per-step C(h)
  * (model.py:234) when rows <= sn_skinny_max_rows(): one pass over the fp32 weights, rows held in shared memory.

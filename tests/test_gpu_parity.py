@@ -376,11 +376,12 @@ def test_peer_fused_adam_degenerate_world1():
     o1, o2 = sn.FusedClampAdam(d1, lr=1e-3), sn.FusedClampAdam(d2, lr=1e-3)
 
     class Fake:
-        pass
+        def pads(self, bucket):
+            return [q + 128 * bucket for q in self.pad_ptrs]
     a2 = d2.arena()
     pe = Fake()
     pe.world, pe.rank = 1, 0
-    pe.pad = torch.zeros(32, dtype=torch.int32, device="cuda")
+    pe.pad = torch.zeros(32 * 16, dtype=torch.int32, device="cuda")
     pe.param_ptrs, pe.grad_ptrs, pe.pad_ptrs = [a2.flat.data_ptr()], [a2.gflat.data_ptr()], [pe.pad.data_ptr()]
     for _ in range(3):
         for d in (d1, d2):
