@@ -40,7 +40,8 @@ SIGNATURES = {
     "sn_recur_bwd_bf16": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _I32] + [_P] * 11),
     "sn_recur_cl_max_clusters": (_I32, [_I64]),
     "sn_recur_fwd_cl": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _I32] + [_P] * 11),
-    "sn_recur_bwd_cl": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _I32] + [_P] * 10),
+    "sn_recur_bwd_cl": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _I32] + [_P] * 11),
+    "sn_gate_wait": (_I32, [_P, _I64, _P]),
     "sn_cast_bf16_gate_interleave": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _P]),
     "sn_recur_fwd_gemm": (_I32, [_I32, _I64, _I64, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sn_recur_hprev": (_I32, [_P, _P, _P, _P, _I64, _I64, _P, _P]),

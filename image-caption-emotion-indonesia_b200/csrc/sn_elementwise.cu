@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // Memory-bound kernels of the hot path: K1 gather/dropout/pack, K5 log-softmax+NLL(+grad, argmax,
 // top-5), deterministic loss reduction, K7 fused clamp+Adam.  All HBM-bound: coalesced, 16-byte
 // vectorised where the layout allows, grids sized from the SM count.
@@ -284,7 +285,13 @@ __device__ __forceinline__ void st_release_sys(int* p, int v) {
 template <int W>      // world size as a template parameter: the W peer loads / stores of an element are all in flight
 __global__ void __launch_bounds__(256) dp_adam_fused_kernel(DpPeers P, AdamRanges R, const float* __restrict__ coef,
                                                             float* __restrict__ m, float* __restrict__ v, float beta1,
-                                                            float beta2, float eps, float clip) {
+                                                            float beta2, float eps, float clip, int dbg) {
+  if (dbg) {        // timing experiments only (SN_DP_DEBUG): bit 0 = local gradient reads only, bit 1 = local stores only
+    for (int q = 0; q < P.world; ++q) {
+      if (dbg & 1) P.grad[q] = P.grad[P.rank];
+      if (dbg & 2) P.param[q] = P.param[P.rank];
+    }
+  }
   __shared__ int s_epoch, s_last;
   int* mypad = P.pad[P.rank];
   if (threadIdx.x == 0) s_epoch = mypad[PAD_EPOCH] + 1;
@@ -314,32 +321,46 @@ __global__ void __launch_bounds__(256) dp_adam_fused_kernel(DpPeers P, AdamRange
     const int64_t lim = (aid + 1) * ADAM_CHUNK < end ? (aid + 1) * ADAM_CHUNK : end;
     const float ss = coef[2 * r], bc = coef[2 * r + 1];
     if ((base & 3) == 0 && lim - base == ADAM_CHUNK) {
+      // NIT iterations at a time with ALL their loads issued up front: the peer loads cross NVLink (~2 us each), so the
+      // number of them in flight per thread, not the instruction count, sets the pace
+      constexpr int NIT = W <= 4 ? 4 : 2;
 #pragma unroll
-      for (int it = 0; it < ADAM_CHUNK / (256 * 4); ++it) {
-        const int64_t i = base + (int64_t)(it * 256 + threadIdx.x) * 4;
-        float4 t[W];
+      for (int it0 = 0; it0 < ADAM_CHUNK / (256 * 4); it0 += NIT) {
+        float4 t[NIT][W], m4[NIT], v4[NIT], p4[NIT];
 #pragma unroll
-        for (int q = 0; q < W; ++q) t[q] = __ldcg(reinterpret_cast<const float4*>(P.grad[q] + i));
-        float4 g4 = t[0];
+        for (int u = 0; u < NIT; ++u) {
+          const int64_t i = base + (int64_t)((it0 + u) * 256 + threadIdx.x) * 4;
 #pragma unroll
-        for (int q = 1; q < W; ++q) { g4.x += t[q].x; g4.y += t[q].y; g4.z += t[q].z; g4.w += t[q].w; }
-        float4 m4 = *reinterpret_cast<const float4*>(m + i);
-        float4 v4 = *reinterpret_cast<const float4*>(v + i);
-        float4 p4 = *reinterpret_cast<const float4*>(P.param[P.rank] + i);
-        float* gp = &g4.x; float* mp = &m4.x; float* vp = &v4.x; float* pp = &p4.x;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float gi = gp[k];
-          if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
-          const float mi = mp[k] + (1.f - beta1) * (gi - mp[k]);
-          const float vi = vp[k] * beta2 + (1.f - beta2) * gi * gi;
-          pp[k] = pp[k] - ss * (mi / (sqrtf(vi) / bc + eps));
-          mp[k] = mi; vp[k] = vi;
+          for (int q = 0; q < W; ++q) t[u][q] = __ldcg(reinterpret_cast<const float4*>(P.grad[q] + i));
         }
-        *reinterpret_cast<float4*>(m + i) = m4;
-        *reinterpret_cast<float4*>(v + i) = v4;
 #pragma unroll
-        for (int q = 0; q < W; ++q) *reinterpret_cast<float4*>(P.param[q] + i) = p4;
+        for (int u = 0; u < NIT; ++u) {
+          const int64_t i = base + (int64_t)((it0 + u) * 256 + threadIdx.x) * 4;
+          m4[u] = *reinterpret_cast<const float4*>(m + i);
+          v4[u] = *reinterpret_cast<const float4*>(v + i);
+          p4[u] = *reinterpret_cast<const float4*>(P.param[P.rank] + i);
+        }
+#pragma unroll
+        for (int u = 0; u < NIT; ++u) {
+          const int64_t i = base + (int64_t)((it0 + u) * 256 + threadIdx.x) * 4;
+          float4 g4 = t[u][0];
+#pragma unroll
+          for (int q = 1; q < W; ++q) { g4.x += t[u][q].x; g4.y += t[u][q].y; g4.z += t[u][q].z; g4.w += t[u][q].w; }
+          float* gp = &g4.x; float* mp = &m4[u].x; float* vp = &v4[u].x; float* pp = &p4[u].x;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float gi = gp[k];
+            if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+            const float mi = mp[k] + (1.f - beta1) * (gi - mp[k]);
+            const float vi = vp[k] * beta2 + (1.f - beta2) * gi * gi;
+            pp[k] = pp[k] - ss * (mi / (sqrtf(vi) / bc + eps));
+            mp[k] = mi; vp[k] = vi;
+          }
+          *reinterpret_cast<float4*>(m + i) = m4[u];
+          *reinterpret_cast<float4*>(v + i) = v4[u];
+#pragma unroll
+          for (int q = 0; q < W; ++q) *reinterpret_cast<float4*>(P.param[q] + i) = p4[u];
+        }
       }
       continue;
     }
@@ -545,9 +566,11 @@ int32_t sn_dp_adam_fused(int32_t world, int32_t rank, void* const* grad_ptrs, vo
   if (n_ranges > 0) adam_prepare_kernel<<<1, 64, 0, st>>>(R, steps_dev, lr_dev, coef_ws, beta1, beta2);
   // every rank launches the same grid even when it owns no chunk: the kernel is also the cross-GPU barrier
   int64_t mine = (R.chunk_start[R.n] + world - 1) / world;
-  int64_t cap = (int64_t)sn::dev_info().sm_count * 8;      // one owned chunk per CTA whenever they all fit
+  // persistent: at most 3 CTAs per SM loop over the slots (every CTA ends with a system-scope fence and an atomic)
+  int64_t cap = (int64_t)sn::dev_info().sm_count * 3;
   unsigned grid = (unsigned)(mine < 1 ? 1 : (mine < cap ? mine : cap));
-#define SN_DP_LAUNCH(WW) dp_adam_fused_kernel<WW><<<grid, 256, 0, st>>>(P, R, coef_ws, m, v, beta1, beta2, eps, clip)
+  static const int dbg = [] { const char* e = getenv("SN_DP_DEBUG"); return e ? atoi(e) : 0; }();
+#define SN_DP_LAUNCH(WW) dp_adam_fused_kernel<WW><<<grid, 256, 0, st>>>(P, R, coef_ws, m, v, beta1, beta2, eps, clip, dbg)
   switch (world) {
     case 1: SN_DP_LAUNCH(1); break;
     case 2: SN_DP_LAUNCH(2); break;

@@ -40,6 +40,7 @@ struct CArgs {
   const float* XP; const __nv_bfloat16* Wb; const float* bhh; const float* h_init;
   float* Hall; __nv_bfloat16* Hb; __nv_bfloat16* Hprevb; float* Call; float* gates; float* c_state;
   const float* c_init; const float* dHall; float* dZ; __nv_bfloat16* dZb; float* dh_carry; float* dc_carry;
+  int* start_flag;      // optional [3]: {arrivals, generations started, generations consumed by sn_gate_wait}
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -337,6 +338,15 @@ __global__ void __launch_bounds__(NTH, 1) recur_bwd_cl_kernel(CArgs a) {
   const int rank = (int)cluster_ctarank();
   const int s0 = (int)cluster_id_x() * NS, u0 = rank * 32;
   const int K4 = 4 * H;
+  // "every CTA of this launch is resident": lets work queued behind sn_gate_wait start on the SMs this kernel leaves free
+  // only AFTER its clusters have been placed (a cluster needs 16 completely free SMs of one GPC)
+  if (tid == 0 && a.start_flag) {
+    if (atomicAdd(a.start_flag, 1) == (int)gridDim.x - 1) {
+      a.start_flag[0] = 0;
+      __threadfence();
+      atomicAdd(a.start_flag + 1, 1);
+    }
+  }
 
   // W_hh rows of this CTA (k = gate*32 + unit -> row gate*H + u0 + unit), all H columns, as B fragments:
   // b0 = {W[k0 + 2q][n], W[k0 + 2q + 1][n]}, b1 = same at k0 + 8;  n = unit (warp*NTB + nt)*8 + lane/4.
@@ -519,6 +529,26 @@ __global__ void __launch_bounds__(NTH, 1) recur_bwd_cl_kernel(CArgs a) {
   cluster_sync();
 }
 
+// flag[1] = launches of the reverse recurrence whose CTAs all became resident (bumped by the kernel itself),
+// flag[2] = launches this gate has accounted for.  The gate is queued long before the recurrence can start (it only
+// depends on the vocabulary backward), so a bump that is already there when the gate starts belongs to an EARLIER step
+// whose gate timed out: drop it, then wait for this step's bump.  A timeout undoes the accounting, so one missed
+// hand-shake (e.g. the first step, while kernels are still being loaded) cannot shift every later step by one.
+__global__ void gate_wait_kernel(int* flag, long long timeout_cycles) {
+  const long long t0 = clock64();
+  const int stale = sn::ld_acquire(flag + 1);
+  if (stale > flag[2]) flag[2] = stale;
+  const int target = flag[2] + 1;
+  flag[2] = target;
+  while (sn::ld_acquire(flag + 1) < target) {
+    if (clock64() - t0 > timeout_cycles) {       // never hang: the ordering is an optimisation, not a dependency
+      flag[2] = target - 1;
+      return;
+    }
+    __nanosleep(200);
+  }
+}
+
 template <typename Kern>
 int32_t launch_cl(Kern kernel, int CS, size_t smem, const CArgs& a, cudaStream_t stream, const char* what, int* max_clusters) {
   cudaLaunchConfig_t cfg = {};
@@ -601,7 +631,7 @@ int32_t sn_recur_fwd_cl(int32_t cell, int64_t H, int64_t B, const int32_t* batch
 int32_t sn_recur_bwd_cl(int32_t cell, int64_t H, int64_t B, const int32_t* batch_sizes, const int32_t* offsets,
                         int32_t t0, int32_t t1, const void* Whh_bf16, const float* c_init, const float* Call,
                         const float* gates, const float* dHall, float* dZ, void* dZb, float* dh_carry,
-                        float* dc_carry, void* stream) {
+                        float* dc_carry, int32_t* start_flag, void* stream) {
   SN_REQUIRE(cell == SN_CELL_FACTORED || cell == SN_CELL_LSTM, "sn_recur_bwd_cl: bad cell %d", cell);
   SN_REQUIRE(t0 >= 0 && t1 >= t0 && B > 0, "sn_recur_bwd_cl: bad step range");
   SN_REQUIRE(Whh_bf16 && Call && gates && dHall && dZb && dh_carry && dc_carry && batch_sizes && offsets,
@@ -611,8 +641,14 @@ int32_t sn_recur_bwd_cl(int32_t cell, int64_t H, int64_t B, const int32_t* batch
   a.cell = cell; a.B = (int)B; a.t0 = t0; a.t1 = t1; a.bs = batch_sizes; a.off = offsets;
   a.Wb = (const __nv_bfloat16*)Whh_bf16; a.c_init = c_init; a.Call = const_cast<float*>(Call);
   a.gates = const_cast<float*>(gates); a.dHall = dHall; a.dZ = dZ; a.dZb = (__nv_bfloat16*)dZb;
-  a.dh_carry = dh_carry; a.dc_carry = dc_carry;
+  a.dh_carry = dh_carry; a.dc_carry = dc_carry; a.start_flag = start_flag;
   return dispatch(true, H, a, (cudaStream_t)stream, nullptr);
+}
+
+int32_t sn_gate_wait(int32_t* flag3, int64_t timeout_us, void* stream) {
+  SN_REQUIRE(flag3 && timeout_us > 0, "sn_gate_wait: bad argument");
+  gate_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag3, (long long)timeout_us * 2000);
+  return sn::check_launch("sn_gate_wait");
 }
 
 }  // extern "C"

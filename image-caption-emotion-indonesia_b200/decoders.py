@@ -101,7 +101,7 @@ class _DecoderBase(nn.Module):
     # pickled; the arena is rebuilt on first use).  The reference pickles the whole decoder every epoch
     # (save_checkpoint, stylenet/utils.py:62-90) and un-pickles it to resume (train_multitask.py:169-176).
     _TRANSIENT = ("_greedy_graphs", "_decode_sessions", "_side_streams", "_out_w16", "_out_w16_pref", "_out_w16_ev",
-                  "_out_h16", "_seed_dev", "_arena", "_att_cache")
+                  "_out_h16", "_seed_dev", "_arena", "_att_cache", "_gate_flag", "_gate_armed", "_after_recur", "_bucket_hook")
 
     def __getstate__(self):
         st = self.__dict__.copy()
@@ -413,7 +413,7 @@ class _DecoderBase(nn.Module):
                 ops.recur_bwd_gemm(self.cell, H, B, plan, cl.w16["Whh"], cl.Call, cl.gates, dHall, dZ, cl.dZb, dc)
             else:
                 ops.recur_bwd_bf16(self.cell, H, B, d["bs"], d["off"], 0, T, cl.w16["Whh"], None, cl.Call, cl.gates,
-                                   dHall, dZ, cl.dZb, dh, dc)
+                                   dHall, dZ, cl.dZb, dh, dc, start_flag=self.__dict__.pop("_gate_armed", None))
             self._run_deferred()
             with torch.cuda.stream(self._fork()):
                 ops.gemm_bf16(ops.OP_TN, cl.dZb, cl.Hpb, 4 * H, H, N, 4 * H, H, C=gW, ldc=H)
@@ -496,7 +496,7 @@ class _DecoderBase(nn.Module):
             return logits
         return ops.linear_nt(Hall.contiguous(), out.weight, out.bias)
 
-    def _vocab_backward(self, Hall, dlogits, gbuf, Hb=None, dLb=None, defer=None):
+    def _vocab_backward(self, Hall, dlogits, gbuf, Hb=None, dLb=None, defer=None, gate_B=None):
         out = self._out()
         V, H = out.weight.shape
         N = Hall.shape[0]
@@ -528,10 +528,22 @@ class _DecoderBase(nn.Module):
                     # LAUNCHED after it, and is capped to the SMs the 6 clusters leave free.
                     side.wait_stream(torch.cuda.current_stream())
 
+                gate = None
+                if mode_dc == 0 and gate_B is not None and ops.GATE_DC[0] and ops.recur_cluster_ok(H, gate_B):
+                    # the cluster-form reverse recurrence needs 16 completely free SMs per cluster: everything queued on
+                    # this side stream (dC, db_C, the bucket's exchange / Adam) waits behind a gate that opens once the
+                    # recurrence's CTAs are resident, and then runs on the SMs it leaves free
+                    gate = self.__dict__.get("_gate_flag")
+                    if gate is None or gate.device != dHall.device:
+                        gate = self.__dict__["_gate_flag"] = torch.zeros(3, dtype=torch.int32, device=dHall.device)
+                    self.__dict__["_gate_armed"] = gate
+
                 def side_work():
                     if mode_dc == 2:
                         side.wait_stream(torch.cuda.current_stream())       # after the reverse recurrence, full width
                     with torch.cuda.stream(side):
+                        if gate is not None:
+                            ops.gate_wait(gate)
                         ops.gemm_bf16(ops.OP_TN, dLb, Hb, V, H, N, dLb.stride(0), Hb.stride(0), C=gC, ldc=H,
                                       max_pairs=0 if mode_dc == 2 else ops.DC_MAX_PAIRS[0])
                         ops.colsum_bf16(dLb, N, V, dLb.stride(0), gb)
@@ -693,7 +705,8 @@ class _DecoderBase(nn.Module):
             if backward:
                 gbuf = self._grad_target(c.grad_names + list(self._out_names()))
                 deferred = []
-                dHall = self._vocab_backward(c.top.Hall, logits, gbuf, c.top.Hb, dLb, defer=deferred)
+                gate_B = plan.B if (c.top.Hpb is not None and not (plan.B >= ops.RECUR_GEMM_MIN_BATCH[0] and self.hidden_size % 64 == 0)) else None
+                dHall = self._vocab_backward(c.top.Hall, logits, gbuf, c.top.Hb, dLb, defer=deferred, gate_B=gate_B)
                 if dLb is not None:
                     def loss_and_bucket():
                         # the scalar loss is bookkeeping: reduce it behind dC on side stream 0, not in front of dH

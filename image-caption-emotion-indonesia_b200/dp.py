@@ -95,6 +95,7 @@ class PeerExchange:
 
 
 EARLY_PEER_EXCHANGE = [True]     # split the peer-fused exchange+Adam: vocabulary projection early, the rest at the end
+PEER_BUCKETS = [False]           # also exchange the W_hh/U, S/V and embedding buckets as soon as they are final (slower: see step())
 
 
 class DataParallelTrainer:
@@ -147,8 +148,14 @@ class DataParallelTrainer:
                 # and S / V under the rest of the projection backward; only the embedding is left for the end of the step.
                 # Every bucket has its own signal pad (the kernels overlap each other).
                 calls = [0]
+                out_names = set(self.decoder._out_names())
 
                 def early_step(names):
+                    # every exchange kernel costs two cross-GPU barriers plus the skew between the ranks (~50 us measured
+                    # at N=2, profiles/r2_timeline_N2.txt): only the large vocabulary bucket, which has the whole reverse
+                    # recurrence + projection backward to hide under, goes early; everything else is ONE call at the end
+                    if not PEER_BUCKETS[0] and not out_names.issuperset(names):
+                        return
                     self.optimizer.step_peer(peers, only=names, bucket=calls[0])
                     calls[0] += 1
                     early.extend(names)

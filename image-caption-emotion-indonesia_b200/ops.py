@@ -307,6 +307,11 @@ import os as _os
 DC_SCHEDULE = [int(_os.environ.get("SN_DC_SCHEDULE", "0"))]     # measured: 0 is the fastest (profiles/README.md, r2)
 DC_MAX_PAIRS = [int(_os.environ.get("SN_DC_MAX_PAIRS", "37"))]     # half of the 74 SM pairs (measured best, profiles/README.md r2)
 
+# hold the side-stream work of the vocabulary backward behind sn_gate_wait (experiment, OFF: no gain on one GPU --
+# the step is bound by total work, not by the delayed clusters -- and a 2-GPU run with the peer exchange behind the
+# gate did not finish; profiles/README.md r2)
+GATE_DC = [int(_os.environ.get("SN_GATE_DC", "0"))]
+
 # K3 implementation in bf16 mode: "auto" = the cluster form (sn_recur_cl.cu) whenever the hidden size supports it and all
 # sample slices fit the device at once, else the flag-synchronised persistent kernel; "cluster" / "flags" force one.
 RECUR_IMPL = ["auto"]
@@ -342,12 +347,13 @@ def recur_fwd_bf16(cell, H, B, bs, off, t0, t1, XP, Whh_b, bhh, h_init, Hall, Hb
                                   _ptr(c_state), _ptr(ws), _stream()), "sn_recur_fwd_bf16")
 
 
-def recur_bwd_bf16(cell, H, B, bs, off, t0, t1, Whh_b, c_init, Call, gates, dHall, dZ, dZb, dh_carry, dc_carry):
+def recur_bwd_bf16(cell, H, B, bs, off, t0, t1, Whh_b, c_init, Call, gates, dHall, dZ, dZb, dh_carry, dc_carry,
+                   start_flag=None):
     if recur_cluster_ok(H, B):
         check(lib().sn_recur_bwd_cl(cell, H, B, _ptr(bs), _ptr(off), t0, t1, _ptr(_req(Whh_b, torch.bfloat16)),
                                     _ptr(c_init), _ptr(Call), _ptr(gates), _ptr(_req(dHall)), _ptr(dZ),
-                                    _ptr(_req(dZb, torch.bfloat16)), _ptr(dh_carry), _ptr(dc_carry), _stream()),
-              "sn_recur_bwd_cl")
+                                    _ptr(_req(dZb, torch.bfloat16)), _ptr(dh_carry), _ptr(dc_carry), _ptr(start_flag),
+                                    _stream()), "sn_recur_bwd_cl")
         return
     ws = _recur_ws(dZb.device, t1 + 1)
     check(lib().sn_recur_bwd_bf16(cell, H, B, _ptr(bs), _ptr(off), t0, t1, _ptr(_req(Whh_b, torch.bfloat16)),
@@ -522,3 +528,8 @@ def decode_cell(cell, H, R, Wx, Kx, X, group_x, bx, Wh, bh, h_prev, c_prev, src_
     check(lib().sn_decode_cell(cell, H, R, _ptr(_req(Wx)), Wx.stride(0), Kx, _ptr(_req(X)), X.stride(0), group_x,
                                _ptr(bx), _ptr(_req(Wh)), _ptr(bh), _ptr(_req(h_prev)), _ptr(_req(c_prev)),
                                _ptr(src_row), _ptr(_req(h_out)), _ptr(_req(c_out)), _stream()), "sn_decode_cell")
+
+
+def gate_wait(flag3, timeout_us=300):
+    """Queue a one-thread kernel that returns once the cluster-form reverse recurrence (given the same flag) is resident."""
+    check(lib().sn_gate_wait(_ptr(_req(flag3, torch.int32)), int(timeout_us), _stream()), "sn_gate_wait")

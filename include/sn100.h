@@ -189,7 +189,12 @@ int32_t sn_recur_bwd_cl(int32_t cell, int64_t H, int64_t B, const int32_t* batch
                         const int32_t* offsets, int32_t t0, int32_t t1, const void* Whh_bf16,
                         const float* c_init, const float* Call, const float* gates,
                         const float* dHall, float* dZ, void* dZb, float* dh_carry, float* dc_carry,
-                        void* stream);
+                        int32_t* start_flag, void* stream);
+/* start_flag (may be NULL): 3 zero-initialised int32 words.  The backward kernel bumps word 1 once all its CTAs are
+ * resident; sn_gate_wait (one spinning thread, queued on ANOTHER stream) returns when a bump it has not consumed yet
+ * is there (or after timeout_us).  Work queued behind the gate -- the vocabulary weight gradient, bucket exchanges --
+ * then starts on the SMs the clusters leave free instead of taking SMs the clusters still need. */
+int32_t sn_gate_wait(int32_t* flag3, int64_t timeout_us, void* stream);
 
 /* K3 in the LARGE-BATCH regime (B >= ~1000 samples per GPU): one tcgen05 CTA-pair GEMM per time step with the
  * cell fused into the epilogue, instead of the latency-optimised persistent kernel above.
