@@ -59,10 +59,96 @@ def lib():
     return l
 
 
+# fp32 GEMMs: "split" = large ones run on the bf16 tensor cores with 3-limb operands (SN_PREC_BF16X6, fp32-grade
+# accuracy: dropped terms <= 2^-24), small / TMA-illegal ones on the fp32 FFMA kernel; "simt" = always FFMA.
+FP32_GEMM = ["split"]
+SPLIT_MIN_MACS = 1 << 22
+SPLIT_MAX_ACC_K = 768        # longest contraction accumulated in one TMEM accumulator in fp32 mode (see _gemm_split)
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def _split_cols(X, off, rows, K, ld, batch, s, pattern):
+    """Limb-expand an operand whose contraction dimension runs along the columns.  Returns (tensor, ld', s') or None
+    when the group layout is not one of {column blocks of width K, row-stacked contiguous groups}."""
+    Kp = _pad8(K)
+    if batch > 1 and s < ld:
+        if s != K or ld < batch * K:
+            return None
+        G, R = batch, rows
+    elif batch > 1:
+        if s != rows * ld:
+            return None
+        G, R = 1, rows * batch
+    else:
+        G, R = 1, rows
+    out = torch.empty(R, G * 6 * Kp, dtype=torch.bfloat16, device=X.device)
+    check(lib().sn_split_limbs_cols(ctypes.c_void_p(X.data_ptr() + 4 * off), R, G, K, ld, _ptr(out), Kp, pattern,
+                                    _stream()), "sn_split_limbs_cols")
+    return out, G * 6 * Kp, (6 * Kp if G > 1 else rows * 6 * Kp)
+
+
+def _split_rows(X, off, K, cols, ld, batch, s, pattern):
+    """Limb-expand an operand whose contraction dimension runs along the rows ([K, cols] per group)."""
+    Kp, ldp = _pad8(K), _pad8(ld)
+    if batch > 1 and s < ld:
+        if s % 8 != 0:
+            return None
+        G = 1                                    # column groups: the rows are shared, expand the whole matrix once
+    elif batch > 1:
+        if s != K * ld:
+            return None
+        G = batch
+    else:
+        G = 1
+    out = torch.empty(G * 6 * Kp, ldp, dtype=torch.bfloat16, device=X.device)
+    check(lib().sn_split_limbs_rows(ctypes.c_void_p(X.data_ptr() + 4 * off), G, K, ld, ld, _ptr(out), Kp, ldp, pattern,
+                                    _stream()), "sn_split_limbs_rows")
+    return out, ldp, (s if (batch > 1 and s < ld) else 6 * Kp * ldp)
+
+
+def _gemm_split(op, A, B, C, M, N, K, lda, ldb, ldc, bias, beta, batch, sA, sB, sC, sBias, a_off, b_off, c_off,
+                bias_off):
+    if K > 10900:               # 6*Kp must stay a sane contraction length / fit the row-split launch
+        return False
+    # The tensor core aligns every MMA's products to its running fp32 accumulator and truncates (~2^-24 of the
+    # accumulator per 16-deep MMA, one-sided): a contraction of thousands of terms in ONE accumulator drifts past the
+    # fp32 mode's budget (measured: 1.2e-5 on dW_hh with K = 1920 tokens).  Long contractions are therefore cut into
+    # pieces of <= 768 accumulated in separate accumulators (the CTA-pair kernel's deterministic work-space split-K) and
+    # summed in fp32 with round-to-nearest; the single-CTA kernel (M < 256) has no such path -> FFMA there.
+    Kp6 = 6 * _pad8(K)
+    splits = 1
+    if K > SPLIT_MAX_ACC_K:
+        if M < 256 or N % 4 != 0:
+            return False
+        splits = -(-Kp6 // SPLIT_MAX_ACC_K)
+        while splits > 1 and M * N * batch * splits * 4 > (1 << 30):
+            splits -= 1
+    ea = _split_cols(A, a_off, M, K, lda, batch, sA, 0) if op in (OP_NT, OP_NN) else _split_rows(A, a_off, K, M, lda, batch, sA, 0)
+    if ea is None:
+        return False
+    eb = _split_cols(B, b_off, N, K, ldb, batch, sB, 1) if op == OP_NT else _split_rows(B, b_off, K, N, ldb, batch, sB, 1)
+    if eb is None:
+        return False
+    LAUNCHES[0] += 2
+    gemm_bf16(op, ea[0], eb[0], M, N, Kp6, ea[1], eb[1], C=C, ldc=ldc, bias=bias, beta=beta, batch=batch,
+              sA=ea[2] if batch > 1 else 0, sB=eb[2] if batch > 1 else 0, sC=sC, sBias=sBias, c_off=c_off,
+              bias_off=bias_off, splits=splits if splits > 1 else 1, impl="pair" if splits > 1 else None)
+    return True
+
+
 def gemm(op, A, B, C, M, N, K, lda, ldb, ldc, bias=None, beta=0.0, batch=1, sA=0, sB=0, sC=0, sBias=0,
          a_off=0, b_off=0, c_off=0, bias_off=0):
     """C = op(A) op(B) + bias + beta*C.  Offsets are in elements (pointer arithmetic on the base)."""
     _req(A); _req(B); _req(C)
+    # (M >= 256: the time-batched GEMMs.  Per-step GEMMs on <= 96 rows would re-expand their weight operand every step.)
+    if (FP32_GEMM[0] == "split" and M * N * K * batch >= SPLIT_MIN_MACS and M >= 256 and N >= 16 and K >= 16
+            and batch <= 4 and ldc % 4 == 0 and c_off % 4 == 0 and (batch == 1 or sC % 4 == 0)
+            and _gemm_split(op, A, B, C, M, N, K, lda, ldb, ldc, bias, beta, batch, sA, sB, sC, sBias, a_off, b_off,
+                            c_off, bias_off)):
+        return C
     pa = ctypes.c_void_p(A.data_ptr() + 4 * a_off)
     pb = ctypes.c_void_p(B.data_ptr() + 4 * b_off)
     pc = ctypes.c_void_p(C.data_ptr() + 4 * c_off)

@@ -37,7 +37,8 @@ extern "C" {
 
 /* GEMM arithmetic */
 #define SN_PREC_F32 0   /* fp32 FFMA, exact-fp32 accumulation (fp32 parity mode, <=1e-5)       */
-#define SN_PREC_TF32X3 1 /* tcgen05 kind::tf32, 3-pass split (fp32-grade accuracy on tensor cores) */
+#define SN_PREC_BF16X6 1 /* fp32-grade accuracy on the bf16 tensor cores: 3 bf16 limbs per operand, 6 limb products laid
+                            out along K (sn_split_limbs_* + sn_gemm2_bf16 / sn_gemm_bf16); fp32 mode's large GEMMs  */
 #define SN_PREC_BF16 2  /* tcgen05 kind::f16 bf16 operands, fp32 accumulate in TMEM            */
 
 /* recurrent cell kinds */
@@ -90,9 +91,10 @@ int32_t sn_gemm_bf16(int32_t op, int64_t M, int64_t N, int64_t K, const void* A,
                      const void* B, int64_t ldb, float* C, int64_t ldc, void* Cb, int64_t ldcb,
                      const float* bias, float beta, int32_t batch, int64_t strideA, int64_t strideB,
                      int64_t strideC, int64_t strideCb, int64_t strideBias, void* stream);
-/* split-K variant: the K loop is divided over `splits` CTAs per tile, partial tiles are reduced with fp32
- * atomics into a zeroed C (fp32 output only, beta = 0).  splits = 0 picks a factor that fills ~2 waves of
- * the SMs when the tile count alone cannot (weight-gradient GEMMs: few tiles, long K = tokens). */
+/* split-K variant of the single-CTA kernel (small M only; the CTA-pair kernel sn_gemm2_bf16 has its own
+ * deterministic work-space split-K): the K loop is divided over `splits` CTAs per tile, partial tiles are
+ * reduced with fp32 atomics into a zeroed C (fp32 output only, beta = 0; NOT bit-reproducible -- measured
+ * slower than the work-space reduction for the weight-gradient GEMMs, profiles/README.md r1_d).  splits = 1: off. */
 int32_t sn_gemm_bf16_splitk(int32_t op, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
                             const void* B, int64_t ldb, float* C, int64_t ldc, void* Cb, int64_t ldcb,
                             const float* bias, float beta, int32_t batch, int64_t strideA,
@@ -351,6 +353,18 @@ int32_t sn_beam_step_split(const float* logits, int64_t ld, int64_t V, int32_t n
                            int32_t* seqs, int32_t* done_seq, int32_t* done_len, float* done_score,
                            int32_t* n_done, int32_t* out_seq, int32_t* out_len, int32_t* n_unfinished,
                            const int32_t* step_dev, int32_t nch, float* ws, void* stream);
+
+/* ---- SN_PREC_BF16X6: limb expansion of fp32 GEMM operands (see sn_split.cu) ------------------------------------
+ * x = x0 + x1 + x2 (bf16 limbs); left operands get the slots [x1 x0 x2 x0 x1 x0], right operands [x1 x2 x0 x1 x0 x0]
+ * along the contraction dimension, so ONE bf16 GEMM with K' = 6*Kp evaluates a1b1+a0b2+a2b0+a0b1+a1b0+a0b0 in fp32
+ * (smallest products first: the tensor core's accumulator alignment truncates relative to the running sum).
+ *   _cols: K runs along the columns.  src [R, G*K] (pitch ld) -> dst bf16 [R, G*6*Kp] (Kp = K padded to 8, zeros)
+ *   _rows: K runs along the rows.     src [G*K, C] (pitch ld) -> dst bf16 [G*6*Kp, Cp]  (Cp = C padded to 8, zeros)
+ * pattern: 0 = left operand, 1 = right operand. */
+int32_t sn_split_limbs_cols(const float* src, int64_t R, int64_t G, int64_t K, int64_t ld, void* dst,
+                            int64_t Kp, int32_t pattern, void* stream);
+int32_t sn_split_limbs_rows(const float* src, int64_t G, int64_t K, int64_t C, int64_t ld, void* dst,
+                            int64_t Kp, int64_t Cp, int32_t pattern, void* stream);
 
 /* ---- decode steps on FEW rows (single-image beam search, forward_step): matrix-vector kernels -----------------
  * replaces forward_step (stylenet/model.py:115-155, nn.LSTMCell nic/model.py:77) and the per-step C(h)
