@@ -25,30 +25,50 @@ class _StepCtx:
     pass
 
 
+def _n_layers(dec):
+    """Stacked decoders (stack.DecoderFactoredLSTMStack) keep one (h, c) per layer; the reference models have one."""
+    return int(dec.num_layers) if hasattr(dec, "_upper_layers_fwd") and type(dec).__name__.endswith("Stack") else 1
+
+
+def _rw(dec, layer):
+    return dec._recurrent_weights(layer) if layer else dec._recurrent_weights()
+
+
 def single_step(dec, embedded, states, mode):
-    """forward_step(embedded, states[, mode]) -> (h, (h, c)) on the kernels (inference only)."""
+    """forward_step(embedded, states[, mode]) -> (h, (h, c)) on the kernels (inference only).  Stacked decoders take and
+    return states of shape [num_layers, R, H]."""
     h, c = states
-    R, H = h.shape
+    L = _n_layers(dec)
+    stacked = h.dim() == 3
+    if L > 1 and not stacked:
+        raise ValueError("the stack's forward_step takes states of shape [num_layers, R, H]")
+    hs = h.detach().float().contiguous().reshape(L, -1, h.shape[-1])
+    cs = c.detach().float().contiguous().reshape(L, -1, h.shape[-1])
+    R, H = hs.shape[1], hs.shape[2]
     dev = h.device
-    ctx = _StepCtx()
     X = embedded.detach().float().contiguous()
+    h_new = torch.empty(L, R, H, dtype=torch.float32, device=dev)
+    c_new = torch.empty(L, R, H, dtype=torch.float32, device=dev)
     with torch.no_grad():
         ops.lib()
         dec.arena()
-        if R <= ops.SKINNY_MAX_ROWS:
-            h_new = torch.empty(R, H, dtype=torch.float32, device=dev)
-            c_new = torch.empty(R, H, dtype=torch.float32, device=dev)
-            dec._small_step(ctx, X, mode, R, h.detach().float().contiguous(), c.detach().float().contiguous(), None,
-                            h_new, c_new)
-            return h_new, (h_new, c_new)
-        ctx.XP = torch.empty(R, 4 * H, dtype=torch.float32, device=dev)
-        dec._input_projection(ctx, X, mode, 0, R)
-        Whh, bhh = dec._recurrent_weights()
-        h_new = torch.empty(R, H, dtype=torch.float32, device=dev)
-        c_new = c.detach().float().clone()
-        ops.recur_fwd(dec.cell, H, R, _i32(dev, [R]), _i32(dev, [0]), 0, 1, ctx.XP, Whh, bhh,
-                      h.detach().float().contiguous(), h_new, None, None, None, c_new)
-    return h_new, (h_new, c_new)
+        for l in range(L):
+            ctx = _StepCtx()
+            ctx.layer = l
+            kw = {"layer": l} if l else {}
+            if R <= ops.SKINNY_MAX_ROWS:
+                dec._small_step(ctx, X, mode, R, hs[l], cs[l], None, h_new[l], c_new[l], **kw)
+            else:
+                ctx.XP = torch.empty(R, 4 * H, dtype=torch.float32, device=dev)
+                dec._input_projection(ctx, X, mode, 0, R)
+                Whh, bhh = _rw(dec, l)
+                c_new[l].copy_(cs[l])
+                ops.recur_fwd(dec.cell, H, R, _i32(dev, [R]), _i32(dev, [0]), 0, 1, ctx.XP, Whh, bhh, hs[l], h_new[l],
+                              None, None, None, c_new[l])
+            X = h_new[l]
+    if stacked:
+        return h_new[L - 1], (h_new, c_new)
+    return h_new[0], (h_new[0], c_new[0])
 
 
 def _vocab_step(dec, h_new, logits, cache):
@@ -153,8 +173,9 @@ class _DecodeSession:
         self.st = BeamState(n_img, k, dec.max_seq_length, start_token, dev)
         R = self.st.R
         f32 = dict(dtype=torch.float32, device=dev)
-        self.h, self.c = torch.zeros(R, H, **f32), torch.zeros(R, H, **f32)
-        self.h_new = torch.empty(R, H, **f32)
+        self.L = L = _n_layers(dec)
+        self.h, self.c = torch.zeros(L, R, H, **f32), torch.zeros(L, R, H, **f32)      # one state per layer
+        self.h_new = torch.empty(L, R, H, **f32)
         self.logits = torch.empty(R, V, **f32)
         self.X = torch.empty(R, E, **f32)
         self.ctx = _StepCtx()
@@ -173,7 +194,7 @@ class _DecodeSession:
         # re-ordering of the state folded into the next step's read (no index_select kernels)
         self.skinny = R <= ops.SKINNY_MAX_ROWS
         if self.skinny:
-            self.hB, self.cB = torch.zeros(R, H, **f32), torch.zeros(R, H, **f32)
+            self.hB, self.cB = torch.zeros(L, R, H, **f32), torch.zeros(L, R, H, **f32)
             self.flip = 0              # 0: the state is in (h, c); 1: in (hB, cB)
 
     def step(self, step, feed_image, device_step):
@@ -186,16 +207,23 @@ class _DecodeSession:
         else:
             ops.gather_pack_fwd(self.dummy_cap, emb.weight, None, False, self.row_img, self.row_zero, st.prev_word, R,
                                 self.X, 0.0, 0)
-        dec._input_projection(self.ctx, self.X, self.mode, 0, R)
-        Whh, bhh = dec._recurrent_weights()
-        ops.recur_fwd(dec.cell, H, R, self.bs1, self.off1, 0, 1, self.ctx.XP, Whh, bhh, self.h, self.h_new, None, None,
-                      None, self.c)
-        _vocab_step(dec, self.h_new, self.logits, self.cache)
+        X = self.X
+        for l in range(self.L):
+            self.ctx.layer = l
+            if self.L > 1:
+                self.ctx.w16 = self.__dict__.setdefault("_w16_layers", {}).setdefault(l, {})
+            dec._input_projection(self.ctx, X, self.mode, 0, R)
+            Whh, bhh = _rw(dec, l)
+            ops.recur_fwd(dec.cell, H, R, self.bs1, self.off1, 0, 1, self.ctx.XP, Whh, bhh, self.h[l], self.h_new[l], None,
+                          None, None, self.c[l])
+            X = self.h_new[l]
+        _vocab_step(dec, self.h_new[self.L - 1], self.logits, self.cache)
         st.step(self.logits, step, self.end_token, device_step=device_step)
         idx = st.src_row.long()
-        torch.index_select(self.h_new, 0, idx, out=self.h)
-        c_new = self.c.index_select(0, idx)
-        self.c.copy_(c_new)
+        for l in range(self.L):
+            torch.index_select(self.h_new[l], 0, idx, out=self.h[l])
+            c_new = self.c[l].index_select(0, idx)
+            self.c[l].copy_(c_new)
         st.step_dev.add_(1)
 
     def step_skinny(self, step, feed_image, device_step):
@@ -210,8 +238,12 @@ class _DecodeSession:
                                 self.X, 0.0, 0)
         src = (self.h, self.c) if self.flip == 0 else (self.hB, self.cB)
         dst = (self.hB, self.cB) if self.flip == 0 else (self.h, self.c)
-        dec._small_step(self.ctx, self.X, self.mode, R, src[0], src[1], st.src_row, dst[0], dst[1])
-        ops.skinny_linear(out.weight, dst[0], self.logits, R, bias=out.bias)
+        X = self.X
+        for l in range(self.L):
+            kw = {"layer": l} if l else {}
+            dec._small_step(self.ctx, X, self.mode, R, src[0][l], src[1][l], st.src_row, dst[0][l], dst[1][l], **kw)
+            X = dst[0][l]
+        ops.skinny_linear(out.weight, dst[0][self.L - 1], self.logits, R, bias=out.bias)
         st.step(self.logits, step, self.end_token, device_step=device_step)
         st.step_dev.add_(1)
         self.flip ^= 1
@@ -312,6 +344,7 @@ def beam_sample(dec, features, start_token, end_token, k, mode, feed_image, sync
     sess.feats.copy_(feats)
     sess.cache.clear()
     sess.ctx.w16 = {}
+    sess.__dict__.pop("_w16_layers", None)
     graph = sess.graph if use_graph else None
     for step in range(1, dec.max_seq_length + 2):
         if graph is not None and step >= 2:

@@ -974,7 +974,7 @@ class DecoderFactoredLSTM(_DecoderBase):
         ops.gemm_bf16(ops.OP_NN, dA1b, Vb, N, Ein, 4 * F, 4 * F, Ep, C=dX, ldc=Ein)
         return dX
 
-    def _small_step(self, ctx, X, mode, R, h_prev, c_prev, src_row, h_out, c_out):
+    def _small_step(self, ctx, X, mode, R, h_prev, c_prev, src_row, h_out, c_out, layer=0):
         """forward_step for R <= ops.SKINNY_MAX_ROWS rows on the matrix-vector kernels (sn_decode.cu): V and S stages as
         skinny linears, the U stage + W_hh + gates + cell update fused (stylenet/model.py:119-153)."""
         if mode not in STYLES:
@@ -985,17 +985,19 @@ class DecoderFactoredLSTM(_DecoderBase):
         if a1 is None or a1.shape[0] < R:
             a1 = ctx.sk_a1 = torch.empty(max(R, ops.SKINNY_MAX_ROWS), 4 * F, dtype=torch.float32, device=X.device)
             a2 = ctx.sk_a2 = torch.empty_like(a1)
-        ops.skinny_linear(self._stack("V_", (4 * F, Ein)), X, a1, R, bias=self._stack("V_", (4 * F,), bias=True))
-        Sc, bS = self._style_stack(mode, (4 * F, F)), self._style_stack(mode, (4 * F,), bias=True)
+        ops.skinny_linear(self._stack("V_", (4 * F, Ein), layer=layer), X, a1, R,
+                          bias=self._stack("V_", (4 * F,), bias=True, layer=layer))
+        Sc = self._style_stack(mode, (4 * F, F), layer=layer)
+        bS = self._style_stack(mode, (4 * F,), bias=True, layer=layer)
         if F % 32 == 0:
             ops.skinny_linear(Sc, a1, a2, R, bias=bS, group_n=F, group_x=F)
         else:                      # odd factored sizes: one call per gate block
             for g in range(4):
                 ops.skinny_linear(Sc[g * F:(g + 1) * F], a1[:, g * F:(g + 1) * F], a2[:, g * F:(g + 1) * F], R,
                                   bias=bS[g * F:(g + 1) * F])
-        Whh, bhh = self._recurrent_weights()
-        ops.decode_cell(self.cell, H, R, self._stack("U_", (4 * H, F)), F, a2, F, self._stack("U_", (4 * H,), bias=True),
-                        Whh, bhh, h_prev, c_prev, src_row, h_out, c_out)
+        Whh, bhh = self._recurrent_weights(layer)
+        ops.decode_cell(self.cell, H, R, self._stack("U_", (4 * H, F), layer=layer), F, a2, F,
+                        self._stack("U_", (4 * H,), bias=True, layer=layer), Whh, bhh, h_prev, c_prev, src_row, h_out, c_out)
 
     # -- reference surface ---------------------------------------------------------------------------
     def forward(self, captions, lengths, features=None, teacher_forcing_ratio=0.8, mode="factual"):

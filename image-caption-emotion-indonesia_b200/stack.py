@@ -146,12 +146,17 @@ class DecoderFactoredLSTMStack(DecoderFactoredLSTM):
 
     # -- decode ----------------------------------------------------------------------------------------
     def forward_step(self, embedded, states, mode):
-        raise NotImplementedError("forward_step of the stack: use forward()/forward_loss(); per-layer states are "
-                                  "internal to the stack")
+        """One step through all layers.  ``states = (h, c)`` with h, c of shape [num_layers, R, H] (the nn.LSTM
+        convention, seq2seq/model.py:46-49); returns ``(h_top [R, H], (h', c'))``.  Layer l > 0 reads layer l-1's new h
+        (oracle/stack.py::stack_forward_step)."""
+        from .decode import single_step
+        return single_step(self, embedded, states, mode)
 
-    def sample(self, *args, **kwargs):
-        raise NotImplementedError("beam search through the stack is not built yet (use forward(teacher_forcing_ratio=0) "
-                                  "for greedy decoding)")
+    def sample(self, features, start_token, end_token, k=5, factual_limit=-1, mode="factual", feed_image=False):
+        """Beam search with the reference's semantics (stylenet/model.py:198-294) through the stack: every live beam
+        carries one (h, c) per layer (oracle/stack.py::stack_sample)."""
+        from .decode import beam_sample
+        return beam_sample(self, features, start_token, end_token, k, mode, feed_image)[0]
 
 
 class MultitaskSchedule:

@@ -51,3 +51,37 @@ def stack_parameters(layers):
     for layer in layers[1:]:
         ps += [p for n, p in layer.named_parameters() if not (n.startswith("B.") or n.startswith("C."))]
     return ps
+
+
+def stack_forward_step(layers, embedded, states, mode):
+    """One step through the stack: ``states = (h, c)`` with shape [num_layers, R, H]; layer l > 0 reads layer l-1's new
+    h (stylenet/model.py:115-155 per layer, seq2seq/model.py:46-49 for the stacking).  Returns (h_top, (h', c'))."""
+    h, c = states
+    hs, cs = [], []
+    x = embedded
+    for l, layer in enumerate(layers):
+        x, (hl, cl) = layer.forward_step(x, (h[l], c[l]), mode)
+        hs.append(hl)
+        cs.append(cl)
+    return x, (torch.stack(hs, 0), torch.stack(cs, 0))
+
+
+def stack_sample(layers, features, start_token, end_token, k=5, mode="factual", feed_image=False):
+    """Beam search of stylenet/model.py:198-294 (``feed_image``: the app/backend variant) through the stack: the beam
+    state is one (h, c) per layer, re-ordered together (oracle.port.beam_search moves every state tensor along dim 0)."""
+    from oracle.port import beam_search
+    l0 = layers[0]
+    L, H = len(layers), l0.hidden_size
+    feat = features.reshape(1, -1)
+
+    def step_fn(prev, state, step):
+        x = feat.expand(prev.numel(), -1) if (feed_image and step == 1) else l0.B(prev)
+        new = []
+        for l, layer in enumerate(layers):
+            x, (hl, cl) = layer.forward_step(x, (state[2 * l], state[2 * l + 1]), mode)
+            new += [hl, cl]
+        return l0.C(x), tuple(new)
+
+    z = torch.zeros(k, H, dtype=l0.C.weight.dtype)
+    return beam_search(step_fn, tuple(z.clone() for _ in range(2 * L)), l0.vocab_size, start_token, end_token, k,
+                       l0.max_seq_length)

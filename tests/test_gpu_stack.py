@@ -184,3 +184,49 @@ def test_early_vocab_adam_equals_single_step():
     # not bit-exact by construction: the embedding / bias gradients are accumulated with fp32 atomics
     worst = max((rel_l2(outs[0][1][n].cpu(), outs[1][1][n].cpu()), n) for n in outs[0][1])
     assert worst[0] < 1e-5, worst
+
+
+def test_stack_forward_step_and_beam_sample_vs_oracle_composition():
+    """forward_step (states [L, R, H]) and sample() / sample_batch() THROUGH the stack against the oracle composition
+    (oracle/stack.py::stack_forward_step / stack_sample over port layers, float64): states <= 1e-5, ids bit-exact."""
+    import icei_b200 as sn
+    from oracle import port
+    from oracle.stack import stack_forward_step, stack_sample
+    E, H, F, V, L = 44, 64, 96, 517, 3
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(5)
+        layers = [port.DecoderFactoredLSTM(E if l == 0 else H, H, F, V, 1, dropout=0.0, max_seq_length=14) for l in range(L)]
+        for l, layer in enumerate(layers):
+            port.lively_weights(layer, end_bias=2.0, seed=5 + l)
+        torch.set_default_dtype(torch.float32)
+        dec = sn.DecoderFactoredLSTMStack(E, H, F, V, L, dropout=0.0, max_seq_length=14)
+        torch.set_default_dtype(torch.float64)          # (the oracle creates its zero states with the default dtype)
+        dec.load_layer_state_dicts([{k: v.float() for k, v in l.state_dict().items()} for l in layers])
+        dec = dec.cuda().eval()
+        g = torch.Generator().manual_seed(1)
+        for R in (5, 40):                      # matrix-vector kernels / the batched path
+            x = torch.randn(R, E, generator=g)
+            h = torch.randn(L, R, H, generator=g) * 0.5
+            c = torch.randn(L, R, H, generator=g) * 0.5
+            with torch.no_grad():
+                top_r, (h_r, c_r) = stack_forward_step(layers, x, (h, c), "sad")
+                top_g, (h_g, c_g) = dec.forward_step(x.float().cuda(), (h.float().cuda(), c.float().cuda()), "sad")
+            assert tuple(h_g.shape) == (L, R, H)
+            assert rel_l2(top_g.cpu(), top_r) < 1e-5 and rel_l2(h_g.cpu(), h_r) < 1e-5 and rel_l2(c_g.cpu(), c_r) < 1e-5
+        feats = torch.randn(20, E, generator=g)
+        lens = set()
+        for k in (1, 3, 5):
+            with torch.no_grad():
+                want = [stack_sample(layers, feats[i:i + 1], 1, 2, k=k, mode="happy", feed_image=True) for i in range(20)]
+            lens |= {w.shape[1] for w in want}
+            got = dec.sample_batch(feats.float().cuda(), 1, 2, k=k, mode="happy", feed_image=True)     # 20 x k rows
+            for i in range(20):
+                assert torch.equal(got[i].cpu(), want[i]), (k, i)
+            for i in (0, 7):                                                                         # <= 16 rows
+                one = dec.sample(feats[i:i + 1].float().cuda(), 1, 2, k=k, mode="happy", feed_image=True)
+                assert torch.equal(one.cpu(), want[i]), (k, i)
+        assert len(lens) >= 2
+    finally:
+        torch.set_default_dtype(old)
