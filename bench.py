@@ -509,8 +509,10 @@ def run_gpu(args):
     line = None
     if rank == 0:
         hbm_peak, tf_peak, peak_src = measured_peaks()
-        if WORKLOAD == "att" or args.no_roofline:
+        if args.no_roofline:
             roof, kernels = None, None
+        elif WORKLOAD == "att":
+            roof, kernels = att_roofline(dev, hbm_peak, peak_src)
         else:
             roof, kernels = kernel_roofline(w.dec, w.cap_d, w.lens, w.feat_d, hbm_peak, peak_src, tf_peak)
         srt = sorted(per_step)
@@ -567,9 +569,51 @@ def run_gpu(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of the same kernels at
-# B=96, T=20, H=512 (profiles/r1_f_ncu_full_k3_bf16_B96_raw.csv); below the algorithmic bytes because the
-# per-step exchange and most of the outputs stay in the 126 MB L2 for the life of the launch
-NCU_TRAFFIC = {"recur_fwd_bf16_kernel": 18.07e6 + 0.12e6, "recur_bwd_bf16_kernel": 26.11e6 + 0.12e6}
+# B=96, T=20, H=512 (profiles/r2_a_ncu_full_k3_cluster_B96_raw.csv; the flag-synchronised kernels:
+# profiles/r1_f_ncu_full_k3_bf16_B96_raw.csv); below the algorithmic bytes because W_hh is read once and most of the
+# outputs are still in the 126 MB L2 when the launch ends
+NCU_TRAFFIC = {"recur_fwd_cl_kernel<512>": 18.04e6 + 0.002e6, "recur_bwd_cl_kernel<512>": 26.10e6 + 0.10e6,
+               "recur_fwd_bf16_kernel": 18.07e6 + 0.12e6, "recur_bwd_bf16_kernel": 26.11e6 + 0.12e6}
+
+
+def att_roofline(dev, hbm_peak, peak_src):
+    """K4 (attention step) timed alone at configs[2] shapes: 96 samples x 49 pixels, A=512, D=2048 (fp32 operands).
+    ALGORITHMIC bytes per launch (SURVEY 8d): fwd reads att1 + features + h-side vectors, writes context + alpha;
+    bwd re-reads both and read-modify-writes d att1."""
+    import torch
+    from icei_b200 import ops
+    nb, P, A, D = 96, 49, 512, 2048
+    f32 = dict(dtype=torch.float32, device=dev)
+    flush = torch.empty(64 * 1024 * 1024, **f32)
+    att1, feat = torch.randn(nb * P, A, **f32), torch.randn(nb, P, D, **f32)
+    att2, gate_pre, wf = torch.randn(nb, A, **f32), torch.randn(nb, D, **f32), torch.randn(A, **f32)
+    alpha, ctx = torch.empty(nb, P, **f32), torch.empty(nb, D, **f32)
+    dctx, datt2, dgate = torch.randn(nb, D, **f32), torch.empty(nb, A, **f32), torch.empty(nb, D, **f32)
+    datt1, dwf = torch.zeros(nb * P, A, **f32), torch.zeros(A, **f32)
+
+    def timeit(fn, reps=5):
+        fn()
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps
+    t_f = timeit(lambda: ops.att_step_fwd(att1, att2, feat, wf, 0.0, gate_pre, nb, P, A, D, alpha, P, ctx, D))
+    t_b = timeit(lambda: ops.att_step_bwd(att1, att2, feat, wf, 0.0, gate_pre, alpha, P, dctx, D, None, 0, nb, P, A, D,
+                                          datt2, dgate, datt1, dwf, None))
+    by_f = nb * (P * (A + D) * 4 + (A + D) * 4 + (D + P) * 4)
+    by_b = nb * (P * (A + D) * 4 + P * A * 8 + (A + 3 * D + 2 * P) * 4)
+    kernels = {"att_step_fwd_cl_kernel": {"ms": t_f, "alg_bytes": by_f, "gbs": by_f / t_f / 1e6, "frac_of_hbm_peak": by_f / t_f / 1e6 / hbm_peak},
+               "att_step_bwd_cl_kernel": {"ms": t_b, "alg_bytes": by_b, "gbs": by_b / t_b / 1e6, "frac_of_hbm_peak": by_b / t_b / 1e6 / hbm_peak}}
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+            "frac": kernels[dom]["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "note": "timed alone with an L2 flush in front (the 38.5 MB fp32 feature map then comes from HBM); inside the "
+                    "step the map stays in the 126 MB L2 across the 19 time steps"}
+    return roof, kernels
 
 
 def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src, tf_peak=(1638.2, 1368.6)):
@@ -644,7 +688,8 @@ def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src, tf_peak=(1638.
             # XP + c in/out + gates + h fp32 + h bf16 x2 ; W_hh bf16 once
             by_f = N * H * (16 + 8 + 16 + 4 + 4) + 4 * H * H * 2
             by_b = N * H * (16 + 16 + 8 + 4 + 8 + 8) + 4 * H * H * 2
-            names = ("recur_fwd_bf16_kernel", "recur_bwd_bf16_kernel")
+            names = ("recur_fwd_cl_kernel<%d>" % H, "recur_bwd_cl_kernel<%d>" % H) if ops.recur_cluster_ok(H, B) \
+                else ("recur_fwd_bf16_kernel", "recur_bwd_bf16_kernel")
         else:
             Hprev = torch.empty(N, H, **f32)
 
@@ -691,8 +736,9 @@ def kernel_roofline(dec, cap_d, lens, feat_d, hbm_peak, peak_src, tf_peak=(1638.
     bigdom = max(big, key=lambda k: big[k]["ms"])
     roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
             "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC.get(dom) if len(lens) == 96 else None,
-            "traffic_source": "ncu --set full, profiles/r1_f_ncu_full_k3_bf16_B96_raw.csv", "peak_source": peak_src,
-            "note": "latency-bound at B=96: T serial steps, each with an inter-SM exchange through L2 (DESIGN.md 4). "
+            "traffic_source": "ncu --set full, profiles/r2_a_ncu_full_k3_cluster_B96_raw.csv", "peak_source": peak_src,
+            "note": "latency-bound at B=96: T serial steps, each with an exchange of h_t between the 16 CTAs of a cluster "
+                    "through distributed shared memory (DESIGN.md 4). "
                     "At B=4096/GPU the recurrence runs as per-step tcgen05 GEMMs with the cell in the epilogue "
                     "(throughput regime): %.0f GB/s = %.2f of peak" % (big[bigdom]["gbs"], big[bigdom]["gbs"] / hbm_peak),
             "large_batch": {"B": 4096, "kernel": bigdom, "achieved": big[bigdom]["gbs"],

@@ -221,7 +221,7 @@ class _AttBase(_DecoderBase):
             self._lin(c, hprev, hprev_b, self.f_beta.weight, "Wbeta", self.f_beta.bias, c.gate_pre, n, r0_out=r0,
                       x_off_rows=hoff)
             ops.att_step_fwd(c.att1, c.att2[r0:], feats, wfull, 0.0, c.gate_pre[r0:], n, P, A, D,
-                             c.alphas[:, t], Tmax * P, c.CTX[r0:], D)
+                             c.alphas[:, t], Tmax * P, c.CTX[r0:], D, feat_b16=c.featsb)
             if c.tc:
                 ops.cast_bf16(c.CTX, n, D, D, c.CTXb, D, D, src_off=r0 * D, dst_off=r0 * D)
             self._proj_step(c, r0, n)
@@ -286,7 +286,7 @@ class _AttBase(_DecoderBase):
             self._proj_step_bwd(c, dZ, r0, n)        # -> c.dCTX rows
             ops.att_step_bwd(c.att1, c.att2[r0:], c.feats, wfull, 0.0, c.gate_pre[r0:], c.alphas[:, t], Tmax * P,
                              c.dCTX[r0:], D, dAl[:, t] if dAl is not None else None, Tmax * P, n, P, A, D,
-                             datt2[r0:], dgate[r0:], datt1, gwf, dfeat)
+                             datt2[r0:], dgate[r0:], datt1, gwf, dfeat, feat_b16=c.featsb)
             # into h_{t-1}: through decoder_att and f_beta
             if c.tc:
                 ops.cast_bf16(datt2, n, A, A, datt2b, A, A, src_off=r0 * A, dst_off=r0 * A)

@@ -273,14 +273,32 @@ def mean_pixels(feat, B, P, D, out):
     check(lib().sn_mean_pixels(_ptr(_req(feat)), B, P, D, _ptr(out), _stream()), "sn_mean_pixels")
 
 
-def att_step_fwd(att1, att2, feat, wfull, bfull, gate_pre, nb, P, A, D, alpha, ld_alpha, ctx, ldc):
+def _att_b16_ok(feat_b16, att1, A, D):
+    return (feat_b16 is not None and D == 2048 and A % 4 == 0 and feat_b16.data_ptr() % 16 == 0
+            and att1.data_ptr() % 16 == 0)
+
+
+def att_step_fwd(att1, att2, feat, wfull, bfull, gate_pre, nb, P, A, D, alpha, ld_alpha, ctx, ldc, feat_b16=None):
+    """``feat_b16``: bf16 copy of the feature map (bf16 mode) -> the 16-byte-load kernel reading half the bytes."""
+    if _att_b16_ok(feat_b16, att1, A, D) and ldc % 2 == 0:
+        check(lib().sn_att_step_fwd_b16(_ptr(_req(att1)), _ptr(_req(att2)), _ptr(_req(feat_b16, torch.bfloat16)),
+                                        _ptr(_req(wfull)), float(bfull), _ptr(_req(gate_pre)), nb, P, A, D, _ptr(alpha),
+                                        ld_alpha, _ptr(ctx), ldc, _stream()), "sn_att_step_fwd_b16")
+        return
     check(lib().sn_att_step_fwd(_ptr(_req(att1)), _ptr(_req(att2)), _ptr(_req(feat)), _ptr(_req(wfull)),
                                 float(bfull), _ptr(_req(gate_pre)), nb, P, A, D, _ptr(alpha), ld_alpha,
                                 _ptr(ctx), ldc, _stream()), "sn_att_step_fwd")
 
 
 def att_step_bwd(att1, att2, feat, wfull, bfull, gate_pre, alpha, ld_alpha, dctx, ldc, dalpha_extra, ld_da,
-                 nb, P, A, D, datt2, dgate_pre, datt1, dwfull, dfeat):
+                 nb, P, A, D, datt2, dgate_pre, datt1, dwfull, dfeat, feat_b16=None):
+    if dfeat is None and _att_b16_ok(feat_b16, att1, A, D) and datt1.data_ptr() % 16 == 0:
+        check(lib().sn_att_step_bwd_b16(_ptr(_req(att1)), _ptr(_req(att2)), _ptr(_req(feat_b16, torch.bfloat16)),
+                                        _ptr(_req(wfull)), _ptr(_req(gate_pre)), _ptr(alpha), ld_alpha, _ptr(_req(dctx)),
+                                        ldc, _ptr(dalpha_extra), ld_da, nb, P, A, D, _ptr(datt2), _ptr(dgate_pre),
+                                        _ptr(datt1), _ptr(dwfull), _stream()), "sn_att_step_bwd_b16")
+        LAUNCHES[0] += 1
+        return
     check(lib().sn_att_step_bwd(_ptr(_req(att1)), _ptr(_req(att2)), _ptr(_req(feat)), _ptr(_req(wfull)),
                                 float(bfull), _ptr(_req(gate_pre)), _ptr(alpha), ld_alpha, _ptr(_req(dctx)), ldc,
                                 _ptr(dalpha_extra), ld_da, nb, P, A, D, _ptr(datt2), _ptr(dgate_pre),

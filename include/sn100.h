@@ -342,6 +342,18 @@ int32_t sn_beam_step(const float* logits, int64_t ld, int64_t V, int32_t n_img, 
                      int32_t* n_done, int32_t* out_seq, int32_t* out_len, int32_t* n_unfinished,
                      const int32_t* step_dev, void* stream);
 
+/* K4 with a bf16 feature map (bf16 mode): same contract as sn_att_step_fwd / _bwd, `feat_bf16` [B,P,D] bf16 (half the
+ * bytes of the largest tensor of the step, read with 16-byte loads); att1 / att2 / the relu pre-activation stay fp32.
+ * No d feat output.  Needs D == 2048, A % 4 == 0, 16-byte aligned rows; returns -2 when not applicable. */
+int32_t sn_att_step_fwd_b16(const float* att1, const float* att2, const void* feat_bf16, const float* wfull,
+                            float bfull, const float* gate_pre, int64_t nb, int64_t P, int64_t A, int64_t D,
+                            float* alpha, int64_t ld_alpha, float* ctx, int64_t ldc, void* stream);
+int32_t sn_att_step_bwd_b16(const float* att1, const float* att2, const void* feat_bf16, const float* wfull,
+                            const float* gate_pre, const float* alpha, int64_t ld_alpha, const float* dctx,
+                            int64_t ldc, const float* dalpha_extra, int64_t ld_da, int64_t nb, int64_t P,
+                            int64_t A, int64_t D, float* datt2, float* dgate_pre, float* datt1,
+                            float* dwfull, void* stream);
+
 /* sn_beam_step for FEW images: the same step spread over nch x more CTAs (per-chunk log-sum-exp partials, per-chunk
  * top-k of the final scores, per-image merge + bookkeeping).  Same arguments as sn_beam_step plus the chunk count
  * (1..32) and a work space of sn_beam_split_ws_floats() floats.  Same selection rule (score descending, ties -> lower
