@@ -62,11 +62,11 @@ SIGNATURES = {
     "sn_att_step_bwd_b16": (_I32, [_P, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P]),
     "sn_mean_pixels": (_I32, [_P, _I64, _I64, _I64, _P, _P]),
     "sn_beam_split_ws_floats": (_I64, [_I32, _I32, _I32]),
-    "sn_beam_step_split": (_I32, [_P, _I64, _I64, _I32, _I32, _I32, _I32, _I32] + [_P] * 14 + [_I32, _P, _P]),
+    "sn_beam_step_split": (_I32, [_P, _I64, _I64, _I32, _I32, _I32, _I32, _I32] + [_P] * 14 + [_I32, _P, _I32, _P]),
     "sn_split_limbs_cols": (_I32, [_P, _I64, _I64, _I64, _I64, _P, _I64, _I32, _P]),
     "sn_split_limbs_rows": (_I32, [_P, _I64, _I64, _I64, _I64, _P, _I64, _I64, _I32, _P]),
     "sn_skinny_max_rows": (_I32, []),
-    "sn_skinny_linear": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _I64, _P]),
+    "sn_skinny_linear": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I64, _P, _P, _I64, _P, _P]),
     "sn_decode_cell": (_I32, [_I32, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sn_pool_nhwc_fwd": (_I32, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P]),
     "sn_pool_nhwc_bwd": (_I32, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P]),

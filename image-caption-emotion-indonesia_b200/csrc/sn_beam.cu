@@ -189,6 +189,7 @@ struct SplitArgs {
   float* cand_v;    // [n_img][nch][KMAX]
   int* cand_i;
   int nch;
+  int* counter;     // optional: blocks-done counter; the last block of the finish kernel bumps *step_dev (saves a launch)
 };
 
 __device__ __forceinline__ void chunk_range(int V, int nch, int ch, int& c0, int& c1) {
@@ -317,6 +318,15 @@ __global__ void __launch_bounds__(NTS) beam_topk_partial_kernel(SplitArgs s) {
   }
 }
 
+__device__ __forceinline__ void finish_count(SplitArgs& s) {
+  if (s.counter == nullptr) return;
+  __threadfence();
+  if (atomicAdd(s.counter, 1) == (int)gridDim.x - 1) {       // every block has read the step number: advance it
+    *s.counter = 0;
+    *const_cast<int*>(s.b.step_dev) += 1;
+  }
+}
+
 __global__ void __launch_bounds__(32) beam_finish_kernel(SplitArgs s) {
   BeamArgs& a = s.b;
   __shared__ float w_val[KMAX];
@@ -329,6 +339,7 @@ __global__ void __launch_bounds__(32) beam_finish_kernel(SplitArgs s) {
   const int row0 = img * a.kmax;
   if (k == 0) {
     if (lane < a.kmax) a.src_row[row0 + lane] = row0 + lane;
+    if (lane == 0) finish_count(s);
     return;
   }
   const int ncand = s.nch * KMAX;                 // <= 32 * KMAX
@@ -358,6 +369,7 @@ __global__ void __launch_bounds__(32) beam_finish_kernel(SplitArgs s) {
   }
   if (lane != 0) return;
   beam_bookkeep(a, img, k, w_val, w_idx);
+  finish_count(s);
 }
 
 }  // namespace
@@ -385,7 +397,7 @@ extern "C" int32_t sn_beam_step(const float* logits, int64_t ld, int64_t V, int3
 
 extern "C" int64_t sn_beam_split_ws_floats(int32_t n_img, int32_t kmax, int32_t nch) {
   // part [rows][nch][2] + cand_v [n_img][nch][KMAX] + cand_i (int32, same count)
-  return (int64_t)n_img * kmax * nch * 2 + 2 * (int64_t)n_img * nch * KMAX;
+  return (int64_t)n_img * kmax * nch * 2 + 2 * (int64_t)n_img * nch * KMAX + 4;      // + the blocks-done counter
 }
 
 extern "C" int32_t sn_beam_step_split(const float* logits, int64_t ld, int64_t V, int32_t n_img, int32_t kmax, int32_t step,
@@ -393,7 +405,7 @@ extern "C" int32_t sn_beam_step_split(const float* logits, int64_t ld, int64_t V
                                       int32_t* prev_word, int32_t* src_row, int32_t* cur_buf, int32_t* seqs,
                                       int32_t* done_seq, int32_t* done_len, float* done_score, int32_t* n_done,
                                       int32_t* out_seq, int32_t* out_len, int32_t* n_unfinished, const int32_t* step_dev,
-                                      int32_t nch, float* ws, void* stream) {
+                                      int32_t nch, float* ws, int32_t advance_step, void* stream) {
   SN_REQUIRE(kmax >= 1 && kmax <= KMAX, "sn_beam_step_split: beam width %d not in [1,%d]", kmax, KMAX);
   SN_REQUIRE(n_img >= 0 && V > 0 && step >= 1 && ws, "sn_beam_step_split: bad argument");
   SN_REQUIRE(nch >= 1 && nch <= 32, "sn_beam_step_split: 1..32 chunks");
@@ -411,6 +423,9 @@ extern "C" int32_t sn_beam_step_split(const float* logits, int64_t ld, int64_t V
   s.part = ws;
   s.cand_v = ws + (int64_t)n_img * kmax * nch * 2;
   s.cand_i = reinterpret_cast<int*>(s.cand_v + (int64_t)n_img * nch * KMAX);
+  // advance_step: the finish kernel adds 1 to *step_dev once every image is done with this step (the counter word must
+  // be zero on the first call: the caller zero-fills the work space once)
+  s.counter = (advance_step && step_dev) ? s.cand_i + (int64_t)n_img * nch * KMAX : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   beam_lse_partial_kernel<<<dim3((unsigned)nch, (unsigned)(n_img * kmax)), NTS, 0, st>>>(s);
   beam_topk_partial_kernel<<<dim3((unsigned)nch, (unsigned)n_img), NTS, 0, st>>>(s);

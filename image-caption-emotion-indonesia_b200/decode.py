@@ -126,7 +126,9 @@ class BeamState:
 
     SPLIT_MAX_IMAGES = 8          # up to here one CTA per image leaves the GPU idle: spread each image over chunks
 
-    def step(self, logits, step, end_token, device_step=False):
+    def step(self, logits, step, end_token, device_step=False, advance=False):
+        """One beam step.  ``advance``: also add 1 to the device-side step counter (returns True when the kernel did it,
+        False when the caller has to)."""
         p = ops._ptr
         V = logits.shape[1]
         if self.n_img <= self.SPLIT_MAX_IMAGES and V >= 256:
@@ -134,15 +136,15 @@ class BeamState:
             ws = self.__dict__.get("_split_ws")
             if ws is None:
                 n = ops.lib().sn_beam_split_ws_floats(self.n_img, self.kmax, nch)
-                ws = self._split_ws = torch.empty(n, dtype=torch.float32, device=logits.device)
+                ws = self._split_ws = torch.zeros(n, dtype=torch.float32, device=logits.device)
             check(ops.lib().sn_beam_step_split(
                 p(logits), logits.stride(0), V, self.n_img, self.kmax, step, self.max_len, end_token,
                 p(self.k_live), p(self.run_score), p(self.prev_word), p(self.src_row), p(self.cur_buf), p(self.seqs),
                 p(self.done_seq), p(self.done_len), p(self.done_score), p(self.n_done), p(self.out_seq),
                 p(self.out_len), p(self.n_unfinished), p(self.step_dev) if device_step else None, nch, p(ws),
-                ops._stream()), "sn_beam_step_split")
+                1 if (advance and device_step) else 0, ops._stream()), "sn_beam_step_split")
             ops.LAUNCHES[0] += 2
-            return
+            return bool(advance and device_step)
         check(ops.lib().sn_beam_step(
             p(logits), logits.stride(0), logits.shape[1], self.n_img, self.kmax, step, self.max_len, end_token,
             p(self.k_live), p(self.run_score), p(self.prev_word), p(self.src_row), p(self.cur_buf), p(self.seqs),
@@ -230,22 +232,27 @@ class _DecodeSession:
         dec, st = self._dec(), self.st
         emb, out = dec._emb(), dec._out()
         R = st.R
+        fold = hasattr(dec, "factored_size")          # factored decoders: the lookup is folded into the V stage
         if feed_image and step == 1:
-            ops.gather_pack_fwd(self.dummy_cap, emb.weight, self.feats, True, self.row_img, self.row_zero, None, R,
-                                self.X, 0.0, 0)
+            X, rows = self.feats, self.row_img             # row r reads the feature row of its image
         else:
-            ops.gather_pack_fwd(self.dummy_cap, emb.weight, None, False, self.row_img, self.row_zero, st.prev_word, R,
-                                self.X, 0.0, 0)
+            X, rows = emb.weight, st.prev_word             # row r reads the embedding of its previous word
+        if not fold:
+            ops.gather_pack_fwd(self.dummy_cap, emb.weight, self.feats if (feed_image and step == 1) else None,
+                                feed_image and step == 1, self.row_img, self.row_zero,
+                                None if (feed_image and step == 1) else st.prev_word, R, self.X, 0.0, 0)
+            X, rows = self.X, None
         src = (self.h, self.c) if self.flip == 0 else (self.hB, self.cB)
         dst = (self.hB, self.cB) if self.flip == 0 else (self.h, self.c)
-        X = self.X
         for l in range(self.L):
             kw = {"layer": l} if l else {}
+            if l == 0 and rows is not None:
+                kw["x_rows"] = rows
             dec._small_step(self.ctx, X, self.mode, R, src[0][l], src[1][l], st.src_row, dst[0][l], dst[1][l], **kw)
             X = dst[0][l]
         ops.skinny_linear(out.weight, dst[0][self.L - 1], self.logits, R, bias=out.bias)
-        st.step(self.logits, step, self.end_token, device_step=device_step)
-        st.step_dev.add_(1)
+        if not st.step(self.logits, step, self.end_token, device_step=device_step, advance=True):
+            st.step_dev.add_(1)
         self.flip ^= 1
 
     STEPS_PER_GRAPH = 4

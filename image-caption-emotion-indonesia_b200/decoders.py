@@ -974,7 +974,7 @@ class DecoderFactoredLSTM(_DecoderBase):
         ops.gemm_bf16(ops.OP_NN, dA1b, Vb, N, Ein, 4 * F, 4 * F, Ep, C=dX, ldc=Ein)
         return dX
 
-    def _small_step(self, ctx, X, mode, R, h_prev, c_prev, src_row, h_out, c_out, layer=0):
+    def _small_step(self, ctx, X, mode, R, h_prev, c_prev, src_row, h_out, c_out, layer=0, x_rows=None):
         """forward_step for R <= ops.SKINNY_MAX_ROWS rows on the matrix-vector kernels (sn_decode.cu): V and S stages as
         skinny linears, the U stage + W_hh + gates + cell update fused (stylenet/model.py:119-153)."""
         if mode not in STYLES:
@@ -986,7 +986,7 @@ class DecoderFactoredLSTM(_DecoderBase):
             a1 = ctx.sk_a1 = torch.empty(max(R, ops.SKINNY_MAX_ROWS), 4 * F, dtype=torch.float32, device=X.device)
             a2 = ctx.sk_a2 = torch.empty_like(a1)
         ops.skinny_linear(self._stack("V_", (4 * F, Ein), layer=layer), X, a1, R,
-                          bias=self._stack("V_", (4 * F,), bias=True, layer=layer))
+                          bias=self._stack("V_", (4 * F,), bias=True, layer=layer), x_rows=x_rows)
         Sc = self._style_stack(mode, (4 * F, F), layer=layer)
         bS = self._style_stack(mode, (4 * F,), bias=True, layer=layer)
         if F % 32 == 0:

@@ -619,12 +619,13 @@ def bn1d_bwd(x, dy, gamma, save_mean, save_invstd, training, dx, dgamma, dbeta):
 SKINNY_MAX_ROWS = 16
 
 
-def skinny_linear(W, X, out, R, bias=None, group_n=0, group_x=0, K=None):
-    """out[:R] = X[:R] W^T + bias for R <= 16 rows; W [N, K] fp32 (row pitch W.stride(0)); grouped form see sn100.h."""
+def skinny_linear(W, X, out, R, bias=None, group_n=0, group_x=0, K=None, x_rows=None):
+    """out[:R] = X[:R] W^T + bias for R <= 16 rows; W [N, K] fp32 (row pitch W.stride(0)); grouped form see sn100.h.
+    ``x_rows`` (int32 [R]): gather the input rows, X[x_rows[r]] (embedding lookup folded into the stage)."""
     N = W.shape[0]
     K = K if K is not None else W.shape[1]
     check(lib().sn_skinny_linear(_ptr(_req(W)), W.stride(0), N, K, _ptr(_req(X)), X.stride(0), R, group_n, group_x,
-                                 _ptr(bias), _ptr(_req(out)), out.stride(0), _stream()), "sn_skinny_linear")
+                                 _ptr(bias), _ptr(_req(out)), out.stride(0), _ptr(x_rows), _stream()), "sn_skinny_linear")
     return out
 
 

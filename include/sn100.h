@@ -357,14 +357,16 @@ int32_t sn_att_step_bwd_b16(const float* att1, const float* att2, const void* fe
 /* sn_beam_step for FEW images: the same step spread over nch x more CTAs (per-chunk log-sum-exp partials, per-chunk
  * top-k of the final scores, per-image merge + bookkeeping).  Same arguments as sn_beam_step plus the chunk count
  * (1..32) and a work space of sn_beam_split_ws_floats() floats.  Same selection rule (score descending, ties -> lower
- * flat index); the log-sum-exp is combined from chunk partials, so scores may differ from sn_beam_step in the last bit. */
+ * flat index); the log-sum-exp is combined from chunk partials, so scores may differ from sn_beam_step in the last bit.
+ * advance_step != 0 (needs step_dev): the last block adds 1 to *step_dev; the work space must be zero-filled once. */
 int64_t sn_beam_split_ws_floats(int32_t n_img, int32_t kmax, int32_t nch);
 int32_t sn_beam_step_split(const float* logits, int64_t ld, int64_t V, int32_t n_img, int32_t kmax,
                            int32_t step, int32_t max_len, int32_t end_token, int32_t* k_live,
                            float* run_score, int32_t* prev_word, int32_t* src_row, int32_t* cur_buf,
                            int32_t* seqs, int32_t* done_seq, int32_t* done_len, float* done_score,
                            int32_t* n_done, int32_t* out_seq, int32_t* out_len, int32_t* n_unfinished,
-                           const int32_t* step_dev, int32_t nch, float* ws, void* stream);
+                           const int32_t* step_dev, int32_t nch, float* ws, int32_t advance_step,
+                           void* stream);
 
 /* ---- SN_PREC_BF16X6: limb expansion of fp32 GEMM operands (see sn_split.cu) ------------------------------------
  * x = x0 + x1 + x2 (bf16 limbs); left operands get the slots [x1 x0 x2 x0 x1 x0], right operands [x1 x2 x0 x1 x0 x0]
@@ -383,6 +385,8 @@ int32_t sn_split_limbs_rows(const float* src, int64_t G, int64_t K, int64_t C, i
  * (model.py:234) when rows <= sn_skinny_max_rows(): one pass over the fp32 weights, rows held in shared memory.
  * sn_skinny_linear: out[r,n] = bias[n] + W[n,:K] . X[r, xoff(n) : xoff(n)+K], xoff(n) = (n / group_n) * group_x
  *   (group_n = 0: no groups; the four S_g / U_g blocks are groups of F resp. H features reading column block g).
+ *   x_rows (may be NULL): row r of the input is X[x_rows[r]] -- the embedding lookup of the previous words
+ *   (stylenet/model.py:231) folded into the first stage.
  * sn_decode_cell: z_g = Wx[g*H+u,:Kx] . x_g[r] + bx + Wh[g*H+u,:] . h_prev[src_row[r]] + bh, gates, c', h' for
  *   every unit u and row r; x_g = X[r, g*group_x : +Kx] (group_x = 0: the same x for all gates, LSTMCell).
  *   src_row (may be NULL) re-orders the incoming state per row (beam bookkeeping, model.py:275-279): h_out / c_out
@@ -390,7 +394,7 @@ int32_t sn_split_limbs_rows(const float* src, int64_t G, int64_t K, int64_t C, i
 int32_t sn_skinny_max_rows(void);
 int32_t sn_skinny_linear(const float* W, int64_t ldw, int64_t N, int64_t K, const float* X, int64_t ldx,
                          int64_t R, int64_t group_n, int64_t group_x, const float* bias, float* out,
-                         int64_t ldo, void* stream);
+                         int64_t ldo, const int32_t* x_rows, void* stream);
 int32_t sn_decode_cell(int32_t cell, int64_t H, int64_t R, const float* Wx, int64_t ldwx, int64_t Kx,
                        const float* X, int64_t ldx, int64_t group_x, const float* bx, const float* Wh,
                        const float* bh, const float* h_prev, const float* c_prev, const int32_t* src_row,
