@@ -3,6 +3,8 @@
 captions/s swept over images per call, on one GPU, next to the CPU oracle port on the host cores.
 
     python bench_decode.py [--precision fp32|bf16] [--max-images 1024] [--cpu-images 8]
+    torchrun --nproc-per-node N bench_decode.py ...     # N replicas (decode shards images, no collective): every rank
+                                                        # decodes its own `images_per_call`, rank 0 prints the SUM
 
 Greedy = the reference's validation path ``forward(teacher_forcing_ratio=0)`` under no_grad
 (stylenet/train_multitask.py:296-299).  Beam = ``sample(k=5)`` semantics (stylenet/model.py:198-294 with the
@@ -37,13 +39,19 @@ def main():
     import torch
     import icei_b200 as sn
     from icei_b200.decode import beam_sample
-    dev = torch.device("cuda", 0)
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.5)
     sharpen(dec)
     sd = {k: v.clone() for k, v in dec.state_dict().items()}
     dec = dec.to(dev).eval().set_precision(args.precision)
-    g = torch.Generator().manual_seed(1)
+    g = torch.Generator().manual_seed(1 + rank)
     out_rows = []
 
     def timed(fn, reps):
@@ -81,6 +89,20 @@ def main():
                              "k": k, "images_per_call": n, "value": n / dt, "unit": "captions/s",
                              "mean_caption_len": sum(lens) / len(lens), "ms_per_call": dt * 1e3})
         n *= 4
+    if world > 1:
+        # replicas only: aggregate = sum over ranks of each rank's own throughput on its own images
+        import torch.distributed as dist
+        vals = torch.tensor([r["value"] for r in out_rows], dtype=torch.float64, device=dev)
+        lo = vals.clone()
+        dist.all_reduce(vals, op=dist.ReduceOp.SUM)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        for r, v, m in zip(out_rows, vals.tolist(), lo.tolist()):
+            r.update(value=v, n_gpus=world, slowest_rank_value=m, images_per_call_total=r.get("images_per_call", r.get("batch")) * world)
+        if rank == 0:
+            for r in out_rows:
+                print(json.dumps(r), flush=True)
+        dist.destroy_process_group()
+        return
     # ---- CPU oracle port on the host cores -----------------------------------------------------------
     from oracle import port
     torch.set_num_threads(os.cpu_count() or 1)
