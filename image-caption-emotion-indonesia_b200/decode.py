@@ -27,7 +27,7 @@ class _StepCtx:
 
 def _n_layers(dec):
     """Stacked decoders (stack.DecoderFactoredLSTMStack) keep one (h, c) per layer; the reference models have one."""
-    return int(dec.num_layers) if hasattr(dec, "_upper_layers_fwd") and type(dec).__name__.endswith("Stack") else 1
+    return int(dec.num_layers) if getattr(dec, "_layered", False) else 1
 
 
 def _rw(dec, layer):

@@ -27,6 +27,8 @@ from .decoders import DecoderFactoredLSTM, GATES, STYLES, style_attr, _Ctx, _ref
 class DecoderFactoredLSTMStack(DecoderFactoredLSTM):
     """``num_layers`` stacked FactoredLSTM cells behind the ``DecoderFactoredLSTM`` surface."""
 
+    _layered = True          # decode keeps one (h, c) per layer
+
     def __init__(self, embed_size, hidden_size, factored_size, vocab_size, num_layers, feature_size=2048,
                  bias=True, dropout=0.22, max_seq_length=40):
         super().__init__(embed_size, hidden_size, factored_size, vocab_size, num_layers, feature_size, bias, dropout,

@@ -24,6 +24,7 @@ _FILES = {
     "app": "app/backend/model.py",
     "app_att": "app/backend/model_att.py",
     "stylenet_utils": "stylenet/utils.py",
+    "seq2seq": "seq2seq/model.py",
 }
 _cache = {}
 
