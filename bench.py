@@ -155,7 +155,7 @@ def run_reference(args):
                 "(build container), else oracle/port.py (its restatement, pinned at 1e-10); train step = "
                 "train_multitask.py:377-389.  The reference is pure Python/torch: nothing to compile into oracle/_ref",
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
 
 
 def synthetic_batch(B, Tlen, vocab, embed, seed):
@@ -172,21 +172,72 @@ def synthetic_batch(B, Tlen, vocab, embed, seed):
 # ------------------------------------------------------------------------------------------------
 # clocks sampler
 # ------------------------------------------------------------------------------------------------
+_JSON_OUT = None
+
+
 class ClockSampler:
+    """SM clock / throttle-reason samples taken DURING the timed region.  NVML in a thread (10 ms period; a sample costs
+    ~0.1 ms and no process start-up, so a 30 ms timed region at N=8 still gets samples); `nvidia-smi -lms` as the fallback
+    when pynvml is missing.  The device is looked up by UUID so CUDA_VISIBLE_DEVICES remapping cannot pick another GPU."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []          # nvidia-smi text rows
+        self.samples = []       # (sm, max_sm, power_w, reason_mask) from NVML
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
+        self.source = None
+
+    def _nvml_open(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.gpu).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        return pynvml, h
+
+    def _nvml_loop(self):
+        nv, h = self.nvml
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = None
+                self.samples.append((float(sm), float(mx), pw, int(mask)))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        try:
+            self.nvml = self._nvml_open()
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                  "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -196,7 +247,25 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def count(self):
+        return len(self.samples) if self.nvml is not None else len(self.rows)
+
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            nv = self.nvml[0]
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            sm = [x[0] for x in self.samples]
+            mx = [x[1] for x in self.samples]
+            power = [x[2] for x in self.samples if x[2] is not None]
+            reasons = sorted(k for k, b in bits.items() if any(x[3] & b for x in self.samples))
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                    "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": reasons,
+                    "source": "nvml, 10 ms period, during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -206,7 +275,6 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
@@ -215,11 +283,12 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
             except ValueError:
                 continue
-            for nm, val in zip(names, f[5:9]):
+            for nm, val in zip(self.NAMES, f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi -lms 50, during the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -356,40 +425,53 @@ def dp_parity_check(dev, rank, world):
     import torch.distributed as dist
     import icei_b200 as sn
     from oracle import port     # synthetic_batch only (inputs); nothing of the oracle is executed on the path
-    Vp, Ep, Hp, Fp = 1000, 44, 128, 72
-    cap, lens, feats = port.synthetic_batch(12 * world, 9, Vp, E=Ep, ragged=True, seed=5)
-    n_global = sum(lens)
+    from icei_b200 import dp as _dp
 
-    def make():
-        torch.manual_seed(0)
-        d = sn.DecoderFactoredLSTM(Ep, Hp, Fp, Vp, 1, dropout=0.0).to(dev).train()
-        return d, sn.DataParallelTrainer(d, sn.FusedClampAdam(d, lr=5e-4), comm=None)
-    one, _ = make()
-    opt1 = sn.FusedClampAdam(one, lr=5e-4)
-    for _ in range(3):
-        one.zero_grad()
-        for p in one.parameters():
-            p.grad = None
-        one.forward_loss(cap.to(dev), lens, feats.to(dev), mode="happy")
-        opt1.step()
-    dec, tr = make()
-    idx, my_lens = sn.shard_lengths(lens, world, rank)
-    for _ in range(3):
-        tr.step(cap[idx].to(dev), my_lens, feats[idx].to(dev), n_global=n_global, mode="happy")
-    torch.cuda.synchronize()
-    worst = torch.zeros(1, device=dev)
-    same = torch.ones(1, device=dev)
-    for (n, p), (_, q) in zip(dec.named_parameters(), one.named_parameters()):
-        worst = torch.maximum(worst, ((p - q).norm() / q.norm().clamp_min(1e-30)).reshape(1))
-        r0 = p.detach().clone()
-        dist.broadcast(r0, 0)
-        if not torch.equal(r0, p.detach()):
-            same.zero_()
-    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-    dist.all_reduce(same, op=dist.ReduceOp.MIN)
-    return {"max_rel_param_diff_vs_1gpu": float(worst.item()), "ranks_bit_identical": bool(same.item() == 1.0),
-            "steps": 3, "global_batch": 12 * world, "comm": tr.comm,
-            "what": "fp32 mode, ragged global batch sharded over the ranks, 3 steps vs the same steps on 1 GPU"}
+    def run(precision, Vp, Ep, Hp, Fp):
+        cap, lens, feats = port.synthetic_batch(12 * world, 9, Vp, E=Ep, ragged=True, seed=5)
+        n_global = sum(lens)
+
+        def make():
+            torch.manual_seed(0)
+            d = sn.DecoderFactoredLSTM(Ep, Hp, Fp, Vp, 1, dropout=0.0).to(dev).train().set_precision(precision)
+            return d, sn.DataParallelTrainer(d, sn.FusedClampAdam(d, lr=5e-4), comm=None)
+        one, _ = make()
+        opt1 = sn.FusedClampAdam(one, lr=5e-4)
+        for _ in range(3):
+            one.zero_grad()
+            for p in one.parameters():
+                p.grad = None
+            one.forward_loss(cap.to(dev), lens, feats.to(dev), mode="happy")
+            opt1.step()
+        dec, tr = make()
+        idx, my_lens = sn.shard_lengths(lens, world, rank)
+        for _ in range(3):
+            tr.step(cap[idx].to(dev), my_lens, feats[idx].to(dev), n_global=n_global, mode="happy")
+        torch.cuda.synchronize()
+        worst = torch.zeros(1, device=dev)
+        same = torch.ones(1, device=dev)
+        for (n, p), (_, q) in zip(dec.named_parameters(), one.named_parameters()):
+            worst = torch.maximum(worst, ((p - q).norm() / q.norm().clamp_min(1e-30)).reshape(1))
+            r0 = p.detach().clone()
+            dist.broadcast(r0, 0)
+            if not torch.equal(r0, p.detach()):
+                same.zero_()
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        transport = "n/a"
+        if tr.comm == "peer":
+            transport = "pull (peer loads, fp32)" if _dp.PEER_FORM[0] != "push" else \
+                ("push, %s gradients" % ("bf16" if tr.peers.elem_size == 2 else "fp32"))
+        return {"max_rel_param_diff_vs_1gpu": float(worst.item()), "ranks_bit_identical": bool(same.item() == 1.0),
+                "comm": tr.comm, "exchange": transport}
+    r32 = run("fp32", 1000, 44, 128, 72)
+    r16 = run("bf16", 1000, 40, 128, 64)
+    out = dict(r32, steps=3, global_batch=12 * world,
+               what="fp32 mode, ragged global batch sharded over the ranks, 3 steps vs the same steps on 1 GPU")
+    out["bf16_mode"] = dict(r16, what="the same in bf16 mode (the headline's arithmetic; tolerance of the mode 2e-2): "
+                                      "operand roundings are per element, the differences are accumulation order + the "
+                                      "gradient transport dtype")
+    return out
 
 
 def decode_section(dev, cpu_seconds):
@@ -563,7 +645,7 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(40, 1, max_seconds=args.cpu_seconds)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -821,6 +903,12 @@ def main():
     WORKLOAD = args.workload
     if args.batch:
         B_PER_GPU = args.batch
+    # stdout carries the ONE JSON line and nothing else: libraries that write to fd 1 (NCCL's version banner, a
+    # compiler note from a child process) are sent to stderr while the run is in progress
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -56,6 +56,9 @@ SIGNATURES = {
     "sn_ipc_open": (_I32, [_P, _P]),
     "sn_ipc_close": (_I32, [_P]),
     "sn_dp_adam_fused": (_I32, [_I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P]),
+    "sn_dp_slot_elems": (_I64, [_I64, _I32]),
+    "sn_dp_push": (_I32, [_I32, _I32, _P, _P, _I64, _I32, _P, _I32, _P, _I32, _P]),
+    "sn_dp_adam_recv": (_I32, [_I32, _I32, _P, _P, _P, _I64, _I32, _P, _P, _I32, _P, _P, _I32, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I32, _P]),
     "sn_att_step_fwd": (_I32, [_P, _P, _P, _P, _F, _P, _I64, _I64, _I64, _I64, _P, _I64, _P, _I64, _P]),
     "sn_att_step_bwd": (_I32, [_P, _P, _P, _P, _F, _P, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "sn_att_step_fwd_b16": (_I32, [_P, _P, _P, _P, _F, _P, _I64, _I64, _I64, _I64, _P, _I64, _P, _I64, _P]),

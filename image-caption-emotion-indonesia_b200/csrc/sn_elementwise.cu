@@ -1,4 +1,5 @@
 #include <stdlib.h>
+#include <string.h>
 // Memory-bound kernels of the hot path: K1 gather/dropout/pack, K5 log-softmax+NLL(+grad, argmax,
 // top-5), deterministic loss reduction, K7 fused clamp+Adam.  All HBM-bound: coalesced, 16-byte
 // vectorised where the layout allows, grids sized from the SM count.
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restric
 // K7: clamp + Adam, torch.optim.Adam op order (see sn100.h)
 // ------------------------------------------------------------------------------------------
 struct AdamRanges {
-  static constexpr int MAX = 48;
+  static constexpr int MAX = 128;
   int64_t off[MAX], len[MAX];
   float step_size[MAX], bc2_sqrt[MAX];
   int step_idx[MAX];              // device-step mode: index into steps_dev
@@ -199,8 +200,10 @@ __global__ void adam_prepare_kernel(AdamRanges R, int32_t* __restrict__ steps, c
   steps[R.step_idx[r]] = st;
   double bc1 = 1.0 - pow((double)beta1, (double)st);
   double bc2 = 1.0 - pow((double)beta2, (double)st);
-  coef[2 * r] = (float)((double)(*lr) / bc1);
-  coef[2 * r + 1] = (float)sqrt(bc2);
+  // slot = the parameter's step index, not the position in this call: calls that run concurrently on different
+  // streams (bucketed early steps) cover disjoint parameters and therefore never share a slot
+  coef[2 * R.step_idx[r]] = (float)((double)(*lr) / bc1);
+  coef[2 * R.step_idx[r] + 1] = (float)sqrt(bc2);
 }
 constexpr int ADAM_CHUNK = 4096;   // elements per CTA-iteration
 
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(256) adam_clamp_kernel(float* __restrict__ p, 
     while (ch >= R.chunk_start[r + 1]) ++r;
     const int64_t base = R.off[r] + (ch - R.chunk_start[r]) * ADAM_CHUNK;
     const int64_t end = R.off[r] + R.len[r];
-    const float ss = coef ? coef[2 * r] : R.step_size[r], bc = coef ? coef[2 * r + 1] : R.bc2_sqrt[r];
+    const float ss = coef ? coef[2 * R.step_idx[r]] : R.step_size[r], bc = coef ? coef[2 * R.step_idx[r] + 1] : R.bc2_sqrt[r];
     const int64_t lim = base + ADAM_CHUNK < end ? base + ADAM_CHUNK : end;
     if ((base & 3) == 0 && lim - base == ADAM_CHUNK) {
       // full, 16-byte aligned chunk: 128-bit loads/stores, 4 independent elements per thread per pass
@@ -270,8 +273,14 @@ struct DpPeers {
   float* param[8];
   int* pad[8];
   int world, rank;
+  // push form: every rank's receive buffer (world slots of `slot_elems` elements each: slot q of rank o holds rank q's
+  // gradients of the chunks o owns, chunk `aid` at element (aid / world) * ADAM_CHUNK), element size 4 (fp32) or 2 (bf16)
+  void* recv[8];
+  int64_t slot_elems;
+  int* wait_pad[4];     // my pads of the push buckets this call consumes (ARRIVE flags written by the peers' pushes)
+  int n_wait;
 };
-constexpr int PAD_ARRIVE = 0, PAD_DONE = 8, PAD_COUNTER = 16, PAD_EPOCH = 17;
+constexpr int PAD_ARRIVE = 0, PAD_DONE = 8, PAD_COUNTER = 16, PAD_EPOCH = 17, PAD_DONE_COUNTER = 18;
 
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   int v;
@@ -280,6 +289,71 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 }
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- push form, part 1: send my gradients of the chunks I do NOT own to their owners (posted NVLink stores: nothing
+// waits here), then raise my ARRIVE flag in every peer's pad.  Launched on the stream that produced the gradients as
+// soon as a bucket is final, so the transfer runs under the rest of the backward.
+// Fat CTAs (DP_SUB groups of 256 threads, one chunk per group and iteration, at most one CTA per SM): the system-scope
+// fence that closes a CTA costs microseconds once remote stores are in flight and the fences of the CTAs of one SM do
+// not overlap -- one per SM instead of one per 256 threads took the kernel from ~17 us + data to ~6 us + data.
+constexpr int DP_SUB = 4;
+template <typename TT>
+__global__ void __launch_bounds__(256 * DP_SUB) dp_push_kernel(DpPeers P, AdamRanges R, const float* __restrict__ g) {
+  const int W = P.world;
+  __shared__ int s_last;
+  int* mypad = P.pad[P.rank];
+  const int64_t total_chunks = R.chunk_start[R.n];
+  const int sub = threadIdx.x >> 8, tid = threadIdx.x & 255;
+  for (int64_t ch = (int64_t)blockIdx.x * DP_SUB + sub; ch < total_chunks; ch += (int64_t)gridDim.x * DP_SUB) {
+    int r = 0;
+    while (ch >= R.chunk_start[r + 1]) ++r;
+    const int64_t aid = R.off[r] / ADAM_CHUNK + (ch - R.chunk_start[r]);
+    const int owner = (int)(aid % W);
+    if (owner == P.rank) continue;
+    const int64_t end = R.off[r] + R.len[r];
+    const int64_t base = aid * ADAM_CHUNK > R.off[r] ? aid * ADAM_CHUNK : R.off[r];
+    const int64_t lim = (aid + 1) * ADAM_CHUNK < end ? (aid + 1) * ADAM_CHUNK : end;
+    TT* dst = reinterpret_cast<TT*>(P.recv[owner]) + (int64_t)P.rank * P.slot_elems + (aid / W) * ADAM_CHUNK - aid * ADAM_CHUNK;
+    if ((base & 3) == 0 && lim - base == ADAM_CHUNK) {
+      float4 t[ADAM_CHUNK / 1024];
+#pragma unroll
+      for (int u = 0; u < ADAM_CHUNK / 1024; ++u)
+        t[u] = __ldcg(reinterpret_cast<const float4*>(g + base + (int64_t)(u * 256 + tid) * 4));
+#pragma unroll
+      for (int u = 0; u < ADAM_CHUNK / 1024; ++u) {
+        const int64_t i = base + (int64_t)(u * 256 + tid) * 4;
+        if constexpr (sizeof(TT) == 4) {
+          *reinterpret_cast<float4*>(dst + i) = t[u];
+        } else {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(t[u].x, t[u].y), hi = __floats2bfloat162_rn(t[u].z, t[u].w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(dst + i) = pk;
+        }
+      }
+      continue;
+    }
+    for (int64_t i = base + tid; i < lim; i += 256) {
+      if constexpr (sizeof(TT) == 4) dst[i] = g[i]; else dst[i] = __float2bfloat16_rn(g[i]);
+    }
+  }
+  // my stores are on their way: one system fence per block (cumulative over the block's stores through the barrier),
+  // count blocks, the last one tells every peer
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(mypad + PAD_COUNTER, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const int e = mypad[PAD_EPOCH] + 1;
+      for (int q = 0; q < W; ++q) st_release_sys(P.pad[q] + PAD_ARRIVE + P.rank, e);
+      mypad[PAD_COUNTER] = 0;
+    }
+  }
 }
 
 template <int W>      // world size as a template parameter: the W peer loads / stores of an element are all in flight
@@ -319,7 +393,7 @@ __global__ void __launch_bounds__(256) dp_adam_fused_kernel(DpPeers P, AdamRange
     const int64_t end = R.off[r] + R.len[r];
     const int64_t base = aid * ADAM_CHUNK > R.off[r] ? aid * ADAM_CHUNK : R.off[r];
     const int64_t lim = (aid + 1) * ADAM_CHUNK < end ? (aid + 1) * ADAM_CHUNK : end;
-    const float ss = coef[2 * r], bc = coef[2 * r + 1];
+    const float ss = coef[2 * R.step_idx[r]], bc = coef[2 * R.step_idx[r] + 1];
     if ((base & 3) == 0 && lim - base == ADAM_CHUNK) {
       // NIT iterations at a time with ALL their loads issued up front: the peer loads cross NVLink (~2 us each), so the
       // number of them in flight per thread, not the instruction count, sets the pace
@@ -377,19 +451,142 @@ __global__ void __launch_bounds__(256) dp_adam_fused_kernel(DpPeers P, AdamRange
       for (int q = 0; q < W; ++q) P.param[q][i] = pn;
     }
   }
-  // 4. all my reads are done and my stores are on their way: fence, count blocks, last block runs the exit barrier
-  __threadfence_system();
+  // 4. all my reads are done and my stores are on their way: one system fence per block (cumulative over the block's
+  // accesses through the barrier), count blocks, last block runs the exit barrier
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(mypad + PAD_COUNTER, 1) == (int)gridDim.x - 1);
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(mypad + PAD_DONE_COUNTER, 1) == (int)gridDim.x - 1);
+  }
   __syncthreads();
   if (s_last) {
-    __threadfence_system();
+    if (threadIdx.x == 0) __threadfence_system();
+    __syncthreads();
     if (threadIdx.x < P.world) {
       st_release_sys(P.pad[threadIdx.x] + PAD_DONE + P.rank, e);
       while (ld_acquire_sys(mypad + PAD_DONE + threadIdx.x) < e) { }
     }
     __syncthreads();
-    if (threadIdx.x == 0) { mypad[PAD_COUNTER] = 0; mypad[PAD_EPOCH] = e; }
+    if (threadIdx.x == 0) {
+      mypad[PAD_DONE_COUNTER] = 0; mypad[PAD_EPOCH] = e;
+    }
+  }
+}
+
+// ---- push form, part 2: the peers' gradients of my chunks are in my receive buffer (dp_push_kernel).  Wait for their
+// ARRIVE flags (local polls), reduce own fp32 gradient + the received ones in rank order, clamp, Adam on the owned
+// chunks, store the new parameters to every rank, exit barrier.  Written like adam_clamp_kernel (one chunk per CTA
+// iteration, few registers, many CTAs per SM) -- the per-CTA flag poll and exit fence hide under the neighbours' loads.
+// R.chunk_start counts OWNED chunks only (host), so the CTAs share the owned chunks evenly for every world size.
+constexpr int DP_RSUB = 2;
+template <int W, typename TT>
+__global__ void __launch_bounds__(256 * DP_RSUB) dp_recv_adam_kernel(DpPeers P, AdamRanges R, const float* __restrict__ coef,
+                                                           const float* __restrict__ g, const TT* __restrict__ recv,
+                                                           const float* p_loc, float* __restrict__ m, float* __restrict__ v, float beta1,
+                                                           float beta2, float eps, float clip) {
+  __shared__ int s_epoch, s_last;
+  const int rank = P.rank;
+  int* mypad = P.wait_pad[0];
+  if (threadIdx.x == 0) s_epoch = mypad[PAD_EPOCH] + 1;
+  if (threadIdx.x < W * P.n_wait) {
+    const int* wp = P.wait_pad[threadIdx.x / W];
+    const int q = threadIdx.x % W;
+    if (q != rank) { const int we = wp[PAD_EPOCH] + 1; while (ld_acquire_sys(wp + PAD_ARRIVE + q) < we) { } }
+  }
+  __syncthreads();
+  const int e = s_epoch;
+  const int64_t total_chunks = R.chunk_start[R.n];
+  const int sub = threadIdx.x >> 8, tid = threadIdx.x & 255;
+  for (int64_t ch = (int64_t)blockIdx.x * DP_RSUB + sub; ch < total_chunks; ch += (int64_t)gridDim.x * DP_RSUB) {
+    int r = 0;
+    while (ch >= R.chunk_start[r + 1]) ++r;
+    const int64_t a0 = R.off[r] / ADAM_CHUNK;
+    const int64_t aid = a0 + ((rank - a0) % W + W) % W + (ch - R.chunk_start[r]) * W;     // my (ch - start)-th chunk of range r
+    const int64_t end = R.off[r] + R.len[r];
+    const int64_t base = aid * ADAM_CHUNK > R.off[r] ? aid * ADAM_CHUNK : R.off[r];
+    const int64_t lim = (aid + 1) * ADAM_CHUNK < end ? (aid + 1) * ADAM_CHUNK : end;
+    const float ss = coef[2 * R.step_idx[r]], bc = coef[2 * R.step_idx[r] + 1];
+    const int64_t rbase = (aid / W) * ADAM_CHUNK - aid * ADAM_CHUNK;      // arena index -> index in a receive slot
+    if ((base & 3) == 0 && lim - base == ADAM_CHUNK) {
+#pragma unroll
+      for (int it = 0; it < ADAM_CHUNK / (256 * 4); ++it) {
+        const int64_t i = base + (int64_t)(it * 256 + tid) * 4;
+        float4 t[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+          if (q == rank) {
+            t[q] = __ldcg(reinterpret_cast<const float4*>(g + i));
+          } else if constexpr (sizeof(TT) == 4) {
+            t[q] = __ldcg(reinterpret_cast<const float4*>(recv + q * P.slot_elems + rbase + i));
+          } else {
+            const uint2 pk = __ldcg(reinterpret_cast<const uint2*>(recv + q * P.slot_elems + rbase + i));
+            const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+            const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+            t[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          }
+        }
+        float4 m4 = *reinterpret_cast<const float4*>(m + i);
+        float4 v4 = *reinterpret_cast<const float4*>(v + i);
+        float4 p4 = *reinterpret_cast<const float4*>(p_loc + i);
+        float4 g4 = t[0];
+#pragma unroll
+        for (int q = 1; q < W; ++q) { g4.x += t[q].x; g4.y += t[q].y; g4.z += t[q].z; g4.w += t[q].w; }
+        float* gp = &g4.x; float* mp = &m4.x; float* vp = &v4.x; float* pp = &p4.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float gi = gp[k];
+          if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+          const float mi = mp[k] + (1.f - beta1) * (gi - mp[k]);
+          const float vi = vp[k] * beta2 + (1.f - beta2) * gi * gi;
+          pp[k] = pp[k] - ss * (mi / (sqrtf(vi) / bc + eps));
+          mp[k] = mi; vp[k] = vi;
+        }
+        *reinterpret_cast<float4*>(m + i) = m4;
+        *reinterpret_cast<float4*>(v + i) = v4;
+#pragma unroll
+        for (int q = 0; q < W; ++q) *reinterpret_cast<float4*>(P.param[q] + i) = p4;
+      }
+      continue;
+    }
+    for (int64_t i = base + tid; i < lim; i += 256) {
+      float gi = 0.f;
+#pragma unroll
+      for (int q = 0; q < W; ++q) {
+        float gq;
+        if (q == rank) gq = __ldcg(g + i);
+        else if constexpr (sizeof(TT) == 4) gq = __ldcg(recv + q * P.slot_elems + rbase + i);
+        else gq = __bfloat162float(recv[q * P.slot_elems + rbase + i]);
+        gi = q == 0 ? gq : gi + gq;
+      }
+      if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+      const float mi = m[i] + (1.f - beta1) * (gi - m[i]);
+      const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;
+      const float pn = p_loc[i] - ss * (mi / (sqrtf(vi) / bc + eps));
+      m[i] = mi; v[i] = vi;
+#pragma unroll
+      for (int q = 0; q < W; ++q) P.param[q][i] = pn;
+    }
+  }
+  // all my reads are done and my stores are on their way: one system fence per block (cumulative over the block's
+  // accesses through the barrier), count blocks, last block runs the exit barrier and advances the epochs
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(mypad + PAD_DONE_COUNTER, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x == 0) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < W) {
+      st_release_sys(P.pad[threadIdx.x] + PAD_DONE + rank, e);
+      while (ld_acquire_sys(mypad + PAD_DONE + threadIdx.x) < e) { }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mypad[PAD_DONE_COUNTER] = 0; mypad[PAD_EPOCH] = e;
+      for (int k = 1; k < P.n_wait; ++k) P.wait_pad[k][PAD_EPOCH] = P.wait_pad[k][PAD_EPOCH] + 1;
+    }
   }
 }
 
@@ -514,7 +711,7 @@ int32_t sn_adam_clamp_dev(float* p, float* g, float* m, float* v, int32_t n_rang
     R.chunk_start[i + 1] = R.chunk_start[i] + (R.len[i] + ADAM_CHUNK - 1) / ADAM_CHUNK;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  adam_prepare_kernel<<<1, 64, 0, st>>>(R, steps_dev, lr_dev, coef_ws, beta1, beta2);
+  adam_prepare_kernel<<<1, AdamRanges::MAX, 0, st>>>(R, steps_dev, lr_dev, coef_ws, beta1, beta2);
   int64_t chunks = R.chunk_start[R.n];
   if (chunks == 0) return sn::check_launch("sn_adam_clamp_dev");
   int64_t cap = (int64_t)sn::dev_info().sm_count * 8;
@@ -544,6 +741,7 @@ int32_t sn_dp_adam_fused(int32_t world, int32_t rank, void* const* grad_ptrs, vo
   SN_REQUIRE(n_ranges >= 0 && n_ranges <= AdamRanges::MAX, "sn_dp_adam_fused: at most %d ranges per call", AdamRanges::MAX);
   SN_REQUIRE(grad_ptrs && param_ptrs && pad_ptrs && steps_dev && lr_dev && coef_ws && m && v, "sn_dp_adam_fused: null argument");
   DpPeers P;
+  memset(&P, 0, sizeof(P));
   P.world = world; P.rank = rank;
   for (int q = 0; q < 8; ++q) {
     P.grad[q] = q < world ? (float*)grad_ptrs[q] : nullptr;
@@ -563,7 +761,7 @@ int32_t sn_dp_adam_fused(int32_t world, int32_t rank, void* const* grad_ptrs, vo
         (R.len[i] > 0 ? (R.off[i] + R.len[i] - 1) / ADAM_CHUNK - R.off[i] / ADAM_CHUNK + 1 : 0);
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (n_ranges > 0) adam_prepare_kernel<<<1, 64, 0, st>>>(R, steps_dev, lr_dev, coef_ws, beta1, beta2);
+  if (n_ranges > 0) adam_prepare_kernel<<<1, AdamRanges::MAX, 0, st>>>(R, steps_dev, lr_dev, coef_ws, beta1, beta2);
   // every rank launches the same grid even when it owns no chunk: the kernel is also the cross-GPU barrier
   int64_t mine = (R.chunk_start[R.n] + world - 1) / world;
   // persistent: at most 3 CTAs per SM loop over the slots (every CTA ends with a system-scope fence and an atomic)
@@ -583,6 +781,122 @@ int32_t sn_dp_adam_fused(int32_t world, int32_t rank, void* const* grad_ptrs, vo
   }
 #undef SN_DP_LAUNCH
   return sn::check_launch("sn_dp_adam_fused");
+}
+
+static int32_t dp_fill_ranges(AdamRanges& R, int32_t n_ranges, const int64_t* ranges, const int32_t* step_idx, const char* who) {
+  SN_REQUIRE(n_ranges >= 0 && n_ranges <= AdamRanges::MAX, "%s: at most %d ranges per call", who, AdamRanges::MAX);
+  R.n = n_ranges;
+  R.chunk_start[0] = 0;
+  for (int i = 0; i < n_ranges; ++i) {
+    R.off[i] = ranges[2 * i]; R.len[i] = ranges[2 * i + 1]; R.step_idx[i] = step_idx ? step_idx[i] : 0;
+    R.step_size[i] = 0.f; R.bc2_sqrt[i] = 1.f;
+    SN_REQUIRE(R.off[i] >= 0 && R.len[i] >= 0, "%s: bad range %d", who, i);
+    R.chunk_start[i + 1] = R.chunk_start[i] +
+        (R.len[i] > 0 ? (R.off[i] + R.len[i] - 1) / ADAM_CHUNK - R.off[i] / ADAM_CHUNK + 1 : 0);
+  }
+  return 0;
+}
+
+int64_t sn_dp_slot_elems(int64_t arena_elems, int32_t world) {
+  if (arena_elems < 0 || world < 1) return -1;
+  int64_t chunks = (arena_elems + ADAM_CHUNK - 1) / ADAM_CHUNK;
+  return ((chunks + world - 1) / world) * ADAM_CHUNK;
+}
+
+int32_t sn_dp_push(int32_t world, int32_t rank, const float* grad, void* const* recv_ptrs, int64_t slot_elems,
+                   int32_t elem_size, void* const* pad_ptrs, int32_t n_ranges, const int64_t* ranges, int32_t max_ctas,
+                   void* stream) {
+  SN_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "sn_dp_push: bad world/rank %d/%d", world, rank);
+  SN_REQUIRE(grad && recv_ptrs && pad_ptrs && ranges, "sn_dp_push: null argument");
+  SN_REQUIRE(elem_size == 4 || elem_size == 2, "sn_dp_push: elem_size must be 4 (fp32) or 2 (bf16)");
+  SN_REQUIRE(slot_elems > 0 && slot_elems % ADAM_CHUNK == 0, "sn_dp_push: slot_elems must be a positive multiple of %d", ADAM_CHUNK);
+  DpPeers P;
+  memset(&P, 0, sizeof(P));
+  P.world = world; P.rank = rank; P.slot_elems = slot_elems;
+  for (int q = 0; q < world; ++q) {
+    P.recv[q] = recv_ptrs[q]; P.pad[q] = (int*)pad_ptrs[q];
+    SN_REQUIRE(P.recv[q] && P.pad[q], "sn_dp_push: null peer pointer %d", q);
+  }
+  AdamRanges R;
+  if (int32_t rc = dp_fill_ranges(R, n_ranges, ranges, nullptr, "sn_dp_push")) return rc;
+  for (int i = 0; i < n_ranges; ++i)
+    SN_REQUIRE(R.len[i] == 0 || (R.off[i] + R.len[i] - 1) / ADAM_CHUNK / world < slot_elems / ADAM_CHUNK,
+               "sn_dp_push: range %d does not fit the receive slots", i);
+  // every rank launches (the kernel also raises the ARRIVE flags); a light grid: the NVLink stores, not the SMs, set
+  // the pace, and the producing stream's neighbours (weight-gradient GEMMs) keep their SMs
+  int64_t chunks = R.chunk_start[R.n];
+  int64_t cap = (int64_t)sn::dev_info().sm_count;
+  if (max_ctas > 0 && max_ctas < cap) cap = max_ctas;      // background exchange under the backward: leave the GEMMs their SMs
+  int64_t want = (chunks + DP_SUB - 1) / DP_SUB;
+  unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (elem_size == 4) dp_push_kernel<float><<<grid, 256 * DP_SUB, 0, st>>>(P, R, grad);
+  else dp_push_kernel<__nv_bfloat16><<<grid, 256 * DP_SUB, 0, st>>>(P, R, grad);
+  return sn::check_launch("sn_dp_push");
+}
+
+int32_t sn_dp_adam_recv(int32_t world, int32_t rank, float* grad, void* const* param_ptrs, void* recv, int64_t slot_elems,
+                        int32_t elem_size, void* const* pad_ptrs, void* const* wait_pads, int32_t n_wait, float* m, float* v,
+                        int32_t n_ranges, const int64_t* ranges, const int32_t* step_idx, int32_t* steps_dev,
+                        const float* lr_dev, float* coef_ws, float beta1, float beta2, float eps, float clip,
+                        int32_t max_ctas, void* stream) {
+  SN_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "sn_dp_adam_recv: bad world/rank %d/%d", world, rank);
+  SN_REQUIRE(grad && param_ptrs && recv && pad_ptrs && wait_pads && steps_dev && lr_dev && coef_ws && m && v && ranges && step_idx,
+             "sn_dp_adam_recv: null argument");
+  SN_REQUIRE(elem_size == 4 || elem_size == 2, "sn_dp_adam_recv: elem_size must be 4 (fp32) or 2 (bf16)");
+  SN_REQUIRE(n_wait >= 1 && n_wait <= 4, "sn_dp_adam_recv: 1..4 push buckets per call (got %d)", n_wait);
+  SN_REQUIRE(slot_elems > 0 && slot_elems % ADAM_CHUNK == 0, "sn_dp_adam_recv: slot_elems must be a positive multiple of %d", ADAM_CHUNK);
+  SN_REQUIRE(n_ranges >= 1, "sn_dp_adam_recv: no ranges");
+  DpPeers P;
+  memset(&P, 0, sizeof(P));
+  P.world = world; P.rank = rank; P.slot_elems = slot_elems; P.n_wait = n_wait;
+  for (int q = 0; q < world; ++q) {
+    P.param[q] = (float*)param_ptrs[q]; P.pad[q] = (int*)pad_ptrs[q];
+    SN_REQUIRE(P.param[q] && P.pad[q], "sn_dp_adam_recv: null peer pointer %d", q);
+  }
+  P.grad[rank] = grad;
+  P.recv[rank] = recv;
+  for (int k = 0; k < n_wait; ++k) {
+    P.wait_pad[k] = (int*)wait_pads[k];
+    SN_REQUIRE(P.wait_pad[k], "sn_dp_adam_recv: null wait pad %d", k);
+  }
+  SN_REQUIRE(P.wait_pad[0] == P.pad[rank], "sn_dp_adam_recv: pad_ptrs must be every rank's pad of wait bucket 0");
+  AdamRanges R;
+  if (int32_t rc = dp_fill_ranges(R, n_ranges, ranges, step_idx, "sn_dp_adam_recv")) return rc;
+  // chunk_start = prefix of the chunks THIS rank owns in each range (absolute chunk id % world == rank)
+  for (int i = 0; i < n_ranges; ++i) {
+    int64_t own = 0;
+    if (R.len[i] > 0) {
+      const int64_t a0 = R.off[i] / ADAM_CHUNK, a1 = (R.off[i] + R.len[i] - 1) / ADAM_CHUNK;
+      const int64_t first = a0 + ((rank - a0) % world + world) % world;
+      own = first <= a1 ? (a1 - first) / world + 1 : 0;
+      SN_REQUIRE(a1 / world < slot_elems / ADAM_CHUNK, "sn_dp_adam_recv: range %d does not fit the receive slots", i);
+    }
+    R.chunk_start[i + 1] = R.chunk_start[i] + own;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_prepare_kernel<<<1, AdamRanges::MAX, 0, st>>>(R, steps_dev, lr_dev, coef_ws, beta1, beta2);
+  // every rank launches (the kernel is also the exit barrier), also one that owns no chunk of these ranges
+  int64_t mine = (R.chunk_start[R.n] + DP_RSUB - 1) / DP_RSUB;
+  int64_t cap = (int64_t)sn::dev_info().sm_count * 2;
+  if (max_ctas > 0 && max_ctas < cap) cap = max_ctas;
+  unsigned grid = (unsigned)(mine < 1 ? 1 : (mine < cap ? mine : cap));
+  const float* p_loc = P.param[rank];
+#define SN_DP_LAUNCH(WW)                                                                                                   \
+  if (elem_size == 4) dp_recv_adam_kernel<WW, float><<<grid, 256 * DP_RSUB, 0, st>>>(P, R, coef_ws, grad, (const float*)recv, p_loc, m, v, beta1, beta2, eps, clip); \
+  else dp_recv_adam_kernel<WW, __nv_bfloat16><<<grid, 256 * DP_RSUB, 0, st>>>(P, R, coef_ws, grad, (const __nv_bfloat16*)recv, p_loc, m, v, beta1, beta2, eps, clip)
+  switch (world) {
+    case 1: SN_DP_LAUNCH(1); break;
+    case 2: SN_DP_LAUNCH(2); break;
+    case 3: SN_DP_LAUNCH(3); break;
+    case 4: SN_DP_LAUNCH(4); break;
+    case 5: SN_DP_LAUNCH(5); break;
+    case 6: SN_DP_LAUNCH(6); break;
+    case 7: SN_DP_LAUNCH(7); break;
+    default: SN_DP_LAUNCH(8); break;
+  }
+#undef SN_DP_LAUNCH
+  return sn::check_launch("sn_dp_adam_recv");
 }
 
 int32_t sn_mean_pixels(const float* feat, int64_t B, int64_t P, int64_t D, float* out, void* stream) {

@@ -536,10 +536,10 @@ def adam_clamp_dev(p, g, m, v, ranges, step_idx, steps_dev, lr_dev, coef_ws, bet
         for i in range(k):
             R[2 * i], R[2 * i + 1] = ranges[i0 + i]
             S[i] = step_idx[i0 + i]
+        # (coefficient slots are indexed by step_idx: one work space serves every call, also concurrent ones)
         check(lib().sn_adam_clamp_dev(_ptr(_req(p)), _ptr(_req(g)), _ptr(_req(m)), _ptr(_req(v)), k,
                                       ctypes.cast(R, ctypes.c_void_p), ctypes.cast(S, ctypes.c_void_p),
-                                      _ptr(steps_dev), _ptr(lr_dev),
-                                      ctypes.c_void_p(coef_ws.data_ptr() + 4 * 2 * i0), beta1, beta2, eps, clip,
+                                      _ptr(steps_dev), _ptr(lr_dev), _ptr(coef_ws), beta1, beta2, eps, clip,
                                       _stream()), "sn_adam_clamp_dev")
 
 
@@ -568,6 +568,60 @@ def dp_adam_fused(world, rank, grad_ptrs, param_ptrs, pad_ptrs, m, v, ranges, st
                                  ctypes.cast(D, ctypes.c_void_p), _ptr(_req(m)), _ptr(_req(v)), n,
                                  ctypes.cast(R, ctypes.c_void_p), ctypes.cast(S, ctypes.c_void_p), _ptr(steps_dev),
                                  _ptr(lr_dev), _ptr(coef_ws), beta1, beta2, eps, clip, _stream()), "sn_dp_adam_fused")
+
+
+DP_MAX_RANGES = 128      # AdamRanges::MAX (sn_elementwise.cu)
+
+
+def dp_slot_elems(arena_elems, world):
+    return int(lib().sn_dp_slot_elems(int(arena_elems), int(world)))
+
+
+def _ranges_c(ranges, step_idx=None):
+    n = len(ranges)
+    R = (ctypes.c_int64 * (2 * max(n, 1)))()
+    S = (ctypes.c_int32 * max(n, 1))()
+    for i in range(n):
+        R[2 * i], R[2 * i + 1] = ranges[i]
+        if step_idx is not None:
+            S[i] = step_idx[i]
+    return R, S
+
+
+def dp_push(world, rank, grad, recv_ptrs, slot_elems, elem_size, pad_ptrs, ranges, max_ctas=0):
+    """Push-form exchange, part 1 (sn_dp_push): non-blocking send of my gradients of foreign chunks + ARRIVE flags."""
+    # adjacent ranges travel as one (the push has no per-parameter state)
+    merged = []
+    for off, n in sorted(ranges):
+        if merged and merged[-1][0] + merged[-1][1] == off:
+            merged[-1] = (merged[-1][0], merged[-1][1] + n)
+        else:
+            merged.append((off, n))
+    if len(merged) > DP_MAX_RANGES:
+        raise RuntimeError("dp_push: more than %d ranges in one bucket (each call raises the bucket's flags once)" % DP_MAX_RANGES)
+    R, _ = _ranges_c(merged)
+    Rv = (ctypes.c_void_p * world)(*recv_ptrs)
+    D = (ctypes.c_void_p * world)(*pad_ptrs)
+    check(lib().sn_dp_push(world, rank, _ptr(_req(grad)), ctypes.cast(Rv, ctypes.c_void_p), int(slot_elems),
+                           int(elem_size), ctypes.cast(D, ctypes.c_void_p), len(merged),
+                           ctypes.cast(R, ctypes.c_void_p), int(max_ctas), _stream()), "sn_dp_push")
+
+
+def dp_adam_recv(world, rank, grad, param_ptrs, recv, slot_elems, elem_size, pad_ptrs, wait_pads, m, v, ranges, step_idx,
+                 steps_dev, lr_dev, coef_ws, beta1, beta2, eps, clip, max_ctas=0):
+    """Push-form exchange, part 2 (sn_dp_adam_recv): wait for the pushes, reduce, clamp/Adam, parameter all-gather."""
+    if len(ranges) > DP_MAX_RANGES:
+        raise RuntimeError("dp_adam_recv: more than %d ranges in one call" % DP_MAX_RANGES)
+    R, S = _ranges_c(ranges, step_idx)
+    Pp = (ctypes.c_void_p * world)(*param_ptrs)
+    D = (ctypes.c_void_p * world)(*pad_ptrs)
+    Wp = (ctypes.c_void_p * len(wait_pads))(*wait_pads)
+    check(lib().sn_dp_adam_recv(world, rank, _ptr(_req(grad)), ctypes.cast(Pp, ctypes.c_void_p), ctypes.c_void_p(recv.data_ptr()),
+                                int(slot_elems), int(elem_size), ctypes.cast(D, ctypes.c_void_p),
+                                ctypes.cast(Wp, ctypes.c_void_p), len(wait_pads), _ptr(_req(m)), _ptr(_req(v)),
+                                len(ranges), ctypes.cast(R, ctypes.c_void_p), ctypes.cast(S, ctypes.c_void_p),
+                                _ptr(steps_dev), _ptr(lr_dev), _ptr(coef_ws), beta1, beta2, eps, clip, int(max_ctas),
+                                _stream()), "sn_dp_adam_recv")
 
 
 def ipc_export(t):

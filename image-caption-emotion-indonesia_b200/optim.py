@@ -183,6 +183,49 @@ class FusedClampAdam:
                           ranges, idx, self.steps_dev, self.lr_dev, self.coef_ws, self.betas[0], self.betas[1],
                           self.eps, self.grad_clip)
 
+    def _peer_items(self, only, skip):
+        a = self._state()
+        items, foreign = a.grad_ranges()
+        if only is not None:
+            keep = set(only)
+            items = [it for it in items if it[2] in keep]
+        if skip is not None:
+            drop = set(skip)
+            items = [it for it in items if it[2] not in drop]
+        if foreign or any(p.grad is not None for p in self.extra):
+            raise RuntimeError("peer-fused step needs every gradient in the arena")
+        return a, items
+
+    @torch.no_grad()
+    def push_peer(self, peers, only=None, skip=None, bucket=0, max_ctas=0):
+        """Push form, part 1: send this rank's gradients of ``only`` (minus ``skip``) to the chunk owners' receive buffers
+        (non-blocking, on the current stream) and raise this bucket's ARRIVE flags.  Returns False when there was nothing
+        to send (no call was made -- the same on every rank)."""
+        a, items = self._peer_items(only, skip)
+        if not items:
+            return False
+        ops.dp_push(peers.world, peers.rank, a.gflat, peers.recv_ptrs, peers.slot_elems, peers.elem_size,
+                    peers.pads(bucket), [(off, n) for off, n, _ in items], max_ctas=max_ctas)
+        return True
+
+    @torch.no_grad()
+    def step_peer_recv(self, peers, buckets, only=None, skip=None, max_ctas=0):
+        """Push form, part 2: wait for the pushes of ``buckets`` (1..4 bucket ids whose gradients are exactly ``only`` minus
+        ``skip``), reduce, clamp + Adam on the owned chunks, parameter all-gather, exit barrier."""
+        a, items = self._peer_items(only, skip)
+        self._sync_lr()
+        if not items:
+            if buckets:
+                raise RuntimeError("step_peer_recv: pushed buckets without gradients")
+            return
+        ranges = [(off, n) for off, n, _ in items]
+        idx = [self.index[name] for _, _, name in items]
+        mine = [peers.pads(b)[peers.rank] for b in buckets]
+        ops.dp_adam_recv(peers.world, peers.rank, a.gflat, peers.param_ptrs, peers.recv, peers.slot_elems,
+                         peers.elem_size, peers.pads(buckets[0]), mine, self.m, self.v, ranges, idx, self.steps_dev,
+                         self.lr_dev, self.coef_ws, self.betas[0], self.betas[1], self.eps, self.grad_clip,
+                         max_ctas=max_ctas)
+
     def _step_tensor(self, p, key):
         st = self.extra_state.get(key)
         if st is None:

@@ -268,7 +268,9 @@ int32_t sn_adam_clamp(float* p, float* g, float* m, float* v, int32_t n_ranges,
 
 /* Same kernel with the per-parameter step counters and the learning rate in DEVICE memory, so the whole
  * training step can be replayed from a CUDA graph: a prologue kernel increments steps_dev[step_idx[r]] and
- * derives lr/(1-beta1^t), sqrt(1-beta2^t) in double precision into coef_ws (2*n_ranges floats). */
+ * derives lr/(1-beta1^t), sqrt(1-beta2^t) in double precision into coef_ws[2*step_idx[r]], [2*step_idx[r]+1]
+ * (2 * (max step_idx + 1) floats: the slot belongs to the parameter, so calls that run concurrently on different
+ * streams over disjoint parameters never share one). */
 int32_t sn_adam_clamp_dev(float* p, float* g, float* m, float* v, int32_t n_ranges,
                           const int64_t* ranges, const int32_t* step_idx, int32_t* steps_dev,
                           const float* lr_dev, float* coef_ws, float beta1, float beta2, float eps,
@@ -295,6 +297,31 @@ int32_t sn_dp_adam_fused(int32_t world, int32_t rank, void* const* grad_ptrs, vo
                          const int64_t* ranges, const int32_t* step_idx, int32_t* steps_dev,
                          const float* lr_dev, float* coef_ws, float beta1, float beta2, float eps,
                          float clip, void* stream);
+/* Push form of the same exchange, in two calls, so that the gradient transfer leaves the end of the step:
+ *   sn_dp_push      (non-blocking) as soon as a bucket of gradient ranges is final, on the stream that produced it:
+ *                   my gradients of the chunks I do not own go to their owners' receive buffers by posted NVLink
+ *                   stores (fp32, or bf16 when elem_size == 2), then my ARRIVE flag is raised in every peer's pad of
+ *                   this bucket.  Nothing waits: the transfer overlaps the rest of the backward.
+ *   sn_dp_adam_recv for a set of pushed buckets (1..4): waits (local polls) until every peer's pushes of those buckets
+ *                   have landed, reduces own fp32 gradient + the received ones in rank order, clamp + Adam on the owned
+ *                   chunks, parameter all-gather by peer stores, exit barrier (DONE flags in the pads of wait bucket 0).
+ *   recv_ptrs    every rank's receive buffer: `world` slots of sn_dp_slot_elems(arena_elems, world) elements; slot q of
+ *                rank o holds rank q's gradients of o's chunks, chunk `aid` at element (aid / world) * 4096
+ *   pad_ptrs     every rank's pad of the bucket (push) / of wait bucket 0 (recv); wait_pads: MY pads of the consumed
+ *                buckets, wait_pads[0] == pad_ptrs[rank]
+ *   max_ctas     0 = the whole GPU (exchange at the end of the step); > 0 caps the grid (1024-thread CTAs for the push,
+ *                512-thread CTAs for the receive side) for an exchange that runs UNDER the backward and must leave the
+ *                GEMMs their SMs
+ * With elem_size 4 the sum is bit-identical to sn_dp_adam_fused's (same operands, same order). */
+int64_t sn_dp_slot_elems(int64_t arena_elems, int32_t world);
+int32_t sn_dp_push(int32_t world, int32_t rank, const float* grad, void* const* recv_ptrs, int64_t slot_elems,
+                   int32_t elem_size, void* const* pad_ptrs, int32_t n_ranges, const int64_t* ranges,
+                   int32_t max_ctas, void* stream);
+int32_t sn_dp_adam_recv(int32_t world, int32_t rank, float* grad, void* const* param_ptrs, void* recv,
+                        int64_t slot_elems, int32_t elem_size, void* const* pad_ptrs, void* const* wait_pads,
+                        int32_t n_wait, float* m, float* v, int32_t n_ranges, const int64_t* ranges,
+                        const int32_t* step_idx, int32_t* steps_dev, const float* lr_dev, float* coef_ws,
+                        float beta1, float beta2, float eps, float clip, int32_t max_ctas, void* stream);
 
 /* ---- K4: soft attention step (scores -> softmax over pixels -> context -> f_beta gate) ----------
  * replaces Attention.forward after the hoisted encoder_att GEMM (model_att.py:61-70) and the gate

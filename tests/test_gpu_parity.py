@@ -397,6 +397,90 @@ def test_peer_fused_adam_degenerate_world1():
         assert rel_l2(q.detach().cpu(), p.detach().cpu()) < 1e-5, n
 
 
+@pytest.mark.parametrize("world,grad_dtype", [(1, "fp32"), (2, "fp32"), (3, "fp32"), (2, "bf16")])
+def test_peer_push_form_simulated_ranks(world, grad_dtype):
+    """sn_dp_push + sn_dp_adam_recv with `world` ranks simulated on ONE GPU (each 'rank' = its own decoder, arenas,
+    pads and receive buffer; the ranks' kernels run on separate streams so the cross-rank flags make progress):
+    the result must equal the local fused clamp+Adam applied to the rank-ordered sum of the gradients -- to the last
+    bits with fp32 transport (and bit-identical on every rank), and within bf16 rounding of the foreign gradients with bf16 transport.  Buckets: one pushed early
+    and consumed alone, two consumed together, 3 steps (epochs advance, receive buffers are reused)."""
+    import icei_b200 as sn
+    from icei_b200 import ops
+    V, E, H, F = 300, 28, 64, 72
+    torch.manual_seed(0)
+    make = lambda: sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0).cuda().train()
+    ref = make()
+    ranks = [make() for _ in range(world)]
+    for d in ranks:
+        d.load_state_dict(ref.state_dict())
+    oref = sn.FusedClampAdam(ref, lr=1e-3)
+    opts = [sn.FusedClampAdam(d, lr=1e-3) for d in ranks]
+    arenas = [d.arena() for d in ranks]
+    aref = ref.arena()
+    names = list(aref.named)
+    out_names = list(ref._out_names())
+    rest = [n for n in names if n not in out_names]
+    half = len(rest) // 2
+    buckets = [(0, out_names), (1, rest[:half]), (2, rest[half:])]
+    slot = ops.dp_slot_elems(aref.flat.numel(), world)
+    tdt = torch.bfloat16 if grad_dtype == "bf16" else torch.float32
+
+    class Peer:
+        def pads(self, bucket):
+            return [q + 128 * bucket for q in self.pad_ptrs]
+    pads = [torch.zeros(32 * 16, dtype=torch.int32, device="cuda") for _ in range(world)]
+    recvs = [torch.zeros(world * slot, dtype=tdt, device="cuda") for _ in range(world)]
+    peers = []
+    for r in range(world):
+        pe = Peer()
+        pe.world, pe.rank = world, r
+        pe.param_ptrs = [a.flat.data_ptr() for a in arenas]
+        pe.grad_ptrs = [a.gflat.data_ptr() for a in arenas]
+        pe.pad_ptrs = [t.data_ptr() for t in pads]
+        pe.recv_ptrs = [t.data_ptr() for t in recvs]
+        pe.recv, pe.slot_elems, pe.elem_size = recvs[r], slot, (2 if grad_dtype == "bf16" else 4)
+        peers.append(pe)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for step in range(3):
+        gs = [torch.randn(aref.gflat.numel(), device="cuda", generator=g) * (2.0 if step == 1 else 0.2) for _ in range(world)]
+        for a, gr in zip(arenas, gs):
+            a.gflat.copy_(gr)
+            a.publish_grads(names, a.gflat)
+        total = gs[0].clone()
+        for r in range(1, world):
+            total += gs[r]
+        aref.gflat.copy_(total)
+        aref.publish_grads(names, aref.gflat)
+        oref.step()
+        torch.cuda.synchronize()
+        # every rank pushes its buckets (non-blocking), then the consuming calls run concurrently on one stream per rank
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                for b, nm in buckets:
+                    assert opts[r].push_peer(peers[r], only=nm, bucket=b)
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                opts[r].step_peer_recv(peers[r], [0], only=out_names)
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                opts[r].step_peer_recv(peers[r], [1, 2], skip=out_names)
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert int(pads[r][17]) == step + 1 and int(pads[r][32 + 17]) == step + 1 and int(pads[r][64 + 17]) == step + 1
+    for r in range(world):
+        assert torch.equal(arenas[r].flat, arenas[0].flat), "ranks differ"
+    if grad_dtype == "fp32":
+        # (the local kernel and the exchange kernel write the Adam update with differently associated fp32 expressions:
+        # last-bit differences, as in test_peer_fused_adam_degenerate_world1)
+        assert rel_l2(arenas[0].flat.cpu(), aref.flat.cpu()) < 1e-6
+        assert float((arenas[0].flat - aref.flat).abs().max()) < 1e-6
+    else:
+        # bf16 transport of the foreign gradients: an Adam step moves a weight by at most ~lr, 3 steps
+        assert float((arenas[0].flat - aref.flat).abs().max()) <= 3 * 1e-3 * 1.01
+        assert rel_l2(arenas[0].flat.cpu(), aref.flat.cpu()) < 2e-2
+
+
 def _greedy_case(name, precision):
     """(decoder factory, captions, lengths, features, kwargs, golden greedy ids or None)"""
     import icei_b200 as sn
