@@ -13,6 +13,8 @@ no PyTorch/CPU fallback -- tensors must be CUDA tensors on an sm_100 device.
 import random
 from collections import OrderedDict
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -178,7 +180,7 @@ class _DecoderBase(nn.Module):
             torch.cuda.current_stream().wait_event(ev)
         return Wb
 
-    def _shadows_async(self, specs):
+    def _shadows_async(self, specs, max_blocks=24):
         """bf16 operand shadows of fp32 weights, cast on side stream 2 while the main stream gathers / projects.
         ``specs``: [(dict, key, fp32 2-D weight)].  The output tensors are allocated on the CURRENT stream (so the
         caching allocator ties their lifetime to it) and only written on the side stream.  Returns the event the main
@@ -195,7 +197,7 @@ class _DecoderBase(nn.Module):
         side.wait_stream(main)
         with torch.cuda.stream(side):
             for w, out, R, C, Cp in outs:
-                ops.cast_bf16(w, R, C, w.stride(0), out, Cp, Cp, max_blocks=24)
+                ops.cast_bf16(w, R, C, w.stride(0), out, Cp, Cp, max_blocks=max_blocks)
             ev = torch.cuda.Event()
             ev.record(side)
         return ev
@@ -263,10 +265,14 @@ class _DecoderBase(nn.Module):
             c.tok_override = torch.full((N,), -1, dtype=torch.int32, device=dev)
         c.Ein = E
         c.w16 = {}      # bf16 weight shadows of this call (refreshed every forward)
-        c.ev_early = c.ev_late = None
+        c.ev_early = c.ev_late = c.ev_first = None
         if self.bf16:
-            # every weight shadow except the first GEMM's is cast on a side stream, under the gather / first GEMM
+            # every weight shadow is cast on a side stream: the first GEMM's at full width next to the gather (it is on
+            # the critical path), the others throttled (24 CTAs) under the gather / first GEMM
             early, late = self._shadow_specs(c, mode)
+            first = c.__dict__.pop("first_specs", None)
+            if first:
+                c.ev_first = self._shadows_async(first, max_blocks=0)
             if early:
                 c.ev_early = self._shadows_async(early)
             if late:
@@ -404,8 +410,8 @@ class _DecoderBase(nn.Module):
         L = getattr(cl, "layer", 0)
         Whh, _ = self._recurrent_weights(L)
         dZ = torch.empty(N, 4 * H, dtype=torch.float32, device=dev)
-        dh = torch.zeros(B, H, dtype=torch.float32, device=dev)
-        dc = torch.zeros(B, H, dtype=torch.float32, device=dev)
+        dhc = torch.zeros(2, B, H, dtype=torch.float32, device=dev)      # (one fill kernel in front of the recurrence)
+        dh, dc = dhc[0], dhc[1]
         gW, gbW = self._recurrent_grads(gbuf, L)
         if cl.Hpb is not None:
             cl.dZb = torch.empty(N, 4 * H, dtype=torch.bfloat16, device=dev)
@@ -755,6 +761,9 @@ class _DecoderBase(nn.Module):
         return captions.reshape(-1).index_select(0, idx)
 
 
+V_CAST_SIDE = [os.environ.get("SN_V_CAST_SIDE", "1") == "1"]
+
+
 class DecoderFactoredLSTM(_DecoderBase):
     """StyleNet FactoredLSTM decoder -- signature of stylenet/model.py:32-41."""
 
@@ -827,7 +836,9 @@ class DecoderFactoredLSTM(_DecoderBase):
         H, F = self.hidden_size, self.factored_size
         early, late = super()._shadow_specs(c, mode)
         if mode in STYLES:
-            # (V stays on the main stream: its K = 300 -> 304 padded cast is the scalar kernel, 39 us under the block cap)
+            # (V's K = 300 -> 304 padded cast is the scalar kernel, 39 us under the block cap: cast at full width)
+            if V_CAST_SIDE[0]:
+                c.first_specs = [(c.w16, "V", self._stack("V_", (4 * F, c.Ein)))]
             early = [(c.w16, "S", self._style_stack(mode, (4 * F, F))), (c.w16, "U", self._stack("U_", (4 * H, F)))]
         return early, late
 
@@ -880,6 +891,10 @@ class DecoderFactoredLSTM(_DecoderBase):
                 c.A2 = torch.empty(n, 4 * F, dtype=torch.bfloat16, device=dev)
             if X is not None:
                 ops.cast_bf16(X, n, Ein, Ein, c.Xb, Ep, Ep, src_off=r0 * Ein, dst_off=r0 * Ep)
+            ev = c.__dict__.get("ev_first")
+            if ev is not None:                  # the V shadow comes from the side stream
+                torch.cuda.current_stream().wait_event(ev)
+                c.ev_first = None
             ops.gemm_bf16(ops.OP_NT, c.Xb, Vb, n, 4 * F, Ep, Ep, Ep, Cb=c.A1, ldcb=4 * F, bias=bV, a_off=r0 * Ep,
                           cb_off=r0 * 4 * F)
             ev = c.__dict__.get("ev_early")

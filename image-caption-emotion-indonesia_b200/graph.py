@@ -13,6 +13,8 @@ so the first all-reduce still overlaps the reverse-time recurrence and no collec
 
 Only fully teacher-forced steps are captured (teacher_forcing_ratio >= 1): scheduled sampling draws a host
 coin per time step (stylenet/model.py:181) that changes the kernel sequence."""
+import os
+
 import torch
 
 from . import ops
@@ -41,7 +43,12 @@ class GraphedTrainStep:
         self.segments = []          # [(graph, ranges to all-reduce after it | None)]
         if (trainer.world == 1 or getattr(trainer, 'comm', 'nccl') == 'peer') and not force_segmented:
             g = torch.cuda.CUDAGraph()
-            with ops.no_gc_during_capture(), torch.cuda.graph(g):
+            # SN_MAIN_PRIORITY=-1 captures on a high-priority stream (the main chain's kernel nodes inherit it and the
+            # side streams yield the SMs to them).  Measured: the main chain then finishes ~10 us earlier, the weight-
+            # gradient GEMMs and their Adam buckets ~10 us later -- same step time (profiles/README.md), so it is off
+            prio = int(os.environ.get("SN_MAIN_PRIORITY", "0"))
+            cap = torch.cuda.Stream(priority=prio) if prio != 0 else None
+            with ops.no_gc_during_capture(), (torch.cuda.graph(g, stream=cap) if cap is not None else torch.cuda.graph(g)):
                 self.loss, self.stats = self.trainer.step(self.captions, self.lengths, self.features, **self.kw)
             self.segments.append((g, None))
         else:

@@ -211,7 +211,9 @@ class FusedClampAdam:
     @torch.no_grad()
     def step_peer_recv(self, peers, buckets, only=None, skip=None, max_ctas=0):
         """Push form, part 2: wait for the pushes of ``buckets`` (1..4 bucket ids whose gradients are exactly ``only`` minus
-        ``skip``), reduce, clamp + Adam on the owned chunks, parameter all-gather, exit barrier."""
+        ``skip``), reduce, clamp + Adam on the owned chunks, parameter all-gather, exit barrier.  As with ``step_peer``,
+        ``p.grad`` keeps this rank's LOCAL, unclamped gradient afterwards (the reference's clip_gradient clamps in place,
+        stylenet/utils.py:60; the summed, clamped gradient only ever exists in the owner's registers)."""
         a, items = self._peer_items(only, skip)
         self._sync_lr()
         if not items:
