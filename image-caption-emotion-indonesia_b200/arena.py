@@ -51,6 +51,7 @@ class ParamArena:
         self.flat = None
         self.gflat = None
         self.version = 0
+        self.kernel_epoch = 0       # bumped whenever OUR kernels rewrite parameters (torch's ._version does not see them)
         self._sentinels = (listed[0], listed[-1])
         self._epoch = PARAM_EPOCH[0]
 
@@ -141,6 +142,12 @@ class ParamArena:
                     p.grad = gv
                 else:
                     p.grad.add_(fresh[o:o + k].view(p.shape))
+
+    def content_key(self):
+        """Changes whenever the parameter VALUES may have changed: in-place torch ops bump the version counter of the
+        Parameter they touch (or of the flat buffer), the optimizer kernels / graph replays bump ``kernel_epoch``, a
+        re-bind bumps ``version``."""
+        return (self.version, self.kernel_epoch, self.flat._version, sum(p._version for p in self.named.values()))
 
     def grad_ranges(self):
         """Merged flat (offset, length) ranges of parameters whose .grad is an arena view, plus the list

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32) decode_cell_kernel(
     int cell, int H, int R, const float* __restrict__ Wx, int64_t ldwx, int Kx, const float* __restrict__ X, int64_t ldx,
     int group_x, const float* __restrict__ bx, const float* __restrict__ Wh, const float* __restrict__ bh,
     const float* __restrict__ h_prev, const float* __restrict__ c_prev, const int* __restrict__ src_row,
-    float* __restrict__ h_out, float* __restrict__ c_out) {
+    const int* __restrict__ x_rows, float* __restrict__ h_out, float* __restrict__ c_out) {
   __shared__ float zpart[DC_UNITS][2][RMAX][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ul = warp >> 1, half = warp & 1;
@@ -101,6 +101,10 @@ __global__ void __launch_bounds__(SK_WARPS * 32) decode_cell_kernel(
       // x part: row g*H+u of Wx against x group g (factored: U_g on a2_g ; LSTM: W_ih on x)
       const bool vec = ((ldwx & 3) == 0) && ((Kx & 3) == 0) && ((ldx & 3) == 0) && ((group_x & 3) == 0) &&
                        (((reinterpret_cast<uintptr_t>(Wx) | reinterpret_cast<uintptr_t>(X)) & 15) == 0);
+      // (x_rows: row r of the input is X[x_rows[r]] -- the embedding lookup folded into the cell, collapsed chain)
+      const float* xr[RMAX];
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) xr[r] = X + (int64_t)(r < R ? (x_rows ? x_rows[r] : r) : 0) * ldx;
       if (vec) {
 #pragma unroll 2
         for (int k = lane * 4; k < Kx; k += 128) {
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32) decode_cell_kernel(
             if (r < R) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                const float4 x = __ldg(reinterpret_cast<const float4*>(X + (int64_t)r * ldx + g * group_x + k));
+                const float4 x = __ldg(reinterpret_cast<const float4*>(xr[r] + g * group_x + k));
                 acc[r][g] += w[g].x * x.x + w[g].y * x.y + w[g].z * x.z + w[g].w * x.w;
               }
             }
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32) decode_cell_kernel(
           for (int r = 0; r < RMAX; ++r)
             if (r < R) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) acc[r][g] += w[g] * __ldg(X + (int64_t)r * ldx + g * group_x + k);
+              for (int g = 0; g < 4; ++g) acc[r][g] += w[g] * __ldg(xr[r] + g * group_x + k);
             }
         }
       }
@@ -220,8 +224,8 @@ int32_t sn_skinny_linear(const float* W, int64_t ldw, int64_t N, int64_t K, cons
 
 int32_t sn_decode_cell(int32_t cell, int64_t H, int64_t R, const float* Wx, int64_t ldwx, int64_t Kx, const float* X,
                        int64_t ldx, int64_t group_x, const float* bx, const float* Wh, const float* bh,
-                       const float* h_prev, const float* c_prev, const int32_t* src_row, float* h_out, float* c_out,
-                       void* stream) {
+                       const float* h_prev, const float* c_prev, const int32_t* src_row, const int32_t* x_rows,
+                       float* h_out, float* c_out, void* stream) {
   SN_REQUIRE(cell == SN_CELL_FACTORED || cell == SN_CELL_LSTM, "sn_decode_cell: bad cell %d", cell);
   SN_REQUIRE(Wx && X && Wh && h_prev && c_prev && h_out && c_out && H > 0 && R > 0 && Kx > 0, "sn_decode_cell: bad argument");
   SN_REQUIRE(R <= 16, "sn_decode_cell: at most 16 rows (got %lld)", (long long)R);
@@ -229,7 +233,7 @@ int32_t sn_decode_cell(int32_t cell, int64_t H, int64_t R, const float* Wx, int6
   const size_t smem = 0;
   const unsigned grid = (unsigned)((H + DC_UNITS - 1) / DC_UNITS);
   cudaStream_t st = (cudaStream_t)stream;
-#define SN_CELL(RM) decode_cell_kernel<RM><<<grid, SK_WARPS * 32, smem, st>>>(cell, (int)H, (int)R, Wx, ldwx, (int)Kx, X, ldx, (int)group_x, bx, Wh, bh, h_prev, c_prev, src_row, h_out, c_out)
+#define SN_CELL(RM) decode_cell_kernel<RM><<<grid, SK_WARPS * 32, smem, st>>>(cell, (int)H, (int)R, Wx, ldwx, (int)Kx, X, ldx, (int)group_x, bx, Wh, bh, h_prev, c_prev, src_row, x_rows, h_out, c_out)
   if (R <= 4) SN_CELL(4);
   else if (R == 5) SN_CELL(5);
   else if (R <= 8) SN_CELL(8);

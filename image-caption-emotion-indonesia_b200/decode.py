@@ -153,9 +153,9 @@ class BeamState:
             "sn_beam_step")
 
     def results(self):
-        out = self.out_seq.cpu()
-        n = self.out_len.cpu()
-        return [out[i, :int(n[i])].long().unsqueeze(0) for i in range(self.n_img)]
+        pk = torch.cat([self.out_seq, self.out_len.unsqueeze(1)], 1).cpu()        # one device->host copy, one sync
+        L = self.out_seq.shape[1]
+        return [pk[i, :int(pk[i, L])].long().unsqueeze(0) for i in range(self.n_img)]
 
 
 class _DecodeSession:
@@ -286,6 +286,9 @@ class _DecodeSession:
         self.graph = g
 
 
+COLLAPSE_CHAIN = [True]       # few-row decode: collapse the factored chain once per call (DecoderFactoredLSTM._collapse_chain)
+
+
 def _session(dec, n_img, k, mode, start_token, end_token):
     cache = dec.__dict__.setdefault("_decode_sessions", {})
     key = (n_img, k, mode, start_token, end_token, dec.precision)
@@ -318,13 +321,38 @@ def beam_sample(dec, features, start_token, end_token, k, mode, feed_image, sync
         if use_graph is None:
             use_graph = True
 
-        def restart():
+        def restart_eager():
             st.reset()
             sess.h.zero_()
             sess.c.zero_()
             sess.flip = 0
             sess.step_skinny(1, feed_image, device_step=True)       # step 1 is special (image feed, one live row)
+
+        def restart():
+            # reset + step 1 are ~15 small launches: replayed as one graph per feed_image once the session is warm
+            g0 = sess.__dict__.setdefault("graph0", {}).get(bool(feed_image))
+            if g0 is None and use_graph and sess.graph is not None:
+                s0 = torch.cuda.Stream()
+                s0.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s0):
+                    restart_eager()
+                torch.cuda.current_stream().wait_stream(s0)
+                torch.cuda.synchronize()
+                g0 = torch.cuda.CUDAGraph()
+                with ops.no_gc_during_capture(), torch.cuda.graph(g0):
+                    restart_eager()
+                sess.graph0[bool(feed_image)] = g0
+            if g0 is not None:
+                g0.replay()
+                sess.flip = 1
+            else:
+                restart_eager()
         sess.feats.copy_(feats)
+        if COLLAPSE_CHAIN[0] and hasattr(dec, "_collapse_chain"):
+            # inference: U_g S_g V_g of this mode as one matrix per gate, refreshed once per call (the weights may have
+            # been trained since the last one) -- a decode step is then ONE kernel in front of the vocabulary projection
+            for l in range(sess.L):
+                dec._collapse_chain(sess.ctx, mode, l)
         restart()
         if use_graph and sess.graph is None and sess.calls >= 2:
             sess.capture_skinny()                                    # (runs throw-away steps: start over)

@@ -989,13 +989,52 @@ class DecoderFactoredLSTM(_DecoderBase):
         ops.gemm_bf16(ops.OP_NN, dA1b, Vb, N, Ein, 4 * F, 4 * F, Ep, C=dX, ldc=Ein)
         return dX
 
+    def _collapse_chain(self, ctx, mode, layer=0):
+        """Inference only, once per decode call: the factored chain U_g S_g V_g of ``mode`` as ONE matrix per gate,
+        Wc_g = U_g (S_g V_g) [H, Ein], bc_g = U_g (S_g bV_g + bS_g) + bU_g (stylenet/model.py:119-150 is linear in x
+        between the embedding and the gate sums).  ``_small_step`` then runs a decode step as a single kernel.  The
+        result buffers live in ``ctx`` (fixed addresses: the steps are CUDA-graph captured) and are refreshed in place."""
+        if mode not in STYLES:
+            raise ValueError("mode name wrong: %r (expected one of %s)" % (mode, STYLES))
+        H, F = self.hidden_size, self.factored_size
+        Ein = self.arena().named[self._lp(layer) + "V_" + GATES[0] + ".weight"].shape[1]
+        Vc, bV = self._stack("V_", (4 * F, Ein), layer=layer), self._stack("V_", (4 * F,), bias=True, layer=layer)
+        Sc, bS = self._style_stack(mode, (4 * F, F), layer=layer), self._style_stack(mode, (4 * F,), bias=True, layer=layer)
+        Uc, bU = self._stack("U_", (4 * H, F), layer=layer), self._stack("U_", (4 * H,), bias=True, layer=layer)
+        col = ctx.__dict__.setdefault("collapsed", {})
+        ent = col.get(layer)
+        key = (mode, self.arena().content_key())
+        if ent is not None and ent.get("key") == key:
+            return ent                         # same weights as at the last call (evaluation loops): nothing to refresh
+        dev = Vc.device
+        if ent is None or ent["Wc"].shape != (4 * H, Ein):
+            f32 = dict(dtype=torch.float32, device=dev)
+            ent = col[layer] = {"Wc": torch.empty(4 * H, Ein, **f32), "bc": torch.empty(4 * H, **f32),
+                                "SV": torch.empty(4 * F, Ein, **f32), "t": torch.empty(4 * F, **f32)}
+        with torch.no_grad():
+            ops.gemm(ops.OP_NN, Sc, Vc, ent["SV"], F, Ein, F, F, Ein, Ein, batch=4, sA=F * F, sB=F * Ein, sC=F * Ein)
+            ops.gemm(ops.OP_NN, Uc, ent["SV"], ent["Wc"], H, Ein, F, F, Ein, Ein, batch=4, sA=H * F, sB=F * Ein, sC=H * Ein)
+            ops.gemm(ops.OP_NN, Sc, bV, ent["t"], F, 1, F, F, 1, 1, batch=4, sA=F * F, sB=F, sC=F)
+            ent["t"].add_(bS)
+            ops.gemm(ops.OP_NN, Uc, ent["t"], ent["bc"], H, 1, F, F, 1, 1, batch=4, sA=H * F, sB=F, sC=H)
+            ent["bc"].add_(bU)
+        ent["mode"], ent["key"] = mode, key
+        return ent
+
     def _small_step(self, ctx, X, mode, R, h_prev, c_prev, src_row, h_out, c_out, layer=0, x_rows=None):
         """forward_step for R <= ops.SKINNY_MAX_ROWS rows on the matrix-vector kernels (sn_decode.cu): V and S stages as
-        skinny linears, the U stage + W_hh + gates + cell update fused (stylenet/model.py:119-153)."""
+        skinny linears, the U stage + W_hh + gates + cell update fused (stylenet/model.py:119-153); with the chain
+        collapsed for this call (``_collapse_chain``) the whole step is the fused kernel alone."""
         if mode not in STYLES:
             raise ValueError("mode name wrong: %r (expected one of %s)" % (mode, STYLES))
         H, F = self.hidden_size, self.factored_size
         Ein = X.shape[1]
+        ent = ctx.__dict__.get("collapsed", {}).get(layer)
+        if ent is not None and ent.get("mode") == mode and ent["Wc"].shape[1] == Ein:
+            Whh, bhh = self._recurrent_weights(layer)
+            ops.decode_cell(self.cell, H, R, ent["Wc"], Ein, X, 0, ent["bc"], Whh, bhh, h_prev, c_prev, src_row, h_out,
+                            c_out, x_rows=x_rows)
+            return
         a1, a2 = ctx.__dict__.get("sk_a1"), ctx.__dict__.get("sk_a2")
         if a1 is None or a1.shape[0] < R:
             a1 = ctx.sk_a1 = torch.empty(max(R, ops.SKINNY_MAX_ROWS), 4 * F, dtype=torch.float32, device=X.device)

@@ -99,6 +99,7 @@ class GraphedTrainStep:
             if i == last and last > 0:
                 tr.sync.wait()         # Adam waits for both all-reduces
             g.replay()
+            tr.decoder.arena().kernel_epoch += 1      # the replay rewrote the parameters behind torch's back
             if ranges:
                 tr.sync.launch(tr.decoder.arena().gflat, ranges)
         return self.loss, self.stats

@@ -683,10 +683,11 @@ def skinny_linear(W, X, out, R, bias=None, group_n=0, group_x=0, K=None, x_rows=
     return out
 
 
-def decode_cell(cell, H, R, Wx, Kx, X, group_x, bx, Wh, bh, h_prev, c_prev, src_row, h_out, c_out):
+def decode_cell(cell, H, R, Wx, Kx, X, group_x, bx, Wh, bh, h_prev, c_prev, src_row, h_out, c_out, x_rows=None):
     check(lib().sn_decode_cell(cell, H, R, _ptr(_req(Wx)), Wx.stride(0), Kx, _ptr(_req(X)), X.stride(0), group_x,
                                _ptr(bx), _ptr(_req(Wh)), _ptr(bh), _ptr(_req(h_prev)), _ptr(_req(c_prev)),
-                               _ptr(src_row), _ptr(_req(h_out)), _ptr(_req(c_out)), _stream()), "sn_decode_cell")
+                               _ptr(src_row), _ptr(x_rows), _ptr(_req(h_out)), _ptr(_req(c_out)), _stream()),
+          "sn_decode_cell")
 
 
 def gate_wait(flag3, timeout_us=300):

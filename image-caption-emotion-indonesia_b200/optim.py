@@ -149,6 +149,7 @@ class FusedClampAdam:
         b1, b2 = self.betas
         ranges = [(off, n) for off, n, _ in items]
         idx = [self.index[name] for _, _, name in items]
+        a.kernel_epoch += 1
         ops.adam_clamp_dev(a.flat, a.gflat, self.m, self.v, ranges, idx, self.steps_dev, self.lr_dev, self.coef_ws,
                            b1, b2, self.eps, self.grad_clip)
         # parameters outside the arena (foreign gradient tensors, extra params): same kernel, one range each
@@ -179,6 +180,7 @@ class FusedClampAdam:
         idx = [self.index[name] for _, _, name in items]
         if not ranges:
             return          # every bucket was exchanged early (the same on every rank): no empty barrier-only call
+        a.kernel_epoch += 1
         ops.dp_adam_fused(peers.world, peers.rank, peers.grad_ptrs, peers.param_ptrs, peers.pads(bucket), self.m, self.v,
                           ranges, idx, self.steps_dev, self.lr_dev, self.coef_ws, self.betas[0], self.betas[1],
                           self.eps, self.grad_clip)
@@ -223,6 +225,7 @@ class FusedClampAdam:
         ranges = [(off, n) for off, n, _ in items]
         idx = [self.index[name] for _, _, name in items]
         mine = [peers.pads(b)[peers.rank] for b in buckets]
+        a.kernel_epoch += 1
         ops.dp_adam_recv(peers.world, peers.rank, a.gflat, peers.param_ptrs, peers.recv, peers.slot_elems,
                          peers.elem_size, peers.pads(buckets[0]), mine, self.m, self.v, ranges, idx, self.steps_dev,
                          self.lr_dev, self.coef_ws, self.betas[0], self.betas[1], self.eps, self.grad_clip,

@@ -417,7 +417,9 @@ int32_t sn_split_limbs_rows(const float* src, int64_t G, int64_t K, int64_t C, i
  * sn_decode_cell: z_g = Wx[g*H+u,:Kx] . x_g[r] + bx + Wh[g*H+u,:] . h_prev[src_row[r]] + bh, gates, c', h' for
  *   every unit u and row r; x_g = X[r, g*group_x : +Kx] (group_x = 0: the same x for all gates, LSTMCell).
  *   src_row (may be NULL) re-orders the incoming state per row (beam bookkeeping, model.py:275-279): h_out / c_out
- *   must not alias h_prev / c_prev. */
+ *   must not alias h_prev / c_prev.  x_rows (may be NULL): row r of the input is X[x_rows[r]] -- with the factored
+ *   chain collapsed once per decode call (Wx = U_g S_g V_g, bx = U_g(S_g bV_g + bS_g) + bU_g) the embedding lookup,
+ *   the three projection stages and the cell are this one kernel. */
 int32_t sn_skinny_max_rows(void);
 int32_t sn_skinny_linear(const float* W, int64_t ldw, int64_t N, int64_t K, const float* X, int64_t ldx,
                          int64_t R, int64_t group_n, int64_t group_x, const float* bias, float* out,
@@ -425,7 +427,7 @@ int32_t sn_skinny_linear(const float* W, int64_t ldw, int64_t N, int64_t K, cons
 int32_t sn_decode_cell(int32_t cell, int64_t H, int64_t R, const float* Wx, int64_t ldwx, int64_t Kx,
                        const float* X, int64_t ldx, int64_t group_x, const float* bx, const float* Wh,
                        const float* bh, const float* h_prev, const float* c_prev, const int32_t* src_row,
-                       float* h_out, float* c_out, void* stream);
+                       const int32_t* x_rows, float* h_out, float* c_out, void* stream);
 
 /* ---- encoder tail -> decoder hand-off ---------------------------------------------------
  * sn_pool_nhwc_fwd: AdaptiveAvgPool2d((S,S)) + permute(0,2,3,1) of the trunk output (stylenet/model_att.py:24-28),

@@ -316,3 +316,47 @@ def test_graph_replay_follows_learning_rate_changes():
     torch.cuda.synchronize()
     for (n, p), (_, q) in zip(d1.named_parameters(), d2.named_parameters()):
         assert rel_l2(q.detach().cpu(), p.detach().cpu()) < 1e-5, n
+
+
+@pytest.mark.gpu
+def test_collapsed_chain_follows_weight_updates():
+    """Few-row decode collapses U S V once per call and caches it while the weights are unchanged: an optimizer step
+    (our kernels), an in-place torch update and a load_state_dict must each refresh it -- sample() after the change ==
+    sample() of a fresh decoder holding the same weights."""
+    import icei_b200 as sn
+    from oracle import port
+    V, E, H, F = 300, 28, 64, 64
+    torch.manual_seed(0)
+    dec = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0)
+    port.sharpen_for_decode(dec)
+    dec = dec.cuda()
+    feats = torch.randn(3, E, generator=torch.Generator().manual_seed(2)).cuda()
+    cap, lens, f2 = port.synthetic_batch(8, 7, V, E=E, ragged=True, seed=4)
+    opt = sn.FusedClampAdam(dec, lr=5e-2)
+
+    def fresh_ids():
+        d2 = sn.DecoderFactoredLSTM(E, H, F, V, 1, dropout=0.0).cuda().eval()
+        d2.load_state_dict(dec.state_dict())
+        return [d2.sample(feats[i:i + 1], 1, 2, k=3, mode="happy", feed_image=True) for i in range(3)]
+
+    def ids():
+        dec.eval()
+        return [dec.sample(feats[i:i + 1], 1, 2, k=3, mode="happy", feed_image=True) for i in range(3)]
+
+    for change in ("none", "adam", "torch", "load"):
+        if change == "adam":
+            dec.train()
+            dec.zero_grad()
+            dec.forward_loss(cap.cuda(), lens, f2.cuda(), mode="happy")
+            opt.step()
+        elif change == "torch":
+            with torch.no_grad():
+                dec.U_i.weight.mul_(-1.5)
+        elif change == "load":
+            sd = {k: (v * 0.5 if k.startswith("S_happy") else v) for k, v in dec.state_dict().items()}
+            dec.load_state_dict(sd)
+        for _ in range(3):                       # (the 3rd call of a session replays its captured graphs)
+            got = ids()
+        want = fresh_ids()
+        for a, b in zip(got, want):
+            assert torch.equal(a.cpu(), b.cpu()), change
