@@ -437,17 +437,23 @@ def dp_parity_check(dev, rank, world):
             return d, sn.DataParallelTrainer(d, sn.FusedClampAdam(d, lr=5e-4), comm=None)
         one, _ = make()
         opt1 = sn.FusedClampAdam(one, lr=5e-4)
+        loss1, lossN = [], []
         for _ in range(3):
             one.zero_grad()
             for p in one.parameters():
                 p.grad = None
-            one.forward_loss(cap.to(dev), lens, feats.to(dev), mode="happy")
+            l1, _ = one.forward_loss(cap.to(dev), lens, feats.to(dev), mode="happy")
+            loss1.append(l1.detach().reshape(1).clone())
             opt1.step()
         dec, tr = make()
         idx, my_lens = sn.shard_lengths(lens, world, rank)
         for _ in range(3):
-            tr.step(cap[idx].to(dev), my_lens, feats[idx].to(dev), n_global=n_global, mode="happy")
+            lN, _ = tr.step(cap[idx].to(dev), my_lens, feats[idx].to(dev), n_global=n_global, mode="happy")
+            lN = lN.detach().reshape(1).clone()
+            dist.all_reduce(lN)                 # every rank holds its shard's share of the token-mean loss
+            lossN.append(lN)
         torch.cuda.synchronize()
+        loss_rel = max(abs(float(a) - float(b)) / max(abs(float(b)), 1e-30) for a, b in zip(lossN, loss1))
         worst = torch.zeros(1, device=dev)
         same = torch.ones(1, device=dev)
         for (n, p), (_, q) in zip(dec.named_parameters(), one.named_parameters()):
@@ -462,12 +468,15 @@ def dp_parity_check(dev, rank, world):
         if tr.comm == "peer":
             transport = "pull (peer loads, fp32)" if _dp.PEER_FORM[0] != "push" else \
                 ("push, %s gradients" % ("bf16" if tr.peers.elem_size == 2 else "fp32"))
-        return {"max_rel_param_diff_vs_1gpu": float(worst.item()), "ranks_bit_identical": bool(same.item() == 1.0),
-                "comm": tr.comm, "exchange": transport}
+        return {"max_rel_loss_diff_vs_1gpu": loss_rel, "max_rel_param_diff_vs_1gpu": float(worst.item()),
+                "ranks_bit_identical": bool(same.item() == 1.0), "comm": tr.comm, "exchange": transport}
     r32 = run("fp32", 1000, 44, 128, 72)
     r16 = run("bf16", 1000, 40, 128, 64)
     out = dict(r32, steps=3, global_batch=12 * world,
-               what="fp32 mode, ragged global batch sharded over the ranks, 3 steps vs the same steps on 1 GPU")
+               what="fp32 mode, ragged global batch sharded over the ranks, 3 steps vs the same steps on 1 GPU: loss of "
+                    "every step (steps 2 and 3 see the updated weights) and the parameters afterwards.  The parameter "
+                    "figure is dominated by elements whose summed gradient is ~0: the first Adam steps move them by "
+                    "+-lr whatever the magnitude, so a last-bit difference in the sum becomes a 2*lr difference")
     out["bf16_mode"] = dict(r16, what="the same in bf16 mode (the headline's arithmetic; tolerance of the mode 2e-2): "
                                       "operand roundings are per element, the differences are accumulation order + the "
                                       "gradient transport dtype")
