@@ -226,6 +226,8 @@ class ClockSampler:
 
     def start(self):
         try:
+            if os.environ.get("SN_BENCH_SAMPLER", "nvml") != "nvml":
+                raise RuntimeError("nvidia-smi sampler requested")
             self.nvml = self._nvml_open()
             self.source = "nvml"
             self.t = threading.Thread(target=self._nvml_loop, daemon=True)

@@ -182,13 +182,17 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restric
 // K7: clamp + Adam, torch.optim.Adam op order (see sn100.h)
 // ------------------------------------------------------------------------------------------
 struct AdamRanges {
+  // passed BY VALUE to every optimizer / exchange kernel: kept under the classic 4 KB kernel-parameter limit (28 bytes per
+  // range) -- with 36-byte entries the 128-range struct was 5.5 KB and the configs[1] step got 17 us slower (8 launches)
   static constexpr int MAX = 128;
-  int64_t off[MAX], len[MAX];
+  int64_t off[MAX];
+  int32_t len[MAX];
   float step_size[MAX], bc2_sqrt[MAX];
   int step_idx[MAX];              // device-step mode: index into steps_dev
-  int64_t chunk_start[MAX + 1];   // prefix of per-range chunk counts
+  int32_t chunk_start[MAX + 1];   // prefix of per-range chunk counts
   int n;
 };
+static_assert(sizeof(AdamRanges) <= 3700, "AdamRanges must leave room for the other kernel parameters below 4 KB");
 
 // device-step mode: bump the step counter of every range's parameter and derive the bias-corrected
 // coefficients exactly like torch.optim.Adam does on the host (double precision)
@@ -206,6 +210,7 @@ __global__ void adam_prepare_kernel(AdamRanges R, int32_t* __restrict__ steps, c
   coef[2 * R.step_idx[r] + 1] = (float)sqrt(bc2);
 }
 constexpr int ADAM_CHUNK = 4096;   // elements per CTA-iteration
+constexpr int64_t ADAM_MAX_LEN = (1LL << 31) - 2 * ADAM_CHUNK;      // a range's length is an int32 in AdamRanges
 
 __global__ void __launch_bounds__(256) adam_clamp_kernel(float* __restrict__ p, float* __restrict__ g,
                                                          float* __restrict__ m, float* __restrict__ v,
@@ -678,8 +683,8 @@ int32_t sn_adam_clamp(float* p, float* g, float* m, float* v, int32_t n_ranges, 
     R.chunk_start[0] = 0;
     while (done < n_ranges && R.n < AdamRanges::MAX) {
       int64_t off = ranges[2 * done], len = ranges[2 * done + 1];
-      SN_REQUIRE(off >= 0 && len >= 0, "sn_adam_clamp: bad range %d", done);
-      R.off[R.n] = off; R.len[R.n] = len;
+      SN_REQUIRE(off >= 0 && len >= 0 && len < ADAM_MAX_LEN, "sn_adam_clamp: bad range %d", done);
+      R.off[R.n] = off; R.len[R.n] = (int32_t)len;
       R.step_size[R.n] = step_size[done]; R.bc2_sqrt[R.n] = bc2_sqrt[done];
       R.chunk_start[R.n + 1] = R.chunk_start[R.n] + (len + ADAM_CHUNK - 1) / ADAM_CHUNK;
       ++R.n; ++done;
@@ -705,9 +710,9 @@ int32_t sn_adam_clamp_dev(float* p, float* g, float* m, float* v, int32_t n_rang
   R.n = n_ranges;
   R.chunk_start[0] = 0;
   for (int i = 0; i < n_ranges; ++i) {
-    R.off[i] = ranges[2 * i]; R.len[i] = ranges[2 * i + 1]; R.step_idx[i] = step_idx[i];
+    SN_REQUIRE(ranges[2 * i] >= 0 && ranges[2 * i + 1] >= 0 && ranges[2 * i + 1] < ADAM_MAX_LEN, "sn_adam_clamp_dev: bad range %d", i);
+    R.off[i] = ranges[2 * i]; R.len[i] = (int32_t)ranges[2 * i + 1]; R.step_idx[i] = step_idx[i];
     R.step_size[i] = 0.f; R.bc2_sqrt[i] = 1.f;
-    SN_REQUIRE(R.off[i] >= 0 && R.len[i] >= 0, "sn_adam_clamp_dev: bad range %d", i);
     R.chunk_start[i + 1] = R.chunk_start[i] + (R.len[i] + ADAM_CHUNK - 1) / ADAM_CHUNK;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -753,9 +758,9 @@ int32_t sn_dp_adam_fused(int32_t world, int32_t rank, void* const* grad_ptrs, vo
   R.n = n_ranges;
   R.chunk_start[0] = 0;
   for (int i = 0; i < n_ranges; ++i) {
-    R.off[i] = ranges[2 * i]; R.len[i] = ranges[2 * i + 1]; R.step_idx[i] = step_idx[i];
+    SN_REQUIRE(ranges[2 * i] >= 0 && ranges[2 * i + 1] >= 0 && ranges[2 * i + 1] < ADAM_MAX_LEN, "sn_dp_adam_fused: bad range %d", i);
+    R.off[i] = ranges[2 * i]; R.len[i] = (int32_t)ranges[2 * i + 1]; R.step_idx[i] = step_idx[i];
     R.step_size[i] = 0.f; R.bc2_sqrt[i] = 1.f;
-    SN_REQUIRE(R.off[i] >= 0 && R.len[i] >= 0, "sn_dp_adam_fused: bad range %d", i);
     // chunks on the absolute ADAM_CHUNK grid of the arena (ownership must not depend on the active set, see the kernel)
     R.chunk_start[i + 1] = R.chunk_start[i] +
         (R.len[i] > 0 ? (R.off[i] + R.len[i] - 1) / ADAM_CHUNK - R.off[i] / ADAM_CHUNK + 1 : 0);
@@ -788,9 +793,9 @@ static int32_t dp_fill_ranges(AdamRanges& R, int32_t n_ranges, const int64_t* ra
   R.n = n_ranges;
   R.chunk_start[0] = 0;
   for (int i = 0; i < n_ranges; ++i) {
-    R.off[i] = ranges[2 * i]; R.len[i] = ranges[2 * i + 1]; R.step_idx[i] = step_idx ? step_idx[i] : 0;
+    SN_REQUIRE(ranges[2 * i] >= 0 && ranges[2 * i + 1] >= 0 && ranges[2 * i + 1] < ADAM_MAX_LEN, "%s: bad range %d", who, i);
+    R.off[i] = ranges[2 * i]; R.len[i] = (int32_t)ranges[2 * i + 1]; R.step_idx[i] = step_idx ? step_idx[i] : 0;
     R.step_size[i] = 0.f; R.bc2_sqrt[i] = 1.f;
-    SN_REQUIRE(R.off[i] >= 0 && R.len[i] >= 0, "%s: bad range %d", who, i);
     R.chunk_start[i + 1] = R.chunk_start[i] +
         (R.len[i] > 0 ? (R.off[i] + R.len[i] - 1) / ADAM_CHUNK - R.off[i] / ADAM_CHUNK + 1 : 0);
   }

@@ -273,6 +273,8 @@ class _DecoderBase(nn.Module):
             first = c.__dict__.pop("first_specs", None)
             if first:
                 c.ev_first = self._shadows_async(first, max_blocks=0)
+            second = c.__dict__.pop("second_specs", None)
+            c.ev_second = self._shadows_async(second, max_blocks=0) if second else None
             if early:
                 c.ev_early = self._shadows_async(early)
             if late:
@@ -838,8 +840,13 @@ class DecoderFactoredLSTM(_DecoderBase):
         if mode in STYLES:
             # (V's K = 300 -> 304 padded cast is the scalar kernel, 39 us under the block cap: cast at full width)
             if V_CAST_SIDE[0]:
+                # V and S feed the first two GEMMs of the critical chain: full width, one event each (S must not wait for
+                # U's throttled cast: that left a 7 us bubble between the V and the S stage)
                 c.first_specs = [(c.w16, "V", self._stack("V_", (4 * F, c.Ein)))]
-            early = [(c.w16, "S", self._style_stack(mode, (4 * F, F))), (c.w16, "U", self._stack("U_", (4 * H, F)))]
+                c.second_specs = [(c.w16, "S", self._style_stack(mode, (4 * F, F)))]
+                early = [(c.w16, "U", self._stack("U_", (4 * H, F)))]
+            else:
+                early = [(c.w16, "S", self._style_stack(mode, (4 * F, F))), (c.w16, "U", self._stack("U_", (4 * H, F)))]
         return early, late
 
     def _recurrent_weights(self, layer=0):
@@ -897,12 +904,19 @@ class DecoderFactoredLSTM(_DecoderBase):
                 c.ev_first = None
             ops.gemm_bf16(ops.OP_NT, c.Xb, Vb, n, 4 * F, Ep, Ep, Ep, Cb=c.A1, ldcb=4 * F, bias=bV, a_off=r0 * Ep,
                           cb_off=r0 * 4 * F)
+            ev2 = c.__dict__.get("ev_second")
             ev = c.__dict__.get("ev_early")
-            if ev is not None:                  # the S / U shadows come from the side stream
+            if ev2 is not None:                 # the S shadow has its own event, U's is awaited in front of the U stage
+                torch.cuda.current_stream().wait_event(ev2)
+                c.ev_second = None
+            elif ev is not None:                # the S / U shadows come from the side stream
                 torch.cuda.current_stream().wait_event(ev)
-                c.ev_early = None
+                c.ev_early = ev = None
             ops.gemm_bf16(ops.OP_NT, c.A1, Sb, n, F, F, 4 * F, Fp, Cb=c.A2, ldcb=4 * F, bias=bS, batch=4, sA=F,
                           sB=F * Fp, sCb=F, sBias=F, a_off=r0 * 4 * F, cb_off=r0 * 4 * F)
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+                c.ev_early = None
             ops.gemm_bf16(ops.OP_NT, c.A2, Ub, n, H, F, 4 * F, Fp, C=c.XP, ldc=4 * H, bias=bU, batch=4, sA=F,
                           sB=H * Fp, sC=H, sBias=H, a_off=r0 * 4 * F, c_off=r0 * 4 * H)
             return
