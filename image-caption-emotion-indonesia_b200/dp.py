@@ -107,7 +107,7 @@ EARLY_PEER_EXCHANGE = [True]     # split the peer-fused exchange+Adam: vocabular
 PEER_FORM = [os.environ.get("SN_DP_FORM", "push")]     # "push": sn_dp_push + sn_dp_adam_recv; "pull": sn_dp_adam_fused (peer loads)
 BG_PUSH_SMS = [int(os.environ.get("SN_DP_BG_PUSH_SMS", "16"))]     # grid cap of a push that runs under the backward (0 = whole GPU)
 BG_RECV_CTAS = [int(os.environ.get("SN_DP_BG_RECV_CTAS", "0"))]    # same for its receive side (512-thread CTAs)
-BG_WU = [os.environ.get("SN_DP_BG_WU", "1") == "1"]              # exchange the W_hh / U bucket in the background too
+BG_WU = [os.environ.get("SN_DP_BG_WU", "0") == "1"]              # exchange the W_hh / U bucket in the background too
 PEER_BUCKETS = [False]           # also exchange the W_hh/U, S/V and embedding buckets as soon as they are final (slower: see step())
 
 
