@@ -573,8 +573,19 @@ def dp_adam_fused(world, rank, grad_ptrs, param_ptrs, pad_ptrs, m, v, ranges, st
 DP_MAX_RANGES = 128      # AdamRanges::MAX (sn_elementwise.cu)
 
 
+def merge_adjacent(ranges):
+    """[(offset, length)] sorted with touching neighbours merged."""
+    merged = []
+    for off, n in sorted(ranges):
+        if merged and merged[-1][0] + merged[-1][1] == off:
+            merged[-1] = (merged[-1][0], merged[-1][1] + n)
+        else:
+            merged.append((off, n))
+    return merged
+
+
 def dp_slot_elems(arena_elems, world):
-    return int(lib().sn_dp_slot_elems(int(arena_elems), int(world)))
+    return int(_lib.load().sn_dp_slot_elems(int(arena_elems), int(world)))      # host arithmetic: no device needed
 
 
 def _ranges_c(ranges, step_idx=None):
@@ -590,13 +601,7 @@ def _ranges_c(ranges, step_idx=None):
 
 def dp_push(world, rank, grad, recv_ptrs, slot_elems, elem_size, pad_ptrs, ranges, max_ctas=0):
     """Push-form exchange, part 1 (sn_dp_push): non-blocking send of my gradients of foreign chunks + ARRIVE flags."""
-    # adjacent ranges travel as one (the push has no per-parameter state)
-    merged = []
-    for off, n in sorted(ranges):
-        if merged and merged[-1][0] + merged[-1][1] == off:
-            merged[-1] = (merged[-1][0], merged[-1][1] + n)
-        else:
-            merged.append((off, n))
+    merged = merge_adjacent(ranges)      # adjacent ranges travel as one (the push has no per-parameter state)
     if len(merged) > DP_MAX_RANGES:
         raise RuntimeError("dp_push: more than %d ranges in one bucket (each call raises the bucket's flags once)" % DP_MAX_RANGES)
     R, _ = _ranges_c(merged)

@@ -321,3 +321,42 @@ def test_encoder_signatures_and_state_dict_names_match_reference():
         enc(torch.randn(2, 3, 8, 8))            # CPU tensors: the tail has no CPU fallback
     att = sn.EncoderCNNAtt(backbone=nn.Sequential(nn.Conv2d(3, 8, 3)))
     assert att.encoded_image_size == 14 and list(att.state_dict()) == ["resnet.0.weight", "resnet.0.bias"]
+
+
+def test_dp_receive_slots_and_range_merging():
+    """Host side of the push-form exchange: a rank's receive slot holds its share of the arena's 4096-element chunks
+    (sn_dp_slot_elems is plain host arithmetic: callable without a GPU); ranges of one bucket are merged when they touch."""
+    from icei_b200 import ops
+    for elems, world in [(1, 1), (4096, 2), (4097, 2), (12_400_000, 8), (73_400_000, 8), (5, 3)]:
+        chunks = -(-elems // 4096)
+        want = -(-chunks // world) * 4096
+        assert ops.dp_slot_elems(elems, world) == want
+        # every owned chunk `aid` (aid % world == rank) has a place: slot index aid // world < slot chunks
+        assert (chunks - 1) // world < want // 4096
+    assert ops.dp_slot_elems(-1, 2) == -1 and ops.dp_slot_elems(10, 0) == -1
+    assert ops.merge_adjacent([(100, 20), (0, 50), (50, 50), (130, 5)]) == [(0, 120), (130, 5)]
+    assert ops.merge_adjacent([]) == []
+
+
+def test_arena_content_key_sees_every_kind_of_weight_change():
+    """The few-row decode caches the collapsed U S V chain on ParamArena.content_key(): it must change on in-place torch
+    updates of a Parameter, on load_state_dict, on a re-bind, and when the optimizer kernels / graph replays bump
+    kernel_epoch -- and stay put otherwise."""
+    import icei_b200 as sn
+    torch.manual_seed(0)
+    dec = sn.DecoderFactoredLSTM(12, 16, 8, 30, 1, dropout=0.0)
+    a = dec.arena()
+    k0 = a.content_key()
+    assert a.content_key() == k0
+    with torch.no_grad():
+        dec.U_i.weight.mul_(2.0)
+    k1 = dec.arena().content_key()
+    assert k1 != k0
+    dec.load_state_dict({k: v.clone() for k, v in dec.state_dict().items()})
+    k2 = dec.arena().content_key()
+    assert k2 != k1
+    dec.arena().kernel_epoch += 1
+    k3 = dec.arena().content_key()
+    assert k3 != k2
+    dec.C.weight = torch.nn.Parameter(dec.C.weight.detach().clone())
+    assert dec.arena().content_key() != k3
